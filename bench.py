@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — mel frames/sec of the fused log-mel hot path on N B200s, next to the CPU restatement of the reference.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4shard|cfg3]
+
+One "step" = one pass of the hot path over one batch of synthetic 16 kHz PCM (BASELINE.json configs[1]:
+1024 clips x 10 s, Whisper 80-mel, fft 400 / hop 160).  With N > 1 (launched under torchrun, one rank per GPU)
+every rank processes its own shard of that size — clips are independent, there is no data-path collective —
+and `value` = frames of all ranks / max-over-ranks device time ("scaling": "weak").
+
+  value      device-resident throughput (CUDA events on the launch stream, inputs already in HBM, 655 MB > L2)
+  e2e        same metric through the host-buffer C-ABI call (pinned host PCM -> H2D -> kernel -> D2H) per step
+  roofline   algorithmic bytes per launch (4*S + 4*80*F per clip) / measured launch time vs
+             MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle/ C restatement of src/stft.rs + src/mel.rs on the box's host cores, bounded sample
+
+`--impl reference` times that same CPU restatement (the reference's Rust cannot be built in this image: no
+cargo/rustc) with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (clips per GPU, samples per clip, frontend, description)
+    "cfg2": (1024, 160000, "whisper", "BASELINE configs[1]: 1024 x 10 s @16 kHz, Whisper 80-mel fft400 hop160"),
+    "cfg4shard": (1024, 480000, "whisper", "BASELINE configs[3] per-GPU shard: 1024 x 30 s @16 kHz, Whisper 80-mel"),
+    "cfg3": (1024, 160000, "kaldi", "BASELINE configs[2]: 1024 x 10 s @16 kHz, Kaldi 80-bin fbank + CMN"),
+}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_batch_torch(torch, n_clips, n_samples, device, rank):
+    """Device-side synthetic PCM of SURVEY §8d's recipe (4 detuned tones + noise, every 8th clip silent for 1 s)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + rank)
+    t = torch.arange(n_samples, device=device, dtype=torch.float32) / 16000.0
+    x = torch.empty((n_clips, n_samples), device=device, dtype=torch.float32)
+    blk = 128
+    for c0 in range(0, n_clips, blk):
+        nb = min(blk, n_clips - c0)
+        acc = 0.01 * torch.randn((nb, n_samples), device=device, generator=g)
+        for f0, amp in ((220.0, 0.6), (440.0, 0.25), (880.0, 0.10), (1760.0, 0.05)):
+            det = 1.0 + (torch.rand((nb, 1), device=device, generator=g) - 0.5) * 0.1
+            ph = torch.rand((nb, 1), device=device, generator=g) * 6.283185307
+            acc += amp * torch.sin(6.283185307 * f0 * det * t[None, :] + ph)
+        x[c0:c0 + nb] = acc
+    x[7::8, :16000] = 0.0
+    return x
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle's C restatement, all host threads, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import melspec_oracle as o
+    import oracle_c as oc
+    clips, n_samples, frontend, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample_clips = max(cores, 32)
+    pcm = np.stack([o.synth_clip(i, n_samples) for i in range(min(sample_clips, 16))])
+    pcm = np.ascontiguousarray(np.tile(pcm, (sample_clips // pcm.shape[0] + 1, 1))[:sample_clips])
+    fn = (lambda: oc.whisper_batch(pcm, threads=cores)) if frontend == "whisper" else (lambda: oc.kaldi_batch(pcm, threads=cores))
+    for _ in range(max(args.warmup, 1)):
+        out = fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = fn()
+    dt = (time.perf_counter() - t0) / args.steps
+    frames = out.shape[0] * out.shape[1]
+    v = frames / dt
+    sample = f"{sample_clips} clips x {n_samples / 16000:.0f} s per step ({frames} frames), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "mel frames/sec (Whisper 80-mel, 16 kHz)", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "reference Rust cannot be built here (no cargo); C f64 restatement of "
+                   "src/stft.rs+src/mel.rs from oracle/ timed on host cores"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline(workload):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import melspec_oracle as o
+    import oracle_c as oc
+    clips, n_samples, frontend, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    nclips = max(cores * 2, 16)
+    base = np.stack([o.synth_clip(i, n_samples) for i in range(8)])
+    pcm = np.ascontiguousarray(np.tile(base, (nclips // 8 + 1, 1))[:nclips])
+    fn = (lambda th: oc.whisper_batch(pcm, threads=th)) if frontend == "whisper" else (lambda th: oc.kaldi_batch(pcm, threads=th))
+    fn(cores)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        out = fn(cores)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > 6.0 or reps >= 50:
+            break
+    v_all = reps * out.shape[0] * out.shape[1] / dt
+    one = pcm[:max(2, nclips // cores)]
+    t0 = time.perf_counter()
+    o1 = oc.whisper_batch(one, threads=1) if frontend == "whisper" else oc.kaldi_batch(one, threads=1)
+    v_one = o1.shape[0] * o1.shape[1] / (time.perf_counter() - t0)
+    return {"value": v_all, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{nclips} clips x {n_samples / 16000:.0f} s x {reps} reps on {cores} threads "
+                      f"(single thread: {v_one:.0f} frames/s)", "single_thread_value": v_one}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mel_spec_b200 as ms
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    ms.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    clips, n_samples, frontend, desc = WORKLOADS[args.workload]
+    if frontend == "whisper":
+        h = ms.CudaMelSpectrogram(400, 160, 16000.0, 80, device=local_rank)
+    else:
+        h = ms.Fbank(ms.FbankConfig(), device=local_rank)
+    n_mels = 80
+    F = h.num_frames(n_samples)
+    x = synth_batch_torch(torch, clips, n_samples, dev, rank)
+    out = torch.empty((clips, F, n_mels), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        h.compute_device(x, clips, n_samples, n_samples, out, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = h.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for i in range(args.steps):
+            step()
+            evs[i + 1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = h.launch_count() - l0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tt.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H inside the region)
+    e2e_steps = max(1, args.e2e_steps)
+    hx = torch.empty((clips, n_samples), dtype=torch.float32, pin_memory=True)
+    hx.copy_(x)
+    hout = torch.empty((clips, F, n_mels), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+    h.compute_host_raw(hx.data_ptr(), clips, n_samples, n_samples, hout.data_ptr())   # warm-up (allocates staging)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h.compute_host_raw(hx.data_ptr(), clips, n_samples, n_samples, hout.data_ptr())
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    same = bool(torch.equal(hout.to(dev), out))
+
+    if rank == 0:
+        frames_rank = clips * F
+        ms_per_step = total_ms_max / args.steps
+        value = world * frames_rank / (ms_per_step * 1e-3)
+        algo_bytes = clips * (4 * n_samples + 4 * n_mels * F)
+        kern_ms = total_ms / args.steps                       # rank 0's own average launch duration
+        peak, peak_kind = measured_peak_gbs()
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "mel frames/sec (Whisper 80-mel, 16 kHz)" if frontend == "whisper" else "fbank frames/sec (Kaldi 80-bin, 16 kHz)",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "clips_per_gpu": clips, "samples_per_clip": n_samples, "frames_per_clip": F,
+                       "l2_policy": "inputs larger than L2 (%.0f MB PCM per launch, no flush)" % (clips * n_samples * 4 / 1e6),
+                       "ms_per_step_median_rank0": per[len(per) // 2], "ms_per_step_min_rank0": per[0]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": kern_ms},
+            "e2e": {"value": world * frames_rank / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": clips * n_samples * 4,
+                    "d2h_bytes_per_step": clips * F * n_mels * 4, "ms_per_step": e2e_s * 1e3, "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

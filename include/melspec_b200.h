@@ -1,0 +1,165 @@
+/*
+ * melspec_b200 — C ABI of the B200-native log-mel frontend.
+ *
+ * This is the drop-in boundary for the STFT->mel hot path of wavey-ai/mel-spec: it replaces the private
+ * `mod ffi` of the reference's CUDA backend (reference src/cuda.rs:161-480; the `unsafe extern "C"` block at
+ * src/cuda.rs:185-220 with its 12 CUDA-runtime/cuFFT symbols and `launch_mel_kernel`, C side
+ * src/cuda_kernels.cu:49-66) and sits behind
+ *   - CudaMelSpectrogram::{new, compute_mel_spectrogram, max_frames_per_batch}   (src/cuda.rs:38-101,150-155)
+ *   - Spectrogram::compute_mel_spectrogram_cpu's batch semantics                  (src/stft.rs:119-138)
+ *   - Fbank::{new, compute}                                                       (src/fbank.rs:94-132,141-236)
+ *   - RingBuffer::maybe_mel / Spectrogram::add streaming semantics                (src/rb.rs:86-121, src/stft.rs:48-86)
+ *
+ * Plain C: opaque handles, raw pointers and sizes, int32 status codes.  No torch / STL types cross this line.
+ * All entry points are non-throwing.  A handle is single-threaded (the reference's struct is !Send/!Sync,
+ * src/cuda.rs:27-36); different handles / devices may be used concurrently.  There is no CPU fallback: without
+ * a CUDA device `melspec_create` fails with MELSPEC_ERR_NO_DEVICE (the reference's CudaError::Unavailable,
+ * src/cuda.rs:10-25).
+ */
+#ifndef MELSPEC_B200_H_
+#define MELSPEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MELSPEC_B200_ABI_VERSION 1
+
+/* ---- status codes (0 = success, like cudaError_t in src/cuda_kernels.cu:56-65) ---- */
+enum {
+    MELSPEC_OK = 0,
+    MELSPEC_ERR_INVALID_CONFIG = 1, /* zero sizes (src/cuda.rs:45-49), unsupported fft size, ...           */
+    MELSPEC_ERR_NO_DEVICE = 2,      /* CudaError::Unavailable                                              */
+    MELSPEC_ERR_CUDA = 3,           /* CudaError::Runtime; text via melspec_last_error()                   */
+    MELSPEC_ERR_INVALID_ARG = 4,    /* null pointers, negative sizes, capacity too small                   */
+    MELSPEC_ERR_UNSUPPORTED = 5     /* well-formed request this build has no kernel for                    */
+};
+
+/* ---- which reference pipeline the handle implements ---- */
+enum {
+    MELSPEC_FRONTEND_WHISPER = 0, /* Hann -> FFT -> |X|^2 (bins < N/2) -> Slaney mel -> log10/1e-10 -> per-frame max-8, (x+4)/4
+                                     src/stft.rs:89-169 + src/mel.rs:148-168,645-654                                         */
+    MELSPEC_FRONTEND_KALDI = 1    /* DC removal, pre-emphasis, Povey, zero-pad to 2^k, FFT, power, Kaldi mel (Hz triangles),
+                                     ln(max(e, FLT_EPSILON)), optional CMN.  src/fbank.rs:141-236                            */
+};
+
+/* ---- output layouts ---- */
+enum {
+    MELSPEC_LAYOUT_FRAME_MAJOR = 0, /* out[clip][frame][mel]  == Vec<Vec<f32>> of src/stft.rs:119-138 and Array2 (T,80) of fbank */
+    MELSPEC_LAYOUT_MEL_MAJOR = 1    /* out[clip][mel][frame]  == interleave_frames(.., false, 0) / rust_jfk_golden.npy layout    */
+};
+
+/*
+ * POD configuration.  Mirrors MelConfig (src/config.rs:1-34) for the Whisper frontend and FbankConfig
+ * (src/fbank.rs:25-64) for the Kaldi one.  Zero-initialise, then fill; `melspec_default_config` does it.
+ */
+typedef struct melspec_config {
+    int32_t frontend;      /* MELSPEC_FRONTEND_*                                                               */
+    int32_t fft_size;      /* Whisper: N (400 or 512).  Kaldi: ignored on input (next pow2 of frame_length).   */
+    int32_t hop_size;      /* samples between frames (Whisper hop / Kaldi frame shift)                         */
+    int32_t n_mels;        /* 1..128                                                                           */
+    double sampling_rate;  /* Hz                                                                               */
+    /* Kaldi-only fields (FbankConfig).  Ignored for the Whisper frontend. */
+    int32_t frame_length;  /* samples per frame before zero padding (400)                                      */
+    int32_t apply_cmn;     /* subtract per-mel mean over time (src/fbank.rs:226-233)                           */
+    int32_t use_log_fbank; /* ln() of the floored energies                                                     */
+    int32_t use_power;     /* 1: |X|^2 (only value supported), 0: |X|                                          */
+    double preemphasis;    /* 0.97                                                                             */
+    double low_freq;       /* 20 Hz                                                                            */
+    double high_freq;      /* 0 => Nyquist                                                                     */
+    double energy_floor;   /* <= 0 => FLT_EPSILON                                                              */
+} melspec_config;
+
+typedef struct melspec_handle melspec_handle;
+typedef struct melspec_stream melspec_stream;
+
+/* Fills `cfg` with the reference defaults: Whisper {400,160,80,16000} (README / src/cuda.rs:490-493) or
+ * FbankConfig::default() (src/fbank.rs:46-64).  Returns MELSPEC_ERR_INVALID_ARG for an unknown frontend. */
+int32_t melspec_default_config(int32_t frontend, melspec_config* cfg);
+
+/* Builds the constant tables (window, twiddles, sparse banded filterbank) on `device` and returns a handle.
+ * Replaces CudaMelSpectrogram::new (src/cuda.rs:39-82) / Fbank::new (src/fbank.rs:94-132). */
+int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle** out);
+
+/* Replaces Drop (src/cuda.rs:142-148, 366-375).  NULL is a no-op. */
+void melspec_destroy(melspec_handle* h);
+
+/* Frames produced for a clip of `n_samples`: 0 if shorter than one frame, else (n - frame)/hop + 1
+ * (src/stft.rs:153-157, src/fbank.rs:147-151). */
+int64_t melspec_num_frames(const melspec_handle* h, int64_t n_samples);
+
+/* The reference's batching knob (src/cuda.rs:150-155: min(8192, 64 MiB / bytes-per-frame)); kept for API
+ * parity.  This implementation has no such limit on the device path; the value is what the reference returns. */
+int32_t melspec_max_frames_per_batch(const melspec_handle* h);
+
+int32_t melspec_n_mels(const melspec_handle* h);
+int32_t melspec_fft_size(const melspec_handle* h);
+int32_t melspec_hop_size(const melspec_handle* h);
+
+/* Device-free: the dense filterbank a handle created from `cfg` would project with, row-major
+ * (n_mels, fft_size/2+1) f64 — `mel()` of src/mel.rs:547-589 for the Whisper frontend, `kaldi_mel_filterbank`
+ * (src/fbank.rs:253-301) for the Kaldi one.  `capacity` in doubles.  Usable without a GPU (host logic tests). */
+int32_t melspec_build_filterbank(const melspec_config* cfg, double* out, int64_t capacity);
+
+/* Device-free frame count for `cfg` (same rule as melspec_num_frames). */
+int64_t melspec_num_frames_cfg(const melspec_config* cfg, int64_t n_samples);
+
+/* Dense filterbank the handle projects with, row-major (n_mels, fft_size/2+1) f64 — `mel()` of src/mel.rs:547-589
+ * or `Fbank::dense_filterbank` (src/fbank.rs:243-245).  `capacity` in doubles. */
+int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacity);
+
+/*
+ * The hot path.  Device-resident PCM in, device-resident features out, asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).  Replaces cufftExecZ2Z + launch_mel_kernel +
+ * the host-side windowing and norm_mel_vec of src/cuda.rs:88-139.
+ *
+ *   d_pcm            n_clips rows of f32 samples, row r at d_pcm + r*clip_stride
+ *   n_samples        samples per row (rows shorter than that: pass d_lens)
+ *   d_lens           optional DEVICE array of n_clips int32 valid lengths (<= n_samples); NULL = all n_samples
+ *   d_out            frame-major: [n_clips][F][n_mels], mel-major: [n_clips][n_mels][F], F = melspec_num_frames(n_samples);
+ *                    clip r at d_out + r*out_clip_stride (floats; 0 = dense F*n_mels).  Frames past a short clip's
+ *                    own frame count are left untouched.
+ * Fast path (TMA bulk copies) needs 16-byte aligned d_pcm/d_out, clip_stride % 4 == 0 and n_samples % 4 == 0;
+ * otherwise a slower cooperative-copy path of the same kernel is used (results identical).
+ */
+int32_t melspec_compute_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride,
+                               int64_t n_samples, const int32_t* d_lens, float* d_out, int64_t out_clip_stride,
+                               int32_t layout, void* stream);
+
+/*
+ * Host-buffer convenience with the reference's shape: &[f32] -> Vec<Vec<f32>> ([frame][mel], src/cuda.rs:88-101)
+ * or Fbank::compute's (T, n_mels) (src/fbank.rs:141-236), for a batch of equally long clips.
+ * H2D + kernel + D2H, pipelined over internal streams and pinned staging; blocks until h_out is complete
+ * (the reference synchronises per batch, src/cuda.rs:129).  n_samples < frame length => 0 frames, MELSPEC_OK
+ * (src/cuda.rs:91-93).  `frames_out` (optional) receives F.
+ */
+int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride,
+                             int64_t n_samples, float* h_out, int32_t layout, int64_t* frames_out);
+
+/*
+ * Streaming (overlap-and-save) front end with RingBuffer/Spectrogram::add semantics (src/rb.rs:86-121,
+ * src/stft.rs:48-86) when fed whole hops: frame k covers stream samples [c + k*hop, c + k*hop + N),
+ * c = ceil(N/hop)*hop - N; a trailing partial hop stays buffered and is never emitted.
+ * `push` copies host samples to the device on a side stream, runs the fused kernel on the new frames only
+ * (the last N-hop samples stay resident on the device), and returns the new frames frame-major in h_out.
+ */
+int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, melspec_stream** out);
+int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n, float* h_out,
+                            int64_t out_capacity_frames, int64_t* frames_emitted);
+int32_t melspec_stream_reset(melspec_stream* s);
+void melspec_stream_destroy(melspec_stream* s);
+
+/* Number of kernel launches issued through this handle so far (bench.py's `gpu_launches`). */
+int64_t melspec_launch_count(const melspec_handle* h);
+
+/* Thread-local description of the last failure in this thread ("" if none).  Never NULL. */
+const char* melspec_last_error(void);
+
+int32_t melspec_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELSPEC_B200_H_ */

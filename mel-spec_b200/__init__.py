@@ -1,0 +1,16 @@
+"""melspec_b200 — B200-native log-mel frontend behind the wavey-ai/mel-spec prelude names.
+
+Layout: csrc/ (the sm_100a kernel + the C ABI), lib/ (the built shared library, git-ignored), _lib.py (ctypes
+binding of include/melspec_b200.h), api.py (host-side mirror of the reference interface).
+"""
+from ._lib import build, lib, last_error, LIB_PATH, EXPORTS  # noqa: F401
+from .api import (  # noqa: F401
+    CudaError, CudaMelSpectrogram, Fbank, FbankConfig, MelConfig, RingBuffer, Spectrogram,
+    kaldi_mel_filterbank, mel,
+    FRONTEND_KALDI, FRONTEND_WHISPER, LAYOUT_FRAME_MAJOR, LAYOUT_MEL_MAJOR,
+)
+
+__all__ = [
+    "CudaError", "CudaMelSpectrogram", "Fbank", "FbankConfig", "MelConfig", "RingBuffer", "Spectrogram",
+    "kaldi_mel_filterbank", "mel", "build", "lib",
+]

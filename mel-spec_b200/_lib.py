@@ -1,0 +1,109 @@
+"""ctypes binding of the C ABI in include/melspec_b200.h (the same symbols a Rust `extern "C"` block binds).
+
+The shared library is built in-tree by `build()` (nvcc, sm_100a) and is the ONLY compute path: there is no CPU
+or PyTorch fallback — if the library is missing or no B200 is present, calls raise `CudaError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "lib", "libmelspec_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", "melspec_api.cu")]
+HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_ROOT, "include", "melspec_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+# every symbol include/melspec_b200.h declares
+EXPORTS = [
+    "melspec_abi_version", "melspec_last_error", "melspec_default_config", "melspec_build_filterbank",
+    "melspec_num_frames_cfg", "melspec_create", "melspec_destroy", "melspec_num_frames",
+    "melspec_max_frames_per_batch", "melspec_n_mels", "melspec_fft_size", "melspec_hop_size", "melspec_filterbank",
+    "melspec_compute_device", "melspec_compute_host", "melspec_stream_create", "melspec_stream_push",
+    "melspec_stream_reset", "melspec_stream_destroy", "melspec_launch_count",
+]
+
+
+class MelspecConfig(C.Structure):
+    """struct melspec_config (include/melspec_b200.h)."""
+    _fields_ = [
+        ("frontend", C.c_int32), ("fft_size", C.c_int32), ("hop_size", C.c_int32), ("n_mels", C.c_int32),
+        ("sampling_rate", C.c_double),
+        ("frame_length", C.c_int32), ("apply_cmn", C.c_int32), ("use_log_fbank", C.c_int32), ("use_power", C.c_int32),
+        ("preemphasis", C.c_double), ("low_freq", C.c_double), ("high_freq", C.c_double), ("energy_floor", C.c_double),
+    ]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (cross-compiles without a GPU)."""
+    if force or _stale():
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        nvcc = os.environ.get("NVCC", "nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """Load the library and declare prototypes.  Raises OSError if it was never built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
+    cfgp = C.POINTER(MelspecConfig)
+    L.melspec_abi_version.restype = i32
+    L.melspec_last_error.restype = C.c_char_p
+    L.melspec_default_config.restype = i32
+    L.melspec_default_config.argtypes = [i32, cfgp]
+    L.melspec_build_filterbank.restype = i32
+    L.melspec_build_filterbank.argtypes = [cfgp, C.POINTER(C.c_double), i64]
+    L.melspec_num_frames_cfg.restype = i64
+    L.melspec_num_frames_cfg.argtypes = [cfgp, i64]
+    L.melspec_create.restype = i32
+    L.melspec_create.argtypes = [cfgp, i32, C.POINTER(vp)]
+    L.melspec_destroy.restype = None
+    L.melspec_destroy.argtypes = [vp]
+    L.melspec_num_frames.restype = i64
+    L.melspec_num_frames.argtypes = [vp, i64]
+    for name in ("melspec_max_frames_per_batch", "melspec_n_mels", "melspec_fft_size", "melspec_hop_size"):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = [vp]
+    L.melspec_filterbank.restype = i32
+    L.melspec_filterbank.argtypes = [vp, C.POINTER(C.c_double), i64]
+    L.melspec_compute_device.restype = i32
+    L.melspec_compute_device.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i32, vp]
+    L.melspec_compute_host.restype = i32
+    L.melspec_compute_host.argtypes = [vp, vp, i64, i64, i64, vp, i32, C.POINTER(i64)]
+    L.melspec_stream_create.restype = i32
+    L.melspec_stream_create.argtypes = [vp, i64, C.POINTER(vp)]
+    L.melspec_stream_push.restype = i32
+    L.melspec_stream_push.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.melspec_stream_reset.restype = i32
+    L.melspec_stream_reset.argtypes = [vp]
+    L.melspec_stream_destroy.restype = None
+    L.melspec_stream_destroy.argtypes = [vp]
+    L.melspec_launch_count.restype = i64
+    L.melspec_launch_count.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def last_error() -> str:
+    return lib().melspec_last_error().decode("utf-8", "replace")

@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's public interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the Rust prelude (reference src/prelude.rs:1-23):
+
+    MelConfig                      src/config.rs:1-34
+    CudaError                      src/cuda.rs:10-25   (Runtime / Unavailable)
+    CudaMelSpectrogram             src/cuda.rs:27-155  new(fft, hop, sr, n_mels), compute_mel_spectrogram, max_frames_per_batch
+    Spectrogram.compute_mel_spectrogram   batch semantics of src/stft.rs:119-138 (GPU-backed; there is no CPU path here)
+    FbankConfig / Fbank            src/fbank.rs:25-82, 84-250
+    mel()                          src/mel.rs:547-589  (filterbank; host-only, no GPU needed)
+    RingBuffer                     src/rb.rs:12-122    add_frame / add / maybe_mel, frames come from the streaming C ABI
+
+Arrays are numpy instead of Vec<Vec<f32>> / ndarray; shapes and element order are the reference's.
+Everything numeric happens in `lib/libmelspec_b200.so`; nothing here computes features on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import deque
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+FRONTEND_WHISPER = 0
+FRONTEND_KALDI = 1
+LAYOUT_FRAME_MAJOR = 0
+LAYOUT_MEL_MAJOR = 1
+
+OK, ERR_INVALID_CONFIG, ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID_ARG, ERR_UNSUPPORTED = range(6)
+
+
+class CudaError(RuntimeError):
+    """reference src/cuda.rs:10-25.  `kind` is 'Unavailable' (construction impossible) or 'Runtime'."""
+
+    def __init__(self, kind: str, msg: str, code: int = ERR_CUDA):
+        self.kind, self.msg, self.code = kind, msg, code
+        super().__init__(f"CUDA {'unavailable' if kind == 'Unavailable' else 'error'}: {msg}")
+
+
+def _check(rc: int, constructing: bool = False):
+    if rc == OK:
+        return
+    msg = _lib.last_error()
+    if rc in (ERR_NO_DEVICE, ERR_INVALID_CONFIG, ERR_UNSUPPORTED) and constructing:
+        raise CudaError("Unavailable", msg, rc)      # src/cuda.rs:45-49, 242-294
+    if rc == ERR_INVALID_ARG:
+        raise ValueError(msg)
+    raise CudaError("Runtime", msg, rc)
+
+
+@dataclass(frozen=True)
+class MelConfig:
+    """reference src/config.rs:1-34 (getters become attributes)."""
+    fft_size: int
+    hop_size: int
+    n_mels: int
+    sampling_rate: float
+
+
+@dataclass
+class FbankConfig:
+    """reference src/fbank.rs:25-64 with its Default."""
+    sample_rate: float = 16000.0
+    num_mel_bins: int = 80
+    frame_length_ms: float = 25.0
+    frame_shift_ms: float = 10.0
+    dither: float = 0.0
+    energy_floor: float = 0.0
+    use_energy: bool = False
+    use_log_fbank: bool = True
+    use_power: bool = True
+    preemphasis: float = 0.97
+    apply_cmn: bool = True
+    low_freq: float = 20.0
+    high_freq: float = 0.0
+
+    def frame_length_samples(self) -> int:      # src/fbank.rs:68-70
+        return int(round(self.frame_length_ms / 1000.0 * self.sample_rate))
+
+    def frame_shift_samples(self) -> int:       # src/fbank.rs:73-75
+        return int(round(self.frame_shift_ms / 1000.0 * self.sample_rate))
+
+    def fft_size(self) -> int:                  # src/fbank.rs:78-81
+        n = self.frame_length_samples()
+        return 1 << (n - 1).bit_length()
+
+
+def _whisper_cfg(fft_size, hop_size, n_mels, sampling_rate) -> _lib.MelspecConfig:
+    c = _lib.MelspecConfig()
+    c.frontend, c.fft_size, c.hop_size, c.n_mels = FRONTEND_WHISPER, int(fft_size), int(hop_size), int(n_mels)
+    c.sampling_rate, c.frame_length = float(sampling_rate), int(fft_size)
+    return c
+
+
+def _kaldi_cfg(fc: FbankConfig) -> _lib.MelspecConfig:
+    c = _lib.MelspecConfig()
+    c.frontend = FRONTEND_KALDI
+    c.frame_length, c.hop_size = fc.frame_length_samples(), fc.frame_shift_samples()
+    c.fft_size, c.n_mels, c.sampling_rate = fc.fft_size(), int(fc.num_mel_bins), float(fc.sample_rate)
+    c.apply_cmn, c.use_log_fbank, c.use_power = int(fc.apply_cmn), int(fc.use_log_fbank), int(fc.use_power)
+    c.preemphasis, c.low_freq, c.high_freq, c.energy_floor = fc.preemphasis, fc.low_freq, fc.high_freq, fc.energy_floor
+    return c
+
+
+def mel(sr: float, n_fft: int, n_mels: int) -> np.ndarray:
+    """Slaney filterbank, (n_mels, n_fft/2+1) f64 — `mel(sr, n_fft, n_mels, None, None, false, true)` (src/mel.rs:547-589).
+    Built by the C library's host code; needs no GPU."""
+    cfg = _whisper_cfg(n_fft, 160, n_mels, sr)
+    out = np.zeros((n_mels, n_fft // 2 + 1), dtype=np.float64)
+    _check(_lib.lib().melspec_build_filterbank(C.byref(cfg), out.ctypes.data_as(C.POINTER(C.c_double)), out.size), True)
+    return out
+
+
+def kaldi_mel_filterbank(config: FbankConfig | None = None) -> np.ndarray:
+    """`Fbank::dense_filterbank` (src/fbank.rs:243-245, 253-301), host-only."""
+    fc = config or FbankConfig()
+    cfg = _kaldi_cfg(fc)
+    out = np.zeros((fc.num_mel_bins, fc.fft_size() // 2 + 1), dtype=np.float64)
+    _check(_lib.lib().melspec_build_filterbank(C.byref(cfg), out.ctypes.data_as(C.POINTER(C.c_double)), out.size), True)
+    return out
+
+
+def _ptr(x) -> int:
+    """Raw device address of a torch tensor / anything with data_ptr(), or an int."""
+    if x is None:
+        return 0
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    return int(x)
+
+
+class _Handle:
+    """Owns one melspec_handle (RAII like the reference's Drop, src/cuda.rs:142-148)."""
+
+    def __init__(self, cfg: _lib.MelspecConfig, device: int):
+        self._h = C.c_void_p()
+        self._L = _lib.lib()
+        _check(self._L.melspec_create(C.byref(cfg), int(device), C.byref(self._h)), constructing=True)
+        self.n_mels = self._L.melspec_n_mels(self._h)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.melspec_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shared entry points -------------------------------------------------------------------
+    def num_frames(self, n_samples: int) -> int:
+        return int(self._L.melspec_num_frames(self._h, int(n_samples)))
+
+    def launch_count(self) -> int:
+        return int(self._L.melspec_launch_count(self._h))
+
+    def compute_device(self, d_pcm, n_clips: int, clip_stride: int, n_samples: int, d_out, *, d_lens=None,
+                       out_clip_stride: int = 0, layout: int = LAYOUT_FRAME_MAJOR, stream=None) -> None:
+        """`melspec_compute_device`: device-resident PCM in, features out, asynchronous on `stream`.
+        `d_pcm`, `d_out`, `d_lens` are torch CUDA tensors (or raw addresses); `stream` a torch.cuda.Stream or handle."""
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _check(self._L.melspec_compute_device(self._h, _ptr(d_pcm), int(n_clips), int(clip_stride), int(n_samples),
+                                              _ptr(d_lens), _ptr(d_out), int(out_clip_stride), int(layout), s))
+
+    def compute_host(self, samples, layout: int = LAYOUT_FRAME_MAJOR, out: np.ndarray | None = None) -> np.ndarray:
+        """`melspec_compute_host` on a (n_samples,) or (n_clips, n_samples) f32 host array."""
+        x = np.asarray(samples, dtype=np.float32)
+        single = x.ndim == 1
+        x2 = np.ascontiguousarray(x.reshape(1, -1) if single else x)
+        n_clips, n = x2.shape
+        f = self.num_frames(n)
+        shape = (n_clips, f, self.n_mels) if layout == LAYOUT_FRAME_MAJOR else (n_clips, self.n_mels, f)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == int(np.prod(shape))
+        frames = C.c_int64(0)
+        _check(self._L.melspec_compute_host(self._h, x2.ctypes.data, n_clips, n, n, out.ctypes.data, int(layout),
+                                            C.byref(frames)))
+        out = out.reshape(shape)
+        return out[0] if single else out
+
+    def compute_host_raw(self, h_pcm_ptr: int, n_clips: int, clip_stride: int, n_samples: int, h_out_ptr: int,
+                         layout: int = LAYOUT_FRAME_MAJOR) -> int:
+        """Pointer form of `melspec_compute_host` (pinned torch host tensors in bench.py)."""
+        frames = C.c_int64(0)
+        _check(self._L.melspec_compute_host(self._h, int(h_pcm_ptr), int(n_clips), int(clip_stride), int(n_samples),
+                                            int(h_out_ptr), int(layout), C.byref(frames)))
+        return int(frames.value)
+
+
+class CudaMelSpectrogram(_Handle):
+    """reference src/cuda.rs:27-155.  `CudaMelSpectrogram(fft_size, hop_size, sampling_rate, n_mels)` == `new`."""
+
+    def __init__(self, fft_size: int, hop_size: int, sampling_rate: float, n_mels: int, device: int = 0):
+        if fft_size == 0 or hop_size == 0 or n_mels == 0:      # src/cuda.rs:45-49
+            raise CudaError("Unavailable", "fft_size, hop_size, and n_mels must be non-zero", ERR_INVALID_CONFIG)
+        self.fft_size, self.hop_size, self.sampling_rate = int(fft_size), int(hop_size), float(sampling_rate)
+        super().__init__(_whisper_cfg(fft_size, hop_size, n_mels, sampling_rate), device)
+
+    def max_frames_per_batch(self) -> int:                     # src/cuda.rs:84-86, 150-155
+        return int(self._L.melspec_max_frames_per_batch(self._h))
+
+    def compute_mel_spectrogram(self, samples) -> np.ndarray:
+        """&[f32] -> [frame][mel] f32 (src/cuda.rs:88-101).  Empty / too-short input => shape (0, n_mels)."""
+        return self.compute_host(np.asarray(samples, dtype=np.float32).reshape(-1))
+
+
+class Spectrogram:
+    """Batch entry of reference src/stft.rs:119-138, GPU-backed (handles are cached per configuration)."""
+    _cache: dict = {}
+
+    @classmethod
+    def compute_mel_spectrogram(cls, samples, fft_size: int, hop_size: int, n_mels: int, sampling_rate: float,
+                                device: int = 0) -> np.ndarray:
+        key = (int(fft_size), int(hop_size), int(n_mels), float(sampling_rate), int(device))
+        h = cls._cache.get(key)
+        if h is None:
+            h = cls._cache[key] = CudaMelSpectrogram(fft_size, hop_size, sampling_rate, n_mels, device)
+        return h.compute_mel_spectrogram(samples)
+
+
+class Fbank(_Handle):
+    """reference src/fbank.rs:84-250: `Fbank(FbankConfig()).compute(samples) -> (T, num_mel_bins) f32`."""
+
+    def __init__(self, config: FbankConfig | None = None, device: int = 0):
+        self.config = config or FbankConfig()
+        super().__init__(_kaldi_cfg(self.config), device)
+
+    def compute(self, samples) -> np.ndarray:
+        return self.compute_host(np.asarray(samples, dtype=np.float32).reshape(-1))
+
+    def dense_filterbank(self) -> np.ndarray:
+        return kaldi_mel_filterbank(self.config)
+
+
+class RingBuffer:
+    """reference src/rb.rs:12-122 on the device: samples are queued on the host (bounded FIFO that drops the oldest
+    samples when full, like the VecDeque build of the reference), whole hops are pushed to the streaming C ABI, and
+    `maybe_mel()` hands out one (n_mels, 1) frame at a time (f32; the reference's Array2<f64> cast to f32 at the end)."""
+
+    def __init__(self, config: MelConfig, capacity: int, device: int = 0, max_chunk_samples: int = 1 << 16):
+        self.config = config
+        self.capacity = int(capacity)
+        self._fifo: deque = deque()
+        self._fifo_len = 0
+        self._handle = CudaMelSpectrogram(config.fft_size, config.hop_size, config.sampling_rate, config.n_mels, device)
+        self._L = self._handle._L
+        self._s = C.c_void_p()
+        self._max_chunk = int(max_chunk_samples) // config.hop_size * config.hop_size
+        _check(self._L.melspec_stream_create(self._handle._h, self._max_chunk, C.byref(self._s)), constructing=True)
+        self._ready: deque = deque()
+        self._out = np.empty((self._max_chunk // config.hop_size + 4, config.n_mels), dtype=np.float32)
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s:
+            self._L.melspec_stream_destroy(self._s)
+            self._s = C.c_void_p()
+        self._handle.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_frame(self, samples) -> None:                      # src/rb.rs:54-70
+        x = np.asarray(samples, dtype=np.float32).reshape(-1)
+        if x.size > self.capacity:
+            x = x[-self.capacity:]
+        over = self._fifo_len + x.size - self.capacity
+        while over > 0 and self._fifo:
+            head = self._fifo[0]
+            if head.size <= over:
+                self._fifo.popleft(); self._fifo_len -= head.size; over -= head.size
+            else:
+                self._fifo[0] = head[over:]; self._fifo_len -= over; over = 0
+        self._fifo.append(x.copy())
+        self._fifo_len += x.size
+
+    def add(self, sample: float) -> None:                      # src/rb.rs:72-84
+        self.add_frame(np.asarray([sample], dtype=np.float32))
+
+    def _drain_hops(self, max_hops: int | None = None) -> None:
+        hop = self.config.hop_size
+        n_hops = self._fifo_len // hop
+        if max_hops is not None:
+            n_hops = min(n_hops, max_hops)
+        n_hops = min(n_hops, self._max_chunk // hop)
+        if n_hops == 0:
+            return
+        need = n_hops * hop
+        parts, got = [], 0
+        while got < need:
+            head = self._fifo.popleft()
+            take = min(head.size, need - got)
+            parts.append(head[:take])
+            if take < head.size:
+                self._fifo.appendleft(head[take:])
+            got += take
+        self._fifo_len -= need
+        chunk = np.ascontiguousarray(np.concatenate(parts))
+        emitted = C.c_int64(0)
+        _check(self._L.melspec_stream_push(self._s, chunk.ctypes.data, chunk.size, self._out.ctypes.data,
+                                           self._out.shape[0], C.byref(emitted)))
+        for k in range(int(emitted.value)):
+            self._ready.append(self._out[k].copy())
+
+    def maybe_mel(self):                                       # src/rb.rs:86-121
+        """One hop of queued samples -> at most one frame, exactly like the reference: returns an (n_mels, 1) array
+        or None (not enough samples for a hop yet, or the stream has not seen fft_size samples)."""
+        if not self._ready:
+            if self._fifo_len < self.config.hop_size:
+                return None
+            self._drain_hops(max_hops=1)
+        if not self._ready:
+            return None
+        return self._ready.popleft().reshape(-1, 1)
+
+    def drain(self) -> np.ndarray:
+        """Convenience for long streams: push every queued whole hop in large chunks, return all frames (F, n_mels)."""
+        while self._fifo_len >= self.config.hop_size:
+            self._drain_hops()
+        out = np.stack(list(self._ready)) if self._ready else np.zeros((0, self.config.n_mels), np.float32)
+        self._ready.clear()
+        return out

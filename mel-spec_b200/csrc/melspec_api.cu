@@ -1,0 +1,645 @@
+// melspec_b200 host side: the C ABI declared in include/melspec_b200.h.
+//
+// Builds the constant tables (window, twiddles, sparse banded filterbank -> per-lane projection program) in f64 on
+// the host, owns the device copies, and launches the fused kernel of melspec_kernels.cuh.  No cuFFT, no torch.
+// Reference interfaces replaced: src/cuda.rs:39-155 (CudaMelSpectrogram), src/cuda.rs:161-480 (mod ffi),
+// src/fbank.rs:94-236 (Fbank), src/rb.rs:86-121 + src/stft.rs:48-86 (streaming).
+#include "../../include/melspec_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "melspec_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int32_t fail(int32_t code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int32_t fail_cuda(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return MELSPEC_ERR_CUDA;
+}
+#define MS_CUDA(call)                                           \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call);   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ filterbanks (f64)
+// Slaney scale, the math of SURVEY Appendix A.1 / reference src/mel.rs:547-643 (htk = false, norm = true, 0..sr/2).
+double slaney_hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, brk = 1000.0, brk_mel = brk / f_sp, step = std::log(6.4) / 27.0;
+    return f >= brk ? brk_mel + std::log(f / brk) / step : f / f_sp;
+}
+double slaney_mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, brk = 1000.0, brk_mel = brk / f_sp, step = std::log(6.4) / 27.0;
+    return m >= brk_mel ? brk * std::exp(step * (m - brk_mel)) : f_sp * m;
+}
+void build_slaney(double sr, int n_fft, int n_mels, std::vector<double>& w) {
+    const int nb = n_fft / 2 + 1;
+    w.assign((size_t)n_mels * nb, 0.0);
+    std::vector<double> edge(n_mels + 2);
+    const double lo = slaney_hz_to_mel(0.0), hi = slaney_hz_to_mel(sr / 2.0);
+    const double step = (hi - lo) / (double)(n_mels + 1);
+    for (int i = 0; i < n_mels + 2; ++i) edge[i] = slaney_mel_to_hz(lo + step * (double)i);
+    for (int m = 0; m < n_mels; ++m) {
+        const double up = edge[m + 1] - edge[m], dn = edge[m + 2] - edge[m + 1];
+        const double area = 2.0 / (edge[m + 2] - edge[m]);
+        for (int b = 0; b < nb; ++b) {
+            const double f = (sr / (double)n_fft) * (double)b;
+            const double rise = std::min(std::max((f - edge[m]) / up, 0.0), 1.0);
+            const double fall = std::min(std::max((edge[m + 2] - f) / dn, 0.0), 1.0);
+            w[(size_t)m * nb + b] = std::min(rise, fall) * area;
+        }
+    }
+}
+// Kaldi-mel edges, triangles evaluated in Hz, no area normalisation: reference src/fbank.rs:253-313.
+void build_kaldi(double sr, int n_fft, int n_mels, double low, double high, std::vector<double>& w) {
+    const int nb = n_fft / 2 + 1;
+    w.assign((size_t)n_mels * nb, 0.0);
+    const double ml = 1127.0 * std::log(1.0 + low / 700.0), mh = 1127.0 * std::log(1.0 + high / 700.0);
+    std::vector<double> hz(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i)
+        hz[i] = 700.0 * (std::exp((ml + (mh - ml) * (double)i / (double)(n_mels + 1)) / 1127.0) - 1.0);
+    for (int m = 0; m < n_mels; ++m) {
+        const double l = hz[m], c = hz[m + 1], r = hz[m + 2];
+        if (c <= l || r <= c) continue;
+        for (int b = 0; b < nb; ++b) {
+            const double f = (double)b * sr / (double)n_fft;
+            if (f > l && f <= c) w[(size_t)m * nb + b] = (f - l) / (c - l);
+            else if (f > c && f < r) w[(size_t)m * nb + b] = (r - f) / (r - c);
+        }
+    }
+}
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Validated, normalised view of a melspec_config.
+struct Resolved {
+    int frontend, fft, hop, n_mels, frame_len;
+    double sr, preemph, low, high, floor;
+    int cmn, use_log, use_power;
+};
+
+int32_t resolve(const melspec_config* c, Resolved& r) {
+    if (!c) return fail(MELSPEC_ERR_INVALID_ARG, "config is null");
+    r.frontend = c->frontend;
+    r.hop = c->hop_size;
+    r.n_mels = c->n_mels;
+    r.sr = c->sampling_rate;
+    if (c->frontend == MELSPEC_FRONTEND_WHISPER) {
+        r.fft = c->fft_size;
+        r.frame_len = c->fft_size;
+        if (r.fft <= 0 || r.hop <= 0 || r.n_mels <= 0)
+            return fail(MELSPEC_ERR_INVALID_CONFIG, "fft_size, hop_size, and n_mels must be non-zero");   // src/cuda.rs:45-49
+        r.preemph = 0; r.low = 0; r.high = r.sr / 2; r.floor = 1e-10; r.cmn = 0; r.use_log = 1; r.use_power = 1;
+    } else if (c->frontend == MELSPEC_FRONTEND_KALDI) {
+        r.frame_len = c->frame_length;
+        if (r.frame_len <= 1 || r.hop <= 0 || r.n_mels <= 0)
+            return fail(MELSPEC_ERR_INVALID_CONFIG, "frame_length, hop_size, and n_mels must be non-zero");
+        r.fft = next_pow2(r.frame_len);
+        r.preemph = c->preemphasis; r.low = c->low_freq; r.high = c->high_freq == 0.0 ? r.sr / 2.0 : c->high_freq;
+        r.floor = c->energy_floor > 0.0 ? c->energy_floor : (double)1.1920928955078125e-07f;
+        r.cmn = c->apply_cmn; r.use_log = c->use_log_fbank; r.use_power = c->use_power;
+    } else {
+        return fail(MELSPEC_ERR_INVALID_CONFIG, "unknown frontend");
+    }
+    if (!(r.sr > 0.0)) return fail(MELSPEC_ERR_INVALID_CONFIG, "sampling_rate must be positive");
+    if (r.n_mels > 32 * melspec::kMaxMpl) return fail(MELSPEC_ERR_INVALID_CONFIG, "n_mels must be <= 128");
+    return MELSPEC_OK;
+}
+
+void build_filterbank(const Resolved& r, std::vector<double>& w) {
+    if (r.frontend == MELSPEC_FRONTEND_WHISPER) build_slaney(r.sr, r.fft, r.n_mels, w);
+    else build_kaldi(r.sr, r.fft, r.n_mels, r.low, r.high, w);
+}
+
+int64_t frames_for(const Resolved& r, int64_t n) {
+    return n < r.frame_len ? 0 : (n - r.frame_len) / r.hop + 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ handle
+struct melspec_handle {
+    Resolved cfg;
+    int device = 0;
+    int num_sms = 0;
+    int plan = 0;   // 400 or 512
+    std::vector<double> dense;   // (n_mels, fft/2+1)
+    // device tables
+    float* d_window = nullptr;
+    float4* d_twiddle = nullptr;
+    float2* d_proj = nullptr;
+    int* d_meta = nullptr;
+    int proj_ktot = 0;
+    int mpl = 0;
+    // host-path resources (lazily created)
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    float* d_slot_pcm[3] = {nullptr, nullptr, nullptr};
+    float* d_slot_out[3] = {nullptr, nullptr, nullptr};
+    size_t slot_pcm_cap = 0, slot_out_cap = 0;
+    int64_t launches = 0;
+};
+
+struct melspec_stream {
+    melspec_handle* h = nullptr;
+    int64_t max_chunk = 0;
+    float* d_buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    int64_t cap = 0;        // samples per device buffer
+    int64_t buffered = 0;   // valid samples in d_buf[cur]
+    int64_t to_skip = 0;    // samples still to drop before the first frame (the stream offset c)
+    float* h_pin_in = nullptr;
+    float* h_pin_out = nullptr;
+    float* d_out = nullptr;
+    int64_t out_cap_frames = 0;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+
+namespace {
+
+// P row (in the kernel's power slab) that holds bin b; see melspec_kernels.cuh (row = 10*j + t).
+int p400_row_of_bin(int b) {
+    const int rr = b % 20, q = b / 20;
+    int t, j;
+    if (rr == 0) { t = 0; j = 20 - q; }          // worker 0, high half: bin 20*(20-j)
+    else if (rr == 10) { t = 0; j = q; }          // worker 0, low half: bin 10+20j
+    else if (rr < 10) { t = rr; j = q; }          // worker rr, low half: bin rr+20j
+    else { t = 20 - rr; j = 19 - q; }             // worker 20-rr, high half: bin (20-t) + 20(19-j)
+    return 10 * j + t;
+}
+
+int32_t build_tables(melspec_handle* h) {
+    const Resolved& c = h->cfg;
+    using namespace melspec;
+    if (h->plan != 400) return fail(MELSPEC_ERR_UNSUPPORTED, "only the 400-point plan is built in this revision");
+    const int N = 400, nb = N / 2 + 1;
+    // window: periodic Hann (reference src/stft.rs:141-145), computed in f64, rounded once
+    std::vector<float> win(N);
+    for (int i = 0; i < N; ++i) win[i] = (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N)));
+    // twiddles W_400^(row*n2), laid out [slot][unit] with unit i = (n2 = 2i, 2i+1)
+    std::vector<float4> tw((size_t)p400::TWUNITS, make_float4(0, 0, 0, 0));
+    for (int row = 0; row < 20; ++row) {
+        const int slot = p400::slot_of_row(row);
+        for (int i = 0; i < 10; ++i) {
+            const double a0 = -2.0 * M_PI * (double)((row * (2 * i)) % N) / (double)N;
+            const double a1 = -2.0 * M_PI * (double)((row * (2 * i + 1)) % N) / (double)N;
+            tw[(size_t)slot * p400::TWROW + i] = make_float4((float)std::cos(a0), (float)std::sin(a0), (float)std::cos(a1), (float)std::sin(a1));
+        }
+    }
+    // sparse banded filterbank -> per-lane projection program
+    for (int m = 0; m < c.n_mels; ++m)
+        if (h->dense[(size_t)m * nb] != 0.0)
+            return fail(MELSPEC_ERR_UNSUPPORTED, "filterbank has a non-zero DC column; the kernel never forms bin 0");
+    struct Band { int mel; std::vector<std::pair<int, double>> e; };
+    std::vector<Band> bands(c.n_mels);
+    for (int m = 0; m < c.n_mels; ++m) {
+        bands[m].mel = m;
+        // Whisper drops bins >= N/2 (reference src/mel.rs:158-162)
+        const int last = c.frontend == MELSPEC_FRONTEND_WHISPER ? N / 2 - 1 : N / 2;
+        for (int b = 1; b <= last; ++b) {
+            const double w = h->dense[(size_t)m * nb + b];
+            if (w != 0.0) bands[m].e.push_back({b, w});
+        }
+    }
+    std::vector<Band> sorted = bands;
+    std::stable_sort(sorted.begin(), sorted.end(), [](const Band& a, const Band& b) { return a.e.size() > b.e.size(); });
+    h->mpl = (c.n_mels + 31) / 32;
+    std::vector<int> meta(kMaxMpl + kMaxMpl * 32, -1);
+    int ktot = 0;
+    for (int s = 0; s < kMaxMpl; ++s) {
+        int K = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int r = s * 32 + l;
+            if (r < c.n_mels) K = std::max(K, (int)sorted[r].e.size());
+        }
+        meta[s] = K;
+        ktot += K;
+    }
+    std::vector<float2> proj((size_t)std::max(ktot, 1) * 32, make_float2(0.f, 0.f));
+    int eoff = 0;
+    for (int s = 0; s < kMaxMpl; ++s) {
+        for (int l = 0; l < 32; ++l) {
+            const int r = s * 32 + l;
+            if (r >= c.n_mels) continue;
+            meta[kMaxMpl + s * 32 + l] = sorted[r].mel;
+            for (size_t e = 0; e < sorted[r].e.size(); ++e) {
+                const int row = p400_row_of_bin(sorted[r].e[e].first);
+                float2 ent;
+                ent.x = (float)(sorted[r].e[e].second * 0.25);   // the 1/4 of the two-real-frames untangle
+                int off = 3 * row;
+                std::memcpy(&ent.y, &off, sizeof(int));
+                proj[(size_t)(eoff + (int)e) * 32 + l] = ent;
+            }
+        }
+        eoff += meta[s];
+    }
+    h->proj_ktot = std::max(ktot, 1);
+    MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * N));
+    MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
+    MS_CUDA(cudaMalloc(&h->d_proj, sizeof(float2) * proj.size()));
+    MS_CUDA(cudaMalloc(&h->d_meta, sizeof(int) * meta.size()));
+    MS_CUDA(cudaMemcpy(h->d_window, win.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_twiddle, tw.data(), sizeof(float4) * tw.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_proj, proj.data(), sizeof(float2) * proj.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice));
+    return MELSPEC_OK;
+}
+
+constexpr int kWarps = 8;
+
+template <int MPL, bool HOP160>
+int32_t launch_inst(const melspec::KParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = melspec::melspec400_kernel<kWarps, MPL, HOP160>;
+    static bool configured = false;   // per instantiation
+    static int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured || configured_dev != dev) {
+        MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+        configured_dev = dev;
+    }
+    kern<<<grid, kWarps * 32, smem, st>>>(p);
+    MS_CUDA(cudaGetLastError());
+    return MELSPEC_OK;
+}
+
+// Core launch: device pointers, explicit frame count (frames_per_clip may be smaller than num_frames(n_samples)).
+int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                      int64_t frames_per_clip, const int32_t* d_lens, float* d_out, int64_t out_clip_stride, int32_t layout,
+                      cudaStream_t st) {
+    using namespace melspec;
+    const Resolved& c = h->cfg;
+    if (n_clips == 0 || frames_per_clip == 0) return MELSPEC_OK;
+    if (n_samples > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "n_samples per clip must fit in int32");
+    constexpr int TF = kWarps * p400::FPW;
+    KParams p{};
+    p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
+    p.clip_stride = clip_stride;
+    p.out_clip_stride = out_clip_stride ? out_clip_stride : frames_per_clip * c.n_mels;
+    p.n_samples = (int)n_samples;
+    p.frames_per_clip = (int)frames_per_clip;
+    p.tiles_per_clip = (int)((frames_per_clip + TF - 1) / TF);
+    const int64_t n_tiles = (int64_t)p.tiles_per_clip * n_clips;
+    if (n_tiles > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "too many tiles for one launch");
+    p.n_tiles = (int)n_tiles;
+    p.hop = c.hop; p.n_mels = c.n_mels; p.fft_size = c.fft; p.layout = layout;
+    const bool hop160 = c.hop == 160;
+    const bool aligned_in = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (n_samples % 4 == 0) && (c.hop % 4 == 0);
+    p.bulk_in = aligned_in ? 1 : 0;
+    p.bulk_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) &&
+                 (p.out_clip_stride % 4 == 0);
+    p.window = h->d_window; p.twiddle = h->d_twiddle; p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
+    p.floor_val = (float)c.floor;
+    p.log_mul = (float)std::log10(2.0);
+    p.normalize = 1;
+    // shared-memory carve-up
+    auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    size_t off = 128;
+    p.smem_tw = (int)off; off = up(off + sizeof(float4) * p400::TWUNITS, 128);
+    p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)h->proj_ktot, 128);
+    p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
+    const size_t pcm_words = hop160 ? (size_t)(TF + 2) * p400::CS160 : (size_t)(TF - 1) * c.hop + 400;
+    p.smem_pcm0 = (int)off; off = up(off + pcm_words * 4, 128);
+    p.smem_pcm1 = (int)off; off = up(off + pcm_words * 4, 128);
+    p.smem_warp0 = (int)off;
+    p.smem_stage_off = p400::ZBYTES;
+    p.smem_warp_stride = (int)up(p400::ZBYTES + (size_t)p400::FPW * c.n_mels * 4, 128);
+    off += (size_t)p.smem_warp_stride * kWarps;
+    if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
+    const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
+    int32_t rc;
+    if (h->mpl <= 3) rc = hop160 ? launch_inst<3, true>(p, grid, off, st) : launch_inst<3, false>(p, grid, off, st);
+    else rc = hop160 ? launch_inst<4, true>(p, grid, off, st) : launch_inst<4, false>(p, grid, off, st);
+    if (rc == MELSPEC_OK) h->launches += 1;
+    return rc;
+}
+
+int32_t ensure_host_resources(melspec_handle* h, size_t pcm_bytes, size_t out_bytes) {
+    for (int i = 0; i < 3; ++i)
+        if (!h->streams[i]) MS_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    if (pcm_bytes > h->slot_pcm_cap) {
+        for (int i = 0; i < 3; ++i) {
+            if (h->d_slot_pcm[i]) cudaFree(h->d_slot_pcm[i]);
+            h->d_slot_pcm[i] = nullptr;
+            MS_CUDA(cudaMalloc(&h->d_slot_pcm[i], pcm_bytes));
+        }
+        h->slot_pcm_cap = pcm_bytes;
+    }
+    if (out_bytes > h->slot_out_cap) {
+        for (int i = 0; i < 3; ++i) {
+            if (h->d_slot_out[i]) cudaFree(h->d_slot_out[i]);
+            h->d_slot_out[i] = nullptr;
+            MS_CUDA(cudaMalloc(&h->d_slot_out[i], out_bytes));
+        }
+        h->slot_out_cap = out_bytes;
+    }
+    return MELSPEC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int32_t melspec_abi_version(void) { return MELSPEC_B200_ABI_VERSION; }
+
+const char* melspec_last_error(void) { return g_last_error.c_str(); }
+
+int32_t melspec_default_config(int32_t frontend, melspec_config* cfg) {
+    if (!cfg) return fail(MELSPEC_ERR_INVALID_ARG, "cfg is null");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->frontend = frontend;
+    cfg->hop_size = 160;
+    cfg->n_mels = 80;
+    cfg->sampling_rate = 16000.0;
+    if (frontend == MELSPEC_FRONTEND_WHISPER) {
+        cfg->fft_size = 400;
+        cfg->frame_length = 400;
+        return MELSPEC_OK;
+    }
+    if (frontend == MELSPEC_FRONTEND_KALDI) {   // FbankConfig::default(), src/fbank.rs:46-64
+        cfg->frame_length = 400;
+        cfg->fft_size = 512;
+        cfg->apply_cmn = 1;
+        cfg->use_log_fbank = 1;
+        cfg->use_power = 1;
+        cfg->preemphasis = 0.97;
+        cfg->low_freq = 20.0;
+        cfg->high_freq = 0.0;
+        cfg->energy_floor = 0.0;
+        return MELSPEC_OK;
+    }
+    return fail(MELSPEC_ERR_INVALID_ARG, "unknown frontend");
+}
+
+int32_t melspec_build_filterbank(const melspec_config* cfg, double* out, int64_t capacity) {
+    Resolved r;
+    int32_t rc = resolve(cfg, r);
+    if (rc) return rc;
+    if (!out) return fail(MELSPEC_ERR_INVALID_ARG, "out is null");
+    const int64_t need = (int64_t)r.n_mels * (r.fft / 2 + 1);
+    if (capacity < need) return fail(MELSPEC_ERR_INVALID_ARG, "capacity too small for (n_mels, fft/2+1)");
+    std::vector<double> w;
+    build_filterbank(r, w);
+    std::memcpy(out, w.data(), sizeof(double) * (size_t)need);
+    return MELSPEC_OK;
+}
+
+int64_t melspec_num_frames_cfg(const melspec_config* cfg, int64_t n_samples) {
+    Resolved r;
+    if (resolve(cfg, r)) return -1;
+    return frames_for(r, n_samples);
+}
+
+int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle** out) {
+    if (!out) return fail(MELSPEC_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    Resolved r;
+    int32_t rc = resolve(cfg, r);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MELSPEC_ERR_NO_DEVICE, "CUDA unavailable: no device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(MELSPEC_ERR_NO_DEVICE, "CUDA unavailable: device index out of range");
+    cudaDeviceProp prop;
+    MS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(MELSPEC_ERR_NO_DEVICE, "CUDA unavailable: kernels are built for sm_100a (Blackwell) only");
+    int plan = 0;
+    if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400) plan = 400;
+    else if (r.fft == 512) plan = 512;
+    if (plan != 400) return fail(MELSPEC_ERR_UNSUPPORTED, "this revision implements fft_size 400 (Whisper frontend) only");
+    MS_CUDA(cudaSetDevice(device));
+    melspec_handle* h = new (std::nothrow) melspec_handle();
+    if (!h) return fail(MELSPEC_ERR_CUDA, "out of host memory");
+    h->cfg = r;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->plan = plan;
+    build_filterbank(r, h->dense);
+    rc = build_tables(h);
+    if (rc) {
+        melspec_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MELSPEC_OK;
+}
+
+void melspec_destroy(melspec_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_window);
+    cudaFree(h->d_twiddle);
+    cudaFree(h->d_proj);
+    cudaFree(h->d_meta);
+    for (int i = 0; i < 3; ++i) {
+        if (h->d_slot_pcm[i]) cudaFree(h->d_slot_pcm[i]);
+        if (h->d_slot_out[i]) cudaFree(h->d_slot_out[i]);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    delete h;
+}
+
+int64_t melspec_num_frames(const melspec_handle* h, int64_t n_samples) { return h ? frames_for(h->cfg, n_samples) : -1; }
+
+int32_t melspec_max_frames_per_batch(const melspec_handle* h) {
+    if (!h) return 0;
+    // reference src/cuda.rs:150-155 with sizeof(cufftDoubleComplex) = 16, sizeof(f64) = 8
+    const uint64_t per = 16ull * (uint64_t)h->cfg.fft + 8ull * (uint64_t)h->cfg.n_mels;
+    const uint64_t v = std::max<uint64_t>((64ull * 1024 * 1024) / per, 1);
+    return (int32_t)std::min<uint64_t>(v, 8192);
+}
+
+int32_t melspec_n_mels(const melspec_handle* h) { return h ? h->cfg.n_mels : 0; }
+int32_t melspec_fft_size(const melspec_handle* h) { return h ? h->cfg.fft : 0; }
+int32_t melspec_hop_size(const melspec_handle* h) { return h ? h->cfg.hop : 0; }
+int64_t melspec_launch_count(const melspec_handle* h) { return h ? h->launches : 0; }
+
+int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacity) {
+    if (!h || !out) return fail(MELSPEC_ERR_INVALID_ARG, "null argument");
+    if (capacity < (int64_t)h->dense.size()) return fail(MELSPEC_ERR_INVALID_ARG, "capacity too small");
+    std::memcpy(out, h->dense.data(), sizeof(double) * h->dense.size());
+    return MELSPEC_OK;
+}
+
+int32_t melspec_compute_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride,
+                               int64_t n_samples, const int32_t* d_lens, float* d_out, int64_t out_clip_stride,
+                               int32_t layout, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (n_clips < 0 || n_samples < 0 || clip_stride < 0 || out_clip_stride < 0)
+        return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (layout != MELSPEC_LAYOUT_FRAME_MAJOR && layout != MELSPEC_LAYOUT_MEL_MAJOR)
+        return fail(MELSPEC_ERR_INVALID_ARG, "unknown layout");
+    const int64_t F = frames_for(h->cfg, n_samples);
+    if (n_clips == 0 || F == 0) return MELSPEC_OK;   // empty input => no frames, success (src/cuda.rs:91-93)
+    if (!d_pcm || !d_out) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    if (n_clips > 1 && clip_stride < n_samples) return fail(MELSPEC_ERR_INVALID_ARG, "clip_stride < n_samples");
+    MS_CUDA(cudaSetDevice(h->device));
+    return launch_device(h, d_pcm, n_clips, clip_stride, n_samples, F, d_lens, d_out, out_clip_stride, layout, (cudaStream_t)stream);
+}
+
+int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                             float* h_out, int32_t layout, int64_t* frames_out) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (n_clips < 0 || n_samples < 0 || clip_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (layout != MELSPEC_LAYOUT_FRAME_MAJOR && layout != MELSPEC_LAYOUT_MEL_MAJOR)
+        return fail(MELSPEC_ERR_INVALID_ARG, "unknown layout");
+    const int64_t F = frames_for(h->cfg, n_samples);
+    if (frames_out) *frames_out = F;
+    if (n_clips == 0 || F == 0) return MELSPEC_OK;
+    if (!h_pcm || !h_out) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    if (n_clips > 1 && clip_stride < n_samples) return fail(MELSPEC_ERR_INVALID_ARG, "clip_stride < n_samples");
+    MS_CUDA(cudaSetDevice(h->device));
+    // Clips are cut into chunks that rotate over 3 (stream, device slot) pairs, so the H2D copy of chunk i+1, the
+    // kernel of chunk i and the D2H copy of chunk i-1 overlap when the host buffers are pinned.
+    const int64_t ns4 = (n_samples + 3) / 4 * 4;   // device rows are padded to 16 bytes so the TMA path applies
+    const int64_t clip_out = F * h->cfg.n_mels;
+    const int64_t target = 32ll << 20;             // ~32 MiB of PCM per chunk
+    int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
+    per_chunk = std::min(per_chunk, n_clips);
+    if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
+    int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * clip_out * 4);
+    if (rc) return rc;
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += per_chunk, slot = (slot + 1) % 3) {
+        const int64_t nc = std::min(per_chunk, n_clips - c0);
+        cudaStream_t st = h->streams[slot];
+        if (clip_stride == ns4 || nc == 1) {
+            MS_CUDA(cudaMemcpyAsync(h->d_slot_pcm[slot], h_pcm + c0 * clip_stride, (size_t)((nc - 1) * ns4 + n_samples) * 4,
+                                    cudaMemcpyHostToDevice, st));
+        } else {
+            MS_CUDA(cudaMemcpy2DAsync(h->d_slot_pcm[slot], (size_t)ns4 * 4, h_pcm + c0 * clip_stride, (size_t)clip_stride * 4,
+                                      (size_t)n_samples * 4, (size_t)nc, cudaMemcpyHostToDevice, st));
+        }
+        rc = launch_device(h, h->d_slot_pcm[slot], nc, ns4, ns4 == n_samples ? n_samples : n_samples, F, nullptr,
+                           h->d_slot_out[slot], 0, layout, st);
+        if (rc) return rc;
+        MS_CUDA(cudaMemcpyAsync(h_out + c0 * clip_out, h->d_slot_out[slot], (size_t)nc * clip_out * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 3; ++i) MS_CUDA(cudaStreamSynchronize(h->streams[i]));
+    return MELSPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ streaming
+int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, melspec_stream** out) {
+    if (!h || !out) return fail(MELSPEC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (max_chunk_samples <= 0) return fail(MELSPEC_ERR_INVALID_ARG, "max_chunk_samples must be positive");
+    MS_CUDA(cudaSetDevice(h->device));
+    melspec_stream* s = new (std::nothrow) melspec_stream();
+    if (!s) return fail(MELSPEC_ERR_CUDA, "out of host memory");
+    s->h = h;
+    s->max_chunk = max_chunk_samples;
+    const Resolved& c = h->cfg;
+    s->cap = (max_chunk_samples + c.frame_len + c.hop + 8 + 3) / 4 * 4;
+    s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;   // c = ceil(N/H)*H - N
+    s->out_cap_frames = s->cap / c.hop + 2;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&s->d_buf[i], (size_t)s->cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_out, (size_t)s->out_cap_frames * c.n_mels * 4);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_in, (size_t)max_chunk_samples * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_out, (size_t)s->out_cap_frames * c.n_mels * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->compute_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        melspec_stream_destroy(s);
+        return fail_cuda(e, "melspec_stream_create");
+    }
+    *out = s;
+    return MELSPEC_OK;
+}
+
+int32_t melspec_stream_reset(melspec_stream* s) {
+    if (!s) return fail(MELSPEC_ERR_INVALID_ARG, "stream is null");
+    const Resolved& c = s->h->cfg;
+    s->buffered = 0;
+    s->cur = 0;
+    s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;
+    return MELSPEC_OK;
+}
+
+int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n, float* h_out, int64_t out_capacity_frames,
+                            int64_t* frames_emitted) {
+    if (frames_emitted) *frames_emitted = 0;
+    if (!s) return fail(MELSPEC_ERR_INVALID_ARG, "stream is null");
+    if (n < 0 || n > s->max_chunk) return fail(MELSPEC_ERR_INVALID_ARG, "chunk larger than max_chunk_samples");
+    if (n == 0) return MELSPEC_OK;
+    if (!h_samples) return fail(MELSPEC_ERR_INVALID_ARG, "null samples");
+    melspec_handle* h = s->h;
+    const Resolved& c = h->cfg;
+    MS_CUDA(cudaSetDevice(h->device));
+    // the first c samples of the stream never reach a frame (src/stft.rs:61-66 fed whole hops)
+    const int64_t skip = std::min(s->to_skip, n);
+    s->to_skip -= skip;
+    h_samples += skip;
+    n -= skip;
+    if (n == 0) return MELSPEC_OK;
+    const int64_t total = s->buffered + n;
+    // frames are emitted on whole-hop boundaries: frame k ends at buffer offset k*hop + N
+    const int64_t nf = total >= c.frame_len ? (total - c.frame_len) / c.hop + 1 : 0;
+    if (nf > out_capacity_frames) return fail(MELSPEC_ERR_INVALID_ARG, "out_capacity_frames too small for this push");
+    if (nf > 0 && !h_out) return fail(MELSPEC_ERR_INVALID_ARG, "null output");
+    std::memcpy(s->h_pin_in, h_samples, (size_t)n * 4);
+    float* buf = s->d_buf[s->cur];
+    MS_CUDA(cudaMemcpyAsync(buf + s->buffered, s->h_pin_in, (size_t)n * 4, cudaMemcpyHostToDevice, s->copy_stream));
+    MS_CUDA(cudaEventRecord(s->ev, s->copy_stream));
+    MS_CUDA(cudaStreamWaitEvent(s->compute_stream, s->ev, 0));
+    if (nf > 0) {
+        const int64_t ns4 = std::min<int64_t>((total + 3) / 4 * 4, s->cap);
+        int32_t rc = launch_device(h, buf, 1, s->cap, ns4, nf, nullptr, s->d_out, 0, MELSPEC_LAYOUT_FRAME_MAJOR, s->compute_stream);
+        if (rc) return rc;
+        MS_CUDA(cudaMemcpyAsync(s->h_pin_out, s->d_out, (size_t)nf * c.n_mels * 4, cudaMemcpyDeviceToHost, s->compute_stream));
+        // carry the tail (everything from the start of the next frame) into the other buffer
+        const int64_t consumed = nf * c.hop;
+        const int64_t keep = total - consumed;
+        MS_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, (size_t)keep * 4, cudaMemcpyDeviceToDevice, s->compute_stream));
+        s->cur ^= 1;
+        s->buffered = keep;
+    } else {
+        s->buffered = total;
+    }
+    MS_CUDA(cudaStreamSynchronize(s->compute_stream));
+    if (nf > 0) std::memcpy(h_out, s->h_pin_out, (size_t)nf * c.n_mels * 4);
+    if (frames_emitted) *frames_emitted = nf;
+    return MELSPEC_OK;
+}
+
+void melspec_stream_destroy(melspec_stream* s) {
+    if (!s) return;
+    cudaSetDevice(s->h->device);
+    for (int i = 0; i < 2; ++i)
+        if (s->d_buf[i]) cudaFree(s->d_buf[i]);
+    if (s->d_out) cudaFree(s->d_out);
+    if (s->h_pin_in) cudaFreeHost(s->h_pin_in);
+    if (s->h_pin_out) cudaFreeHost(s->h_pin_out);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->compute_stream) cudaStreamDestroy(s->compute_stream);
+    if (s->ev) cudaEventDestroy(s->ev);
+    delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,435 @@
+// melspec_b200 device code: the fused window -> FFT -> |X|^2 -> banded mel projection -> log -> normalise kernel.
+//
+// Written from scratch for sm_100a.  What it replaces in the reference (wavey-ai/mel-spec):
+//   host windowing/framing   src/stft.rs:147-169      (here: Hann folded into the first FFT stage, in registers)
+//   cufftExecZ2Z             src/cuda.rs:356-357      (here: 2 real frames per complex 400-point FFT, 20x20
+//                                                      Cooley-Tukey with Good-Thomas 4x5 codelets in registers)
+//   mel_kernel               src/cuda_kernels.cu:5-47 (here: sparse banded projection from shared memory)
+//   norm_mel_vec on the host src/mel.rs:458-469       (here: fused, per frame)
+// so PCM is read once from HBM (TMA bulk copies into shared memory) and mel frames are written once.
+//
+// Thread organisation ("plan 400"): a warp owns 3 complex FFTs = 6 frames per pass; 10 lanes cooperate on one FFT
+// (lane = 3*t + g: t = worker 0..9, g = FFT 0..2; lanes 30,31 shadow lane 29).  N = 400 = 20 x 20:
+//   step 1  worker t transforms columns n2 = 2t, 2t+1 (elements x[20*n1 + n2]) with a 20-point DFT -> Y[n2][k1]
+//   exchange through the warp's private shared-memory slab Z[slot(k1)][n2][g]   (only __syncwarp, no CTA barrier)
+//   step 3  worker t owns rows k1 = t and 20-t (t = 0: rows 0 and 10): twiddle, 20-point DFT over n2 -> X[k1 + 20*k2]
+//   untangle: frame A = Re, frame B = Im of the packed input, |A[k]|^2 = |Z[k] + conj Z[N-k]|^2 / 4 (the 1/4 lives
+//   in the mel weights); both Z[k] and Z[N-k] sit in the same worker by construction (rows k1 and 20-k1).
+// Bins 1..200 are produced (DC never is: every supported filterbank has a zero DC column; the host checks).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace melspec {
+
+// ------------------------------------------------------------------------------------------------ parameters
+struct KParams {
+    const float* pcm;        // [n_clips][clip_stride]
+    float* out;              // frame-major [n_clips][F][n_mels] or mel-major [n_clips][n_mels][F]
+    const int32_t* lens;     // optional per-clip valid samples
+    long long clip_stride;   // samples
+    long long out_clip_stride;  // floats
+    int n_samples;           // samples per clip (copy limit)
+    int frames_per_clip;     // F = num_frames(n_samples)
+    int tiles_per_clip;
+    int n_tiles;
+    int hop;
+    int n_mels;
+    int bulk_in;             // 1: TMA bulk loads allowed (alignment checked on the host)
+    int bulk_out;            // 1: TMA bulk stores allowed
+    int layout;              // 0 frame-major, 1 mel-major
+    int fft_size;            // for num_frames(lens[clip])
+    // constant tables (global memory, staged into shared memory once per CTA)
+    const float* window;     // [400]
+    const float4* twiddle;   // [20 slots][11 units]  (w(2i), w(2i+1)) as (re,im,re,im)
+    const float2* proj;      // [proj_ktot][32] (weight, __int_as_float(3*row))
+    const int* proj_meta;    // [kMaxMpl] K_s, then [kMaxMpl][32] mel index or -1
+    int proj_ktot;
+    float floor_val;         // 1e-10 (Whisper) — floor applied to the *unscaled* energy
+    float log_mul;           // log10(2) (Whisper)
+    int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
+    // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
+    int smem_tw, smem_proj, smem_meta, smem_pcm0, smem_pcm1, smem_warp0, smem_warp_stride, smem_stage_off;
+};
+
+constexpr int kMaxMpl = 4;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion reported as bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float warp_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // sm_100a: CREDUX.MAX.F32
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ DFT codelets
+// 5-point forward DFT, in place on (r[k*S], i[k*S]) k = 0..4.
+#define MS_C1 0.30901699437494745f
+#define MS_C2 (-0.80901699437494745f)
+#define MS_S1 0.95105651629515353f
+#define MS_S2 0.58778525229247314f
+
+__device__ __forceinline__ void dft5(float& r0, float& i0, float& r1, float& i1, float& r2, float& i2, float& r3, float& i3,
+                                     float& r4, float& i4) {
+    const float t1r = r1 + r4, t1i = i1 + i4, t2r = r2 + r3, t2i = i2 + i3;
+    const float d1r = r1 - r4, d1i = i1 - i4, d2r = r2 - r3, d2i = i2 - i3;
+    const float a1r = fmaf(MS_C2, t2r, fmaf(MS_C1, t1r, r0)), a1i = fmaf(MS_C2, t2i, fmaf(MS_C1, t1i, i0));
+    const float a2r = fmaf(MS_C1, t2r, fmaf(MS_C2, t1r, r0)), a2i = fmaf(MS_C1, t2i, fmaf(MS_C2, t1i, i0));
+    const float b1r = fmaf(MS_S2, d2r, MS_S1 * d1r), b1i = fmaf(MS_S2, d2i, MS_S1 * d1i);
+    const float b2r = fmaf(-MS_S1, d2r, MS_S2 * d1r), b2i = fmaf(-MS_S1, d2i, MS_S2 * d1i);
+    r0 = r0 + t1r + t2r;
+    i0 = i0 + t1i + t2i;
+    // y1 = a1 - i*b1, y4 = a1 + i*b1, y2 = a2 - i*b2, y3 = a2 + i*b2     (-i*(br + i bi) = bi - i br)
+    r1 = a1r + b1i; i1 = a1i - b1r;
+    r4 = a1r - b1i; i4 = a1i + b1r;
+    r2 = a2r + b2i; i2 = a2i - b2r;
+    r3 = a2r - b2i; i3 = a2i + b2r;
+}
+
+// 20-point forward DFT, natural order in and out, Good-Thomas 4x5 (no twiddles):
+//   input  n = (5a + 4b) mod 20,  output k = (5ka + 16kb) mod 20.
+__device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
+    float tr[4][5], ti[4][5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const int n0 = (4 * b) % 20, n1 = (5 + 4 * b) % 20, n2 = (10 + 4 * b) % 20, n3 = (15 + 4 * b) % 20;
+        const float s02r = xr[n0] + xr[n2], s02i = xi[n0] + xi[n2], d02r = xr[n0] - xr[n2], d02i = xi[n0] - xi[n2];
+        const float s13r = xr[n1] + xr[n3], s13i = xi[n1] + xi[n3], d13r = xr[n1] - xr[n3], d13i = xi[n1] - xi[n3];
+        tr[0][b] = s02r + s13r; ti[0][b] = s02i + s13i;
+        tr[2][b] = s02r - s13r; ti[2][b] = s02i - s13i;
+        tr[1][b] = d02r + d13i; ti[1][b] = d02i - d13r;   // d02 - i*d13
+        tr[3][b] = d02r - d13i; ti[3][b] = d02i + d13r;   // d02 + i*d13
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        dft5(tr[a][0], ti[a][0], tr[a][1], ti[a][1], tr[a][2], ti[a][2], tr[a][3], ti[a][3], tr[a][4], ti[a][4]);
+#pragma unroll
+        for (int kb = 0; kb < 5; ++kb) {
+            xr[(5 * a + 16 * kb) % 20] = tr[a][kb];
+            xi[(5 * a + 16 * kb) % 20] = ti[a][kb];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plan-400 constants
+namespace p400 {
+constexpr int N = 400;
+constexpr int FPW = 6;          // frames per warp pass (3 complex FFTs)
+constexpr int ZROW = 35;        // 16-byte units per Z slot row: 20 complex x 3 FFTs = 30 units + 5 pad  (35 = 3 mod 8)
+constexpr int ZSLOTS = 20;
+constexpr int ZBYTES = ZSLOTS * ZROW * 16;   // 11200 per warp
+constexpr int TWROW = 11;       // 16-byte units per twiddle row: 10 + 1 pad
+constexpr int TWUNITS = ZSLOTS * TWROW;
+constexpr int PAD160 = 12;      // words of padding after each 160-sample hop chunk in the staged PCM tile
+constexpr int CS160 = 160 + PAD160;
+__host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 - r; }
+}  // namespace p400
+
+// ------------------------------------------------------------------------------------------------ the fused kernel
+// NWARPS warps per CTA, one persistent CTA per SM; a tile = NWARPS*6 consecutive frames of one clip.
+template <int NWARPS, int MPL, bool HOP160>
+__global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParams p) {
+    using namespace p400;
+    constexpr int TF = NWARPS * FPW;
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int l30 = lane < 30 ? lane : 29;   // lanes 30,31 shadow lane 29 (same addresses, same values)
+    const int t = l30 / 3;                   // worker within the FFT
+    const int g = l30 - 3 * t;               // which of the warp's 3 FFTs
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);   // full[2], empty[2]
+    float4* s_tw = reinterpret_cast<float4*>(smem + p.smem_tw);
+    float2* s_proj = reinterpret_cast<float2*>(smem + p.smem_proj);
+    int* s_meta = reinterpret_cast<int*>(smem + p.smem_meta);
+    float* s_pcm[2] = {reinterpret_cast<float*>(smem + p.smem_pcm0), reinterpret_cast<float*>(smem + p.smem_pcm1)};
+    unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
+    float4* s_z = reinterpret_cast<float4*>(s_warp);          // Z exchange slab, later reused as the power slab
+    float2* s_p = reinterpret_cast<float2*>(s_warp);
+    float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
+
+    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_empty0 = smem_u32(&bars[2]);
+
+    // ---- one-time setup: tables into shared memory, barriers, per-lane window registers
+    for (int i = threadIdx.x; i < TWUNITS; i += NWARPS * 32) s_tw[i] = p.twiddle[i];
+    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) s_proj[i] = p.proj[i];
+    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) s_meta[i] = p.proj_meta[i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar_full0, 1);
+        mbar_init(bar_full0 + 8, 1);
+        mbar_init(bar_empty0, NWARPS);
+        mbar_init(bar_empty0 + 8, NWARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float w0[20], w1[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        w0[n1] = __ldg(p.window + 20 * n1 + 2 * t);
+        w1[n1] = __ldg(p.window + 20 * n1 + 2 * t + 1);
+    }
+    __syncthreads();
+
+    const int hop = HOP160 ? 160 : p.hop;
+    const int cs = HOP160 ? CS160 : p.hop;   // chunk stride in the staged tile (generic hop: dense)
+
+    // Producer (warp 0): stage the PCM of `tile` into buffer `b`.
+    auto issue_load = [&](int tile, int b) {
+        const int clip = tile / p.tiles_per_clip;
+        const int f0 = (tile - clip * p.tiles_per_clip) * TF;
+        const long long s0 = (long long)f0 * hop;
+        const int need = (TF - 1) * hop + N;
+        const long long left = (long long)p.n_samples - s0;
+        const int avail = left < need ? (int)left : need;
+        const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
+        const uint32_t bar = bar_full0 + 8 * b;
+        if (p.bulk_in) {
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
+            __syncwarp();
+            if (HOP160) {
+                const int nch = (avail + 159) / 160;
+                for (int k = lane; k < nch; k += 32) {
+                    const int n = min(160, avail - 160 * k);
+                    bulk_g2s(smem_u32(s_pcm[b] + k * CS160), src + 160 * k, (uint32_t)n * 4u, bar);
+                }
+            } else {
+                constexpr int PIECE = 4096;   // samples per bulk copy
+                const int npc = (avail + PIECE - 1) / PIECE;
+                for (int k = lane; k < npc; k += 32) {
+                    const int n = min(PIECE, avail - PIECE * k);
+                    bulk_g2s(smem_u32(s_pcm[b] + k * PIECE), src + PIECE * k, (uint32_t)n * 4u, bar);
+                }
+            }
+        } else {   // unaligned input: cooperative copy by warp 0 (same layout), then a plain arrive
+            for (int i = lane; i < avail; i += 32) {
+                const int dst = HOP160 ? i + PAD160 * (i / 160) : i;
+                s_pcm[b][dst] = __ldg(src + i);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+    };
+
+    if (warp == 0 && (int)blockIdx.x < p.n_tiles) issue_load(blockIdx.x, 0);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        if (warp == 0 && next < p.n_tiles) {
+            if (it >= 1) mbar_wait(bar_empty0 + 8 * (buf ^ 1), ((it - 1) >> 1) & 1);   // all warps done reading it
+            issue_load(next, buf ^ 1);
+        }
+
+        const int clip = tile / p.tiles_per_clip;
+        const int f0 = (tile - clip * p.tiles_per_clip) * TF;
+        int nfr = p.frames_per_clip;
+        if (p.lens) {
+            const int len = min(p.lens[clip], p.n_samples);
+            nfr = len < p.fft_size ? 0 : (len - p.fft_size) / hop + 1;
+        }
+        const int fw0 = f0 + warp * FPW;                       // first frame of this warp's pass
+        const int nvalid = max(0, min(FPW, nfr - fw0));        // warp-uniform
+
+        mbar_wait(bar_full0 + 8 * buf, (it >> 1) & 1);
+
+        // ------------------------------------------------------------------ step 1: window + column DFTs
+        float ar[20], ai[20], br[20], bi[20];   // column 2t (re = frame A, im = frame B) and column 2t+1
+        if (nvalid > 0) {
+            const float* pa = s_pcm[buf] + (warp * FPW + g) * cs + 2 * t;   // frame A = fw0 + g
+            const float* pb = pa + 3 * cs;                                   // frame B = fw0 + g + 3
+            if (nvalid == FPW) {
+#pragma unroll
+                for (int n1 = 0; n1 < 20; ++n1) {
+                    const int off = 20 * n1 + (HOP160 ? PAD160 * (n1 / 8) : 0);
+                    float2 a, b;
+                    if (HOP160) {
+                        a = *reinterpret_cast<const float2*>(pa + off);
+                        b = *reinterpret_cast<const float2*>(pb + off);
+                    } else {
+                        a = make_float2(pa[off], pa[off + 1]);
+                        b = make_float2(pb[off], pb[off + 1]);
+                    }
+                    ar[n1] = a.x * w0[n1]; ai[n1] = b.x * w0[n1];
+                    br[n1] = a.y * w1[n1]; bi[n1] = b.y * w1[n1];
+                }
+            } else {   // ragged tail: frames past the clip's last frame contribute exact zeros
+                const bool va = g < nvalid, vb = g + 3 < nvalid;
+#pragma unroll
+                for (int n1 = 0; n1 < 20; ++n1) {
+                    const int off = 20 * n1 + (HOP160 ? PAD160 * (n1 / 8) : 0);
+                    const float a0 = va ? pa[off] : 0.f, a1 = va ? pa[off + 1] : 0.f;
+                    const float b0 = vb ? pb[off] : 0.f, b1 = vb ? pb[off + 1] : 0.f;
+                    ar[n1] = a0 * w0[n1]; ai[n1] = b0 * w0[n1];
+                    br[n1] = a1 * w1[n1]; bi[n1] = b1 * w1[n1];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty0 + 8 * buf);   // this warp no longer needs the staged PCM
+        if (nvalid == 0) continue;
+
+        dft20(ar, ai);
+        dft20(br, bi);
+#pragma unroll
+        for (int k1 = 0; k1 < 20; ++k1)
+            s_z[ZROW * slot_of_row(k1) + l30] = make_float4(ar[k1], ai[k1], br[k1], bi[k1]);
+        __syncwarp();
+
+        // ------------------------------------------------------------------ step 3: twiddle + row DFTs
+        float xr[20], xi[20], yr[20], yi[20];   // rows t and 20-t (t = 0: rows 0 and 10) = slots t and 10+t
+        {
+            const float4* z1 = s_z + ZROW * t + g;
+            const float4* z2 = s_z + ZROW * (10 + t) + g;
+            const float4* tw1 = s_tw + TWROW * t;
+            const float4* tw2 = s_tw + TWROW * (10 + t);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const float4 v = z1[3 * i], w = tw1[i];
+                xr[2 * i] = v.x * w.x - v.y * w.y;     xi[2 * i] = fmaf(v.x, w.y, v.y * w.x);
+                xr[2 * i + 1] = v.z * w.z - v.w * w.w; xi[2 * i + 1] = fmaf(v.z, w.w, v.w * w.z);
+                const float4 u = z2[3 * i], q = tw2[i];
+                yr[2 * i] = u.x * q.x - u.y * q.y;     yi[2 * i] = fmaf(u.x, q.y, u.y * q.x);
+                yr[2 * i + 1] = u.z * q.z - u.w * q.w; yi[2 * i + 1] = fmaf(u.z, q.w, u.w * q.z);
+            }
+        }
+        __syncwarp();   // every lane has its rows in registers: the slab may now be overwritten with powers
+        dft20(xr, xi);
+        dft20(yr, yi);
+        {
+            // Pair slot j: generic worker (rows a, 20-a): (X[j], Y[19-j])  -> bin a+20j (j<10) or its mirror.
+            // Worker 0 (rows 0, 10): j<10: (Y[j], Y[19-j]) -> bin 10+20j;  j>=10: (X[j], X[20-j]) -> bin 20(20-j).
+            const bool t0 = (t == 0);
+#pragma unroll
+            for (int j = 0; j < 20; ++j) {
+                float ur = xr[j], ui = xi[j], vr = yr[19 - j], vi = yi[19 - j];
+                if (j < 10) { ur = t0 ? yr[j] : ur; ui = t0 ? yi[j] : ui; }
+                else        { vr = t0 ? xr[20 - j] : vr; vi = t0 ? xi[20 - j] : vi; }
+                const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
+                const float pwa = fmaf(sr, sr, di * di);   // 4|A[k]|^2
+                const float pwb = fmaf(si, si, dr * dr);   // 4|B[k]|^2
+                s_p[30 * j + l30] = make_float2(pwa, pwb);
+            }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ banded mel projection + log (+ normalise)
+        float lg[MPL][FPW];
+        float mx[FPW];
+#pragma unroll
+        for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
+        {
+            int eoff = 0;
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int K = s_meta[s];
+                float acc[FPW];
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
+                for (int e = 0; e < K; ++e) {
+                    const float2 ent = s_proj[(eoff + e) * 32 + lane];
+                    const float2* pr = s_p + __float_as_int(ent.y);
+                    const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
+                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[3] = fmaf(ent.x, p0.y, acc[3]);
+                    acc[1] = fmaf(ent.x, p1.x, acc[1]); acc[4] = fmaf(ent.x, p1.y, acc[4]);
+                    acc[2] = fmaf(ent.x, p2.x, acc[2]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
+                }
+                eoff += K;
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) {
+                    lg[s][q] = p.log_mul * __log2f(fmaxf(acc[q], p.floor_val));
+                    mx[q] = fmaxf(mx[q], lg[s][q]);
+                }
+            }
+        }
+        if (p.normalize) {
+#pragma unroll
+            for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
+        }
+
+        // ------------------------------------------------------------------ store
+        if (p.layout == 0) {
+            if (lane == 0) bulk_wait_read0();   // previous pass's bulk store has finished reading the staging rows
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q) {
+                        const float v = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                        s_stage[q * p.n_mels + mel] = v;
+                    }
+                }
+            }
+            float* dst = p.out + (long long)clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
+            const int nout = nvalid * p.n_mels;
+            if (p.bulk_out) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
+                    bulk_commit();
+                }
+            } else {
+                __syncwarp();
+                for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
+                __syncwarp();
+            }
+        } else {   // mel-major: out[clip][mel][frame]
+            float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q) {
+                        const float v = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                        if (q < nvalid) dst[(long long)mel * p.frames_per_clip + q] = v;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) bulk_wait0();   // all bulk stores of this warp have landed before the CTA retires
+}
+
+}  // namespace melspec

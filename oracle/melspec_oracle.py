@@ -1,0 +1,334 @@
+"""CPU oracle for the log-mel hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A numpy/f64 restatement of the reference's CPU algorithm (wavey-ai/mel-spec @ ac3bbdd).  Only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may
+import this module; the product path (`mel-spec_b200/`) never does and fails loudly without its
+CUDA library.
+
+Parity status: PINNED.  The reference's Rust sources cannot be built here (no cargo/rustc), and its
+FFT lives in a third-party crate that is not vendored (`rustfft = "6.2.0"`, Cargo.toml:18, caret
+requirement, no lock file); it is used strictly as an unnormalised forward DFT
+(src/stft.rs:26-27,79-80,99-110; src/fbank.rs:122-123,193-194), so `numpy.fft.fft` in f64 stands in
+for it.  `tests/test_oracle.py` pins this module against every golden vector the reference's own
+tests hold for the path (tests/golden/, copied by tests/golden/make_fixtures.py):
+
+  * rust_jfk_golden.npy   (src/rb.rs:134-179, |d| <= 1e-6)        -> whisper_mel_stream, fft 512
+  * mel_filters_80x201    (src/mel.rs:837-850, |d| <= 1e-7)       -> slaney_mel_filterbank(16000,400,80)
+  * nemo_filters_80x257   (src/mel.rs:852-871, |d| <= 1e-7)       -> slaney_mel_filterbank(16000,512,80)
+  * kaldi_fbank_jfk       (src/fbank.rs:439-535, shape + printed distance only in the reference)
+
+Every function cites the reference lines it follows.  Nothing here is copied from the reference; it
+is the same arithmetic written as array operations.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+F32_EPS = float(np.finfo(np.float32).eps)  # f32::EPSILON, src/fbank.rs:213
+
+
+# --------------------------------------------------------------------------------------------
+# Framing / STFT  (src/stft.rs)
+# --------------------------------------------------------------------------------------------
+def hann_window(fft_size: int) -> np.ndarray:
+    """Periodic Hann, f64.  src/stft.rs:141-145 (and 29-31)."""
+    i = np.arange(fft_size, dtype=np.float64)
+    return 0.5 * (1.0 - np.cos((2.0 * math.pi * i) / float(fft_size)))
+
+
+def num_frames(n_samples: int, fft_size: int, hop_size: int) -> int:
+    """src/stft.rs:153-157: 0 if too short, else (len - fft)/hop + 1 (integer division)."""
+    if n_samples < fft_size:
+        return 0
+    return (n_samples - fft_size) // hop_size + 1
+
+
+def frame_windows(samples: np.ndarray, fft_size: int, hop_size: int, window: np.ndarray) -> np.ndarray:
+    """src/stft.rs:147-169: frame k = samples[k*hop : k*hop+fft] (as f64) * window.  (F, fft) f64."""
+    samples = np.asarray(samples, dtype=np.float32)
+    nf = num_frames(samples.shape[0], fft_size, hop_size)
+    if nf == 0:
+        return np.zeros((0, fft_size), dtype=np.float64)
+    idx = (np.arange(nf) * hop_size)[:, None] + np.arange(fft_size)[None, :]
+    return samples.astype(np.float64)[idx] * window[None, :]
+
+
+def stft_all(samples: np.ndarray, fft_size: int, hop_size: int) -> np.ndarray:
+    """src/stft.rs:89-115 `compute_all_cpu`: full complex forward DFT of each windowed real frame."""
+    fr = frame_windows(samples, fft_size, hop_size, hann_window(fft_size))
+    if fr.shape[0] == 0:
+        return np.zeros((0, fft_size), dtype=np.complex128)
+    return np.fft.fft(fr, axis=1)
+
+
+# --------------------------------------------------------------------------------------------
+# Slaney mel filterbank (src/mel.rs:547-643)
+# --------------------------------------------------------------------------------------------
+def hz_to_mel(f: float, htk: bool = False) -> float:
+    """src/mel.rs:591-607."""
+    if htk:
+        return 2595.0 * math.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3.0
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = math.log(6.4) / 27.0
+    if f >= min_log_hz:
+        return min_log_mel + math.log(f / min_log_hz) / logstep
+    return f / f_sp
+
+
+def mel_to_hz(m: float, htk: bool = False) -> float:
+    """src/mel.rs:609-625."""
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3.0
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = math.log(6.4) / 27.0
+    if m >= min_log_mel:
+        return min_log_hz * math.exp(logstep * (m - min_log_mel))
+    return f_sp * m
+
+
+def mel_frequencies(n_mels: int, fmin: float, fmax: float, htk: bool = False) -> np.ndarray:
+    """src/mel.rs:631-637 (ndarray `linspace`: start + i*step, step=(end-start)/(n-1))."""
+    lo, hi = hz_to_mel(fmin, htk), hz_to_mel(fmax, htk)
+    step = (hi - lo) / (n_mels - 1) if n_mels > 1 else 0.0
+    mels = lo + step * np.arange(n_mels, dtype=np.float64)
+    return np.array([mel_to_hz(float(m), htk) for m in mels], dtype=np.float64)
+
+
+def fft_frequencies(sr: float, n_fft: int) -> np.ndarray:
+    """src/mel.rs:639-643."""
+    return (sr / n_fft) * np.arange(n_fft // 2 + 1, dtype=np.float64)
+
+
+def slaney_mel_filterbank(sr: float, n_fft: int, n_mels: int, f_min: float | None = None,
+                          f_max: float | None = None, htk: bool = False, norm: bool = True) -> np.ndarray:
+    """src/mel.rs:547-589 `mel()`: librosa-style triangles + Slaney area normalisation.  (n_mels, n_fft/2+1) f64."""
+    fftfreqs = fft_frequencies(sr, n_fft)
+    f_min = 0.0 if f_min is None else f_min
+    f_max = sr / 2.0 if f_max is None else f_max
+    mel_f = mel_frequencies(n_mels + 2, f_min, f_max, htk)
+    fdiff = mel_f[1:] - mel_f[:-1]
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, n_fft // 2 + 1), dtype=np.float64)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.minimum(np.clip(lower, 0.0, 1.0), np.clip(upper, 0.0, 1.0))
+    if norm:
+        enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+        w *= enorm[:, None]
+    return w
+
+
+def sparse_rows(filters: np.ndarray):
+    """src/mel.rs:48-71 `SparseMelFilterbank::from_dense`: per row the (bin, weight) pairs with weight != 0."""
+    rows = []
+    for r in filters:
+        nz = np.nonzero(r != 0.0)[0]
+        rows.append((nz.astype(np.int64), r[nz].astype(np.float64)))
+    return rows
+
+
+# --------------------------------------------------------------------------------------------
+# Whisper path (src/mel.rs:13-32, 148-168, 645-654; src/stft.rs:119-138)
+# --------------------------------------------------------------------------------------------
+def project_stft_log10(stft: np.ndarray, filters: np.ndarray) -> np.ndarray:
+    """src/mel.rs:148-168: E[m] = sum_b W[m,b] |X[b]|^2 with |X|^2 := 0 for b >= len/2; log10(max(E,1e-10)).
+
+    stft: (F, N) complex128; filters: (M, N/2+1) f64  ->  (F, M) f64.
+    """
+    n = stft.shape[1]
+    half = n // 2
+    power = np.zeros((stft.shape[0], filters.shape[1]), dtype=np.float64)
+    nb = min(half, filters.shape[1])
+    power[:, :nb] = stft[:, :nb].real ** 2 + stft[:, :nb].imag ** 2
+    # sparse == dense up to summation order (src/mel.rs:887-911 pins them to 1e-12); the sparse rows
+    # are contiguous bands summed in ascending bin order, which is what a row-by-row dot does here.
+    e = np.zeros((stft.shape[0], filters.shape[0]), dtype=np.float64)
+    for m, (bins, wts) in enumerate(sparse_rows(filters)):
+        acc = np.zeros(stft.shape[0], dtype=np.float64)
+        for b, w in zip(bins, wts):
+            acc = acc + w * power[:, b]
+        e[:, m] = acc
+    return np.log10(np.maximum(e, 1e-10))
+
+
+def norm_mel_f64(logmel: np.ndarray) -> np.ndarray:
+    """src/mel.rs:645-654 (== norm_mel 449-455) applied per frame: t = max - 8; (max(x,t)+4)/4."""
+    t = logmel.max(axis=-1, keepdims=True) - 8.0
+    return (np.maximum(logmel, t) + 4.0) / 4.0
+
+
+def norm_mel_vec_f32(logmel_f32: np.ndarray) -> np.ndarray:
+    """src/mel.rs:458-469: the f32 variant the reference's GPU backends apply on the host."""
+    x = np.asarray(logmel_f32, dtype=np.float32)
+    t = x.max(axis=-1, keepdims=True) - np.float32(8.0)
+    return ((np.maximum(x, t) + np.float32(4.0)) / np.float32(4.0)).astype(np.float32)
+
+
+def whisper_mel_batch(samples: np.ndarray, fft_size: int = 400, hop_size: int = 160, n_mels: int = 80,
+                      sampling_rate: float = 16000.0, filters: np.ndarray | None = None) -> np.ndarray:
+    """src/stft.rs:119-138 `Spectrogram::compute_mel_spectrogram_cpu`.  Returns (F, n_mels) f32, frame-major."""
+    if filters is None:
+        filters = slaney_mel_filterbank(sampling_rate, fft_size, n_mels)
+    st = stft_all(samples, fft_size, hop_size)
+    if st.shape[0] == 0:
+        return np.zeros((0, n_mels), dtype=np.float32)
+    return norm_mel_f64(project_stft_log10(st, filters)).astype(np.float32)
+
+
+def stream_offset(fft_size: int, hop_size: int) -> int:
+    """First-frame offset of the streaming path when fed whole hops (src/stft.rs:61-66): ceil(N/H)*H - N."""
+    return -(-fft_size // hop_size) * hop_size - fft_size
+
+
+def whisper_mel_stream(samples: np.ndarray, fft_size: int = 512, hop_size: int = 160, n_mels: int = 80,
+                       sampling_rate: float = 16000.0) -> np.ndarray:
+    """RingBuffer::maybe_mel -> Spectrogram::add -> MelSpectrogram::add fed whole hops.
+
+    Literal restatement of src/stft.rs:48-86 (shift hop_buf by one hop, append, emit once idx >= fft) driven as
+    src/rb.rs:86-121 drives it (only full hops are ever handed over; a trailing partial hop is never emitted).
+    Returns (F, n_mels) f32, frame-major.
+    """
+    samples = np.asarray(samples, dtype=np.float32)
+    window = hann_window(fft_size)
+    filters = slaney_mel_filterbank(sampling_rate, fft_size, n_mels)
+    hop_buf = np.zeros(fft_size, dtype=np.float64)
+    idx = 0
+    frames = []
+    for h in range(samples.shape[0] // hop_size):
+        chunk = samples[h * hop_size:(h + 1) * hop_size].astype(np.float64)
+        hop_buf[:fft_size - hop_size] = hop_buf[hop_size:].copy()
+        hop_buf[fft_size - hop_size:] = chunk
+        idx += hop_size
+        if idx >= fft_size:
+            frames.append(hop_buf * window)
+    if not frames:
+        return np.zeros((0, n_mels), dtype=np.float32)
+    st = np.fft.fft(np.stack(frames), axis=1)
+    return norm_mel_f64(project_stft_log10(st, filters)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# Kaldi fbank path (src/fbank.rs)
+# --------------------------------------------------------------------------------------------
+def kaldi_hz_to_mel(hz: float) -> float:
+    """src/fbank.rs:305-307."""
+    return 1127.0 * math.log(1.0 + hz / 700.0)
+
+
+def kaldi_mel_to_hz(mel: float) -> float:
+    """src/fbank.rs:311-313."""
+    return 700.0 * (math.exp(mel / 1127.0) - 1.0)
+
+
+def kaldi_mel_filterbank(sample_rate: float = 16000.0, fft_size: int = 512, num_mel_bins: int = 80,
+                         low_freq: float = 20.0, high_freq: float = 8000.0) -> np.ndarray:
+    """src/fbank.rs:253-301: edges linear in Kaldi-mel, triangles evaluated in Hz, no area norm."""
+    nb = fft_size // 2 + 1
+    lo, hi = kaldi_hz_to_mel(low_freq), kaldi_hz_to_mel(high_freq)
+    hz = [kaldi_mel_to_hz(lo + (hi - lo) * i / (num_mel_bins + 1)) for i in range(num_mel_bins + 2)]
+    w = np.zeros((num_mel_bins, nb), dtype=np.float64)
+    for m in range(num_mel_bins):
+        left, center, right = hz[m], hz[m + 1], hz[m + 2]
+        if center <= left or right <= center:
+            continue
+        for b in range(nb):
+            f = b * sample_rate / fft_size
+            if left < f <= center:
+                w[m, b] = (f - left) / (center - left)
+            elif center < f < right:
+                w[m, b] = (right - f) / (right - center)
+    return w
+
+
+def povey_window(frame_len: int = 400) -> np.ndarray:
+    """src/fbank.rs:100-105."""
+    i = np.arange(frame_len, dtype=np.float64)
+    a = 2.0 * math.pi * i / float(frame_len - 1)
+    return np.power(0.5 - 0.5 * np.cos(a), 0.85)
+
+
+def kaldi_fbank(samples: np.ndarray, sample_rate: float = 16000.0, num_mel_bins: int = 80,
+                frame_length_ms: float = 25.0, frame_shift_ms: float = 10.0, preemphasis: float = 0.97,
+                low_freq: float = 20.0, high_freq: float = 0.0, energy_floor: float = 0.0,
+                use_log_fbank: bool = True, use_power: bool = True, apply_cmn: bool = True) -> np.ndarray:
+    """src/fbank.rs:141-236 `Fbank::compute`.  Returns (T, num_mel_bins) f32."""
+    samples = np.asarray(samples, dtype=np.float32)
+    frame_len = int(round(frame_length_ms / 1000.0 * sample_rate))      # fbank.rs:68-70
+    frame_shift = int(round(frame_shift_ms / 1000.0 * sample_rate))    # fbank.rs:73-75
+    fft_size = 1 << (frame_len - 1).bit_length()                       # next_power_of_two, fbank.rs:78-81
+    if samples.shape[0] < frame_len:
+        return np.zeros((0, num_mel_bins), dtype=np.float32)
+    hf = sample_rate / 2.0 if high_freq == 0.0 else high_freq
+    filt = kaldi_mel_filterbank(sample_rate, fft_size, num_mel_bins, low_freq, hf)
+    window = povey_window(frame_len)
+    t = 1 + (samples.shape[0] - frame_len) // frame_shift
+    starts = np.arange(t) * frame_shift
+    x = samples.astype(np.float64)
+    fr = x[starts[:, None] + np.arange(frame_len)[None, :]]            # (T, L)
+    mean = fr.sum(axis=1, keepdims=True) / frame_len                   # fbank.rs:166-170 (sequential f64 sum)
+    z = fr - mean
+    if preemphasis > 0.0:                                              # fbank.rs:172-181
+        y = z.copy()
+        y[:, 1:] = z[:, 1:] - preemphasis * z[:, :-1]
+        prev = np.zeros(t, dtype=np.float64)
+        prev[1:] = x[starts[1:] - 1] - mean[1:, 0]
+        first = z[:, 0] - preemphasis * prev
+        first[0] = z[0, 0] if starts[0] == 0 else first[0]
+        y[:, 0] = first
+    else:
+        y = z
+    buf = np.zeros((t, fft_size), dtype=np.float64)
+    buf[:, :frame_len] = y * window[None, :]                           # fbank.rs:184-190
+    spec = np.fft.fft(buf, axis=1)[:, :fft_size // 2 + 1]
+    power = spec.real ** 2 + spec.imag ** 2 if use_power else np.abs(spec)   # fbank.rs:197-203
+    e = np.zeros((t, num_mel_bins), dtype=np.float64)
+    for m, (bins, wts) in enumerate(sparse_rows(filt)):               # project_power_f64, mel.rs:106-125
+        acc = np.zeros(t, dtype=np.float64)
+        for b, w in zip(bins, wts):
+            acc = acc + w * power[:, b]
+        e[:, m] = acc
+    floor = energy_floor if energy_floor > 0.0 else F32_EPS            # fbank.rs:210-214
+    e = np.maximum(e, floor)
+    if use_log_fbank:
+        e = np.log(e)
+    feats = e.astype(np.float32)                                       # fbank.rs:221
+    if apply_cmn and t > 0:                                            # fbank.rs:226-233 (f32 mean per mel)
+        feats = feats - feats.mean(axis=0, dtype=np.float32)[None, :]
+    return feats.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# Synthetic workload: the reference's own 4-tone test signal (src/cuda.rs:494-502) with per-clip
+# detune/phase, Gaussian noise, and every 8th clip silent for its first second.
+# --------------------------------------------------------------------------------------------
+def synth_clip(clip_index: int, n_samples: int, sample_rate: float = 16000.0) -> np.ndarray:
+    rng = np.random.default_rng(1234 + clip_index)
+    t = np.arange(n_samples, dtype=np.float64) / sample_rate
+    x = np.zeros(n_samples, dtype=np.float64)
+    for f0, amp in ((220.0, 0.6), (440.0, 0.25), (880.0, 0.10), (1760.0, 0.05)):
+        f = f0 * (1.0 + rng.uniform(-0.05, 0.05))
+        ph = rng.uniform(0.0, 2.0 * math.pi)
+        x += amp * np.sin(2.0 * math.pi * f * t + ph)
+    x += 0.01 * rng.standard_normal(n_samples)
+    if clip_index % 8 == 7:
+        x[:int(sample_rate)] = 0.0
+    return x.astype(np.float32)
+
+
+def reference_test_signal(n_samples: int = 16000, sample_rate: float = 16000.0) -> np.ndarray:
+    """The exact f32 signal of src/cuda.rs:494-502 (computed in f32 like the Rust code)."""
+    i = np.arange(n_samples, dtype=np.float32)
+    t = i / np.float32(sample_rate)
+    two_pi = np.float32(2.0) * np.float32(math.pi)
+    x = (np.float32(0.6) * np.sin(two_pi * np.float32(220.0) * t)
+         + np.float32(0.25) * np.sin(two_pi * np.float32(440.0) * t)
+         + np.float32(0.10) * np.sin(two_pi * np.float32(880.0) * t)
+         + np.float32(0.05) * np.sin(two_pi * np.float32(1760.0) * t))
+    return x.astype(np.float32)

@@ -1,0 +1,229 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: `pytest -m gpu`.
+
+Tolerance (BASELINE.json north_star / SURVEY §8c): Whisper path <= 1e-4 max-abs against the f64 oracle, written
+as WHISPER_TOL below.  The reference's own CUDA-vs-CPU test accepts 0.08 max / 0.01 mean (src/cuda.rs:540-544).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import melspec_oracle as o
+import oracle_c as oc
+
+pytestmark = pytest.mark.gpu
+
+WHISPER_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mel_spec_b200 as mod
+    mod.build()
+    return mod
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    assert t.cuda.is_available(), "these tests need a GPU"
+    return t
+
+
+@pytest.fixture(scope="module")
+def mel400(m):
+    h = m.CudaMelSpectrogram(400, 160, 16000.0, 80)
+    yield h
+    h.close()
+
+
+def _device_run(torch, h, pcm, lens=None, layout=0, n_mels=80):
+    x = torch.from_numpy(np.ascontiguousarray(pcm)).cuda()
+    b, s = x.shape
+    f = h.num_frames(s)
+    shape = (b, f, n_mels) if layout == 0 else (b, n_mels, f)
+    out = torch.full(shape, float("nan"), dtype=torch.float32, device="cuda")
+    dl = None if lens is None else torch.tensor(lens, dtype=torch.int32, device="cuda")
+    h.compute_device(x, b, s, s, out, d_lens=dl, layout=layout)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ reference's own cases
+def test_jfk_whisper400_vs_oracle(m, mel400, jfk):
+    # BASELINE config 1 at the Whisper configuration (fft 400): no golden file exists for fft 400,
+    # the pinned oracle is the truth.
+    got = mel400.compute_mel_spectrogram(jfk)
+    want = o.whisper_mel_batch(jfk, 400, 160, 80, 16000.0)
+    assert got.shape == want.shape == (1098, 80)
+    d = np.abs(got - want)
+    assert d.max() <= WHISPER_TOL, d.max()
+
+
+def test_reference_cuda_test_signal(m, mel400):
+    # src/cuda.rs:488-545: 1 s of 4 sines; same frame count; reference tolerance 0.08/0.01, ours 1e-4
+    x = o.reference_test_signal()
+    got = mel400.compute_mel_spectrogram(x)
+    want = o.whisper_mel_batch(x)
+    assert got.shape == want.shape == (98, 80)
+    d = np.abs(got - want)
+    assert d.max() < 0.08 and d.mean() < 0.01
+    assert d.max() <= WHISPER_TOL, d.max()
+
+
+def test_readme_shapes_and_silence(m, mel400):
+    # tests/readme_examples.rs:11-18: zeros(16000) -> non-empty, rows of 80; silence sits on the 1e-10 floor => -1.5
+    got = mel400.compute_mel_spectrogram(np.zeros(16000, np.float32))
+    assert got.shape == (98, 80)
+    assert np.all(got == -1.5)
+    got2 = m.Spectrogram.compute_mel_spectrogram(np.zeros(16000, np.float32), 400, 160, 80, 16000.0)
+    assert np.array_equal(got, got2)
+
+
+def test_empty_and_short_inputs(m, mel400):
+    # src/cuda.rs:91-93: too-short input => Ok(vec![])
+    for n in (0, 1, 399):
+        assert mel400.compute_mel_spectrogram(np.zeros(n, np.float32)).shape == (0, 80)
+    got = mel400.compute_mel_spectrogram(np.ones(400, np.float32) * 0.5)
+    want = o.whisper_mel_batch(np.ones(400, np.float32) * 0.5)
+    assert got.shape == (1, 80) and np.abs(got - want).max() <= WHISPER_TOL
+    assert mel400.max_frames_per_batch() == 8192          # src/cuda.rs:150-155 at fft 400 / 80 mels
+
+
+# ------------------------------------------------------------------------------------------ synthetic batches
+def test_synthetic_batch_vs_oracle(m, mel400, torch):
+    # BASELINE config 2 shape at a size the oracle finishes in seconds: first 8 clips of the 10 s workload
+    pcm = np.stack([o.synth_clip(i, 160000) for i in range(8)])
+    got = _device_run(torch, mel400, pcm)
+    want = oc.whisper_batch(pcm, threads=8)
+    assert got.shape == want.shape == (8, 998, 80)
+    d = np.abs(got - want)
+    assert d.max() <= WHISPER_TOL, d.max()
+    # clip 7 starts with one second of digital silence: floor frames are exactly -1.5
+    assert np.all(got[7, :90] == -1.5)
+
+
+@pytest.mark.parametrize("n", [400, 559, 560, 1199, 7919, 8080, 16000, 16001, 16002, 16003, 30000])
+def test_ragged_lengths_single_clip(m, mel400, n):
+    # every tail shape: partial last tile, partial last warp pass, odd sample counts (non-TMA path on the host side
+    # pads rows to 4 samples; the device path is exercised unaligned in test_unaligned_device_pointers)
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    got = mel400.compute_mel_spectrogram(x)
+    want = o.whisper_mel_batch(x)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= WHISPER_TOL
+
+
+def test_per_clip_lengths(m, mel400, torch):
+    rng = np.random.default_rng(5)
+    s = 20000
+    lens = [20000, 0, 399, 400, 4000, 12345, 19999, 8080]
+    pcm = (rng.standard_normal((len(lens), s)) * 0.2).astype(np.float32)
+    got = _device_run(torch, mel400, pcm, lens=lens)
+    for i, n in enumerate(lens):
+        want = o.whisper_mel_batch(pcm[i, :n])
+        f = want.shape[0]
+        assert np.abs(got[i, :f] - want).max() <= WHISPER_TOL if f else True
+        assert np.isnan(got[i, f:]).all(), "frames past a clip's own length must stay untouched"
+
+
+def test_mel_major_layout(m, mel400, torch):
+    pcm = np.stack([o.synth_clip(i, 16000) for i in range(3)])
+    a = _device_run(torch, mel400, pcm, layout=0)
+    b = _device_run(torch, mel400, pcm, layout=1)
+    assert b.shape == (3, 80, 98)
+    assert np.array_equal(a.transpose(0, 2, 1), b)
+
+
+def test_unaligned_device_pointers(m, mel400, torch):
+    # odd strides / offsets force the cooperative-copy input path and the plain-store output path
+    rng = np.random.default_rng(9)
+    s = 8003
+    pcm = (rng.standard_normal((3, s)) * 0.3).astype(np.float32)
+    buf = torch.zeros(3 * s + 1, dtype=torch.float32, device="cuda")
+    buf[1:] = torch.from_numpy(pcm.reshape(-1)).cuda()
+    f = mel400.num_frames(s)
+    outbuf = torch.full((3 * f * 80 + 1,), float("nan"), dtype=torch.float32, device="cuda")
+    mel400.compute_device(buf[1:], 3, s, s, outbuf[1:])
+    torch.cuda.synchronize()
+    got = outbuf[1:].cpu().numpy().reshape(3, f, 80)
+    want = np.stack([o.whisper_mel_batch(pcm[i]) for i in range(3)])
+    assert np.abs(got - want).max() <= WHISPER_TOL
+
+
+def test_other_mel_counts_and_hops(m, torch):
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(24000) * 0.2).astype(np.float32)
+    for n_mels, hop in ((128, 160), (40, 160), (80, 200), (80, 128)):
+        h = m.CudaMelSpectrogram(400, hop, 16000.0, n_mels)
+        got = h.compute_mel_spectrogram(x)
+        want = o.whisper_mel_batch(x, 400, hop, n_mels, 16000.0)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= WHISPER_TOL, (n_mels, hop)
+        h.close()
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_batch_properties(m, mel400, torch):
+    """BASELINE config 2 at full size (1024 x 10 s): size-independent properties instead of an oracle pass.
+    (1) a clip's features do not depend on the batch around it; (2) every clip is finite and within the normalised
+    range; (3) shifting a clip by k hops shifts its frames by k (frames are position independent); (4) spot-check
+    of clips against the oracle."""
+    base = np.stack([o.synth_clip(i, 160000) for i in range(16)])
+    pcm = np.tile(base, (64, 1))                     # 1024 clips
+    x = torch.from_numpy(pcm).cuda()
+    out = torch.empty((1024, 998, 80), dtype=torch.float32, device="cuda")
+    mel400.compute_device(x, 1024, 160000, 160000, out)
+    torch.cuda.synchronize()
+    ref = out[:16]
+    for r in range(1, 64):
+        assert torch.equal(out[16 * r:16 * (r + 1)], ref), r          # (1) bit-identical regardless of batch position
+    got = ref.cpu().numpy()
+    assert np.isfinite(got).all() and got.min() >= -1.5 and got.max() < 3.0          # (2)
+    shifted = _device_run(torch, mel400, base[:4, 160 * 7:])
+    assert np.abs(shifted - got[:4, 7:7 + shifted.shape[1]]).max() <= 2e-5                 # (3)
+    want = oc.whisper_batch(base[[0, 7, 15]], threads=3)
+    assert np.abs(got[[0, 7, 15]] - want).max() <= WHISPER_TOL                              # (4)
+
+
+def test_host_batch_api_matches_device_api(m, mel400, torch):
+    pcm = np.stack([o.synth_clip(i, 48000) for i in range(7)])
+    a = mel400.compute_host(pcm)
+    b = _device_run(torch, mel400, pcm)
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ streaming
+def test_streaming_matches_stream_oracle(m, jfk):
+    # RingBuffer semantics (src/rb.rs:86-121) at fft 400: first frame at sample 80, trailing partial hop dropped
+    rb = m.RingBuffer(m.MelConfig(400, 160, 80, 16000.0), capacity=1 << 20)
+    frames = []
+    rng = np.random.default_rng(0)
+    pos = 0
+    x = jfk[:48000 + 77]
+    while pos < x.size:
+        n = int(rng.integers(1, 1500))
+        rb.add_frame(x[pos:pos + n])
+        pos += n
+        while True:
+            fr = rb.maybe_mel()
+            if fr is None:
+                break
+            assert fr.shape == (80, 1)
+            frames.append(fr[:, 0])
+    got = np.stack(frames)
+    want = o.whisper_mel_stream(x, 400, 160, 80, 16000.0)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= WHISPER_TOL
+    rb.close()
+
+
+def test_streaming_large_chunks(m, jfk):
+    rb = m.RingBuffer(m.MelConfig(400, 160, 80, 16000.0), capacity=1 << 22, max_chunk_samples=16000)
+    rb.add_frame(jfk)
+    got = rb.drain()
+    want = o.whisper_mel_stream(jfk, 400, 160, 80, 16000.0)
+    assert got.shape == want.shape == (1098, 80)
+    assert np.abs(got - want).max() <= WHISPER_TOL
+    rb.close()

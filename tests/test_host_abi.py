@@ -1,0 +1,79 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/melspec_b200.h declares, and its
+device-free host logic (filterbanks, framing, config validation, error strings) matches the oracle.  No compute."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import melspec_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mel_spec_b200 as mod
+    mod.build()
+    return mod
+
+
+def test_library_exports_every_declared_symbol(m):
+    hdr = open(os.path.join(ROOT, "include", "melspec_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(melspec_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    L = m.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert sorted(m.EXPORTS) == declared
+    assert L.melspec_abi_version() == 1
+
+
+def test_filterbanks_match_golden_and_oracle(m, golden_dir):
+    assert np.abs(m.mel(16000, 400, 80) - np.load(os.path.join(golden_dir, "mel_filters_80x201.npy"))).max() <= 1e-7
+    assert np.abs(m.mel(16000, 512, 80) - np.load(os.path.join(golden_dir, "nemo_filters_80x257.npy"))).max() <= 1e-7
+    assert np.abs(m.mel(16000, 400, 80) - o.slaney_mel_filterbank(16000, 400, 80)).max() <= 1e-12
+    assert np.abs(m.mel(16000, 512, 128) - o.slaney_mel_filterbank(16000, 512, 128)).max() <= 1e-12
+    assert np.abs(m.kaldi_mel_filterbank() - o.kaldi_mel_filterbank()).max() <= 1e-12
+    assert m.mel(16000, 400, 80).shape == (80, 201)          # tests/readme_examples.rs:37-38
+
+
+def test_default_configs_and_frame_counts(m):
+    from mel_spec_b200._lib import MelspecConfig
+    L = m.lib()
+    cfg = MelspecConfig()
+    assert L.melspec_default_config(0, C.byref(cfg)) == 0
+    assert (cfg.fft_size, cfg.hop_size, cfg.n_mels, cfg.sampling_rate) == (400, 160, 80, 16000.0)
+    for n, want in ((0, 0), (399, 0), (400, 1), (16000, 98), (160000, 998), (480000, 2998), (57600000, 359998)):
+        assert L.melspec_num_frames_cfg(C.byref(cfg), n) == want == o.num_frames(n, 400, 160)
+    assert L.melspec_default_config(1, C.byref(cfg)) == 0
+    assert (cfg.frame_length, cfg.hop_size, cfg.preemphasis, cfg.low_freq, cfg.apply_cmn) == (400, 160, 0.97, 20.0, 1)
+    assert L.melspec_num_frames_cfg(C.byref(cfg), 176000) == 1098
+    assert L.melspec_default_config(7, C.byref(cfg)) != 0
+
+
+def test_invalid_configs_are_rejected_without_a_device(m):
+    from mel_spec_b200._lib import MelspecConfig
+    L = m.lib()
+    cfg = MelspecConfig()
+    L.melspec_default_config(0, C.byref(cfg))
+    cfg.n_mels = 0                                           # src/cuda.rs:45-49
+    buf = (C.c_double * 8)()
+    assert L.melspec_build_filterbank(C.byref(cfg), buf, 8) == 1
+    assert b"non-zero" in L.melspec_last_error()
+    cfg.n_mels = 80
+    assert L.melspec_build_filterbank(C.byref(cfg), buf, 8) == 4      # capacity too small
+    with pytest.raises(m.CudaError) as ei:
+        m.CudaMelSpectrogram(0, 160, 16000.0, 80)
+    assert ei.value.kind == "Unavailable"
+
+
+def test_no_cpu_fallback(m):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; the no-device error path is exercised on CPU boxes")
+    with pytest.raises(m.CudaError) as ei:
+        m.CudaMelSpectrogram(400, 160, 16000.0, 80)
+    assert ei.value.kind == "Unavailable" and "no CPU fallback" in str(ei.value)

@@ -1,0 +1,118 @@
+"""Pins the CPU oracle (oracle/) against every golden vector the reference's own tests hold for the hot path.
+CPU only.  Reference tests restated: src/rb.rs:134-179, src/mel.rs:786-871, 887-911, src/stft.rs:175-194,
+src/fbank.rs:354-386, 439-535, tests/readme_examples.rs:11-52."""
+import os
+
+import numpy as np
+import pytest
+
+import melspec_oracle as o
+import oracle_c as oc
+
+
+def test_stream_path_matches_rust_golden(jfk, golden_dir):
+    # src/rb.rs:134-179: fft 512 / hop 160 / 80 mels, |d| <= 1e-6 per element
+    gold = np.load(os.path.join(golden_dir, "rust_jfk_golden.npy"))
+    got = o.whisper_mel_stream(jfk, 512, 160, 80, 16000.0)
+    assert got.T.shape == gold.shape == (80, 1097)
+    assert np.abs(got.T - gold).max() <= 1e-6
+
+
+def test_batch_path_is_stream_path_shifted(jfk, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "rust_jfk_golden.npy"))
+    c = o.stream_offset(512, 160)
+    assert c == 128 and o.stream_offset(400, 160) == 80
+    got = o.whisper_mel_batch(jfk[c:], 512, 160, 80, 16000.0)
+    assert np.abs(got.T - gold).max() <= 1e-6
+
+
+def test_c_oracle_matches_rust_golden(jfk, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "rust_jfk_golden.npy"))
+    got = oc.whisper_batch(jfk[128:], 512, 160, 80, 16000.0)[0]
+    assert np.abs(got.T - gold).max() <= 1e-6
+
+
+@pytest.mark.parametrize("fft", [400, 512])
+def test_c_oracle_matches_numpy_oracle_whisper(jfk, fft):
+    a = oc.whisper_batch(jfk, fft, 160, 80, 16000.0)[0]
+    b = o.whisper_mel_batch(jfk, fft, 160, 80, 16000.0)
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= 1e-6
+
+
+def test_c_oracle_threads_agree():
+    x = np.stack([o.synth_clip(i, 16000) for i in range(5)])
+    assert np.array_equal(oc.whisper_batch(x, threads=1), oc.whisper_batch(x, threads=3))
+
+
+def test_mel_filters_golden(golden_dir):
+    # src/mel.rs:837-850 and 852-871: <= 1e-7
+    assert np.abs(o.slaney_mel_filterbank(16000, 400, 80) - np.load(os.path.join(golden_dir, "mel_filters_80x201.npy"))).max() <= 1e-7
+    assert np.abs(o.slaney_mel_filterbank(16000, 512, 80) - np.load(os.path.join(golden_dir, "nemo_filters_80x257.npy"))).max() <= 1e-7
+    assert np.abs(oc.slaney_filterbank(16000, 400, 80) - o.slaney_mel_filterbank(16000, 400, 80)).max() <= 1e-12
+    assert np.abs(oc.kaldi_filterbank() - o.kaldi_mel_filterbank()).max() <= 1e-12
+
+
+def test_mel_scale_known_answers():
+    # src/mel.rs:786-804
+    assert abs(o.hz_to_mel(60.0) - 0.9) < 1e-10
+    assert abs(o.mel_to_hz(3.0) - 200.0) < 1e-10
+    # librosa mel_frequencies(n_mels=40) end points (src/mel.rs:806-822)
+    mf = o.mel_frequencies(40, 0.0, 11025.0)
+    assert mf[0] == 0.0 and abs(mf[-1] - 11025.0) < 5e-3 and abs(mf[1] - 85.317) < 5e-3
+    ff = o.fft_frequencies(22050.0, 16)    # src/mel.rs:824-835
+    assert np.allclose(ff, [0.0, 1378.125, 2756.25, 4134.375, 5512.5, 6890.625, 8268.75, 9646.875, 11025.0])
+
+
+def test_sparse_structure():
+    # src/mel.rs:887-911: sparse == dense, nnz < 10 %
+    f = o.slaney_mel_filterbank(16000, 400, 80)
+    rows = o.sparse_rows(f)
+    nnz = sum(len(b) for b, _ in rows)
+    assert nnz * 10 < f.size
+    rng = np.random.default_rng(0)
+    p = rng.random(201)
+    dense = f @ p
+    sparse = np.array([np.dot(w, p[b]) for b, w in rows])
+    assert np.abs(dense - sparse).max() <= 1e-12
+    assert np.all(f[:, 0] == 0.0)             # DC column is zero (the CUDA kernel relies on it)
+    assert np.all(o.kaldi_mel_filterbank()[:, 0] == 0.0)
+
+
+def test_framing_rules():
+    # src/stft.rs:153-157, src/fbank.rs:147-151
+    assert o.num_frames(399, 400, 160) == 0
+    assert o.num_frames(400, 400, 160) == 1
+    assert o.num_frames(160000, 400, 160) == 998
+    assert o.num_frames(480000, 400, 160) == 2998
+    assert o.num_frames(176000, 512, 160) == 1097
+    assert o.whisper_mel_batch(np.zeros(100, np.float32)).shape == (0, 80)
+    # silence hits the 1e-10 floor: (-10 + 4)/4 = -1.5 everywhere
+    assert np.all(o.whisper_mel_batch(np.zeros(16000, np.float32)) == -1.5)
+
+
+def test_stream_gating():
+    # src/stft.rs:175-194 restated on the stream oracle: no frame until fft_size samples were seen
+    x = np.ones(160 * 2, np.float32)
+    assert o.whisper_mel_stream(x, 400, 160, 80).shape[0] == 0
+    assert o.whisper_mel_stream(np.ones(160 * 3, np.float32), 400, 160, 80).shape[0] == 1
+
+
+def test_kaldi_shape_and_distance_to_knf_golden(jfk, golden_dir):
+    # src/fbank.rs:439-535 asserts shape + finiteness + variance only; the distance is the reference's own
+    gold = np.load(os.path.join(golden_dir, "kaldi_fbank_jfk.npy")).T
+    got = o.kaldi_fbank(jfk)
+    assert got.shape == gold.shape == (1098, 80)
+    assert np.isfinite(got).all() and got.var() > 0.1
+    d = np.abs(got - gold)
+    assert d.max() < 2e-2 and d.mean() < 4e-3
+    c = oc.kaldi_batch(jfk)[0]
+    assert np.abs(c - got).max() < 1e-4      # f32 CMN mean order differs (f64 accumulate vs pairwise f32)
+    assert np.abs(oc.kaldi_batch(jfk, cmn=False)[0] - o.kaldi_fbank(jfk, apply_cmn=False)).max() <= 1e-6
+
+
+def test_kaldi_config_known_answers():
+    # src/fbank.rs:354-386
+    assert abs(o.kaldi_mel_to_hz(o.kaldi_hz_to_mel(1000.0)) - 1000.0) < 1e-9
+    assert o.kaldi_fbank(np.zeros(16000, np.float32)).shape == (98, 80)
+    assert o.kaldi_fbank(np.zeros(399, np.float32)).shape == (0, 80)
