@@ -11,12 +11,30 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+def _host_tag() -> str:
+    """-march=native code must run on the CPU it was built for: tag the build with this host's CPU flags."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()
+
+
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libmelspec_oracle.so")
     src = os.path.join(_HERE, "melspec_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        # -march=native must match the machine that runs it: always rebuild when the .so is missing/stale.
+    tagf = os.path.join(_HERE, "libmelspec_oracle.so.host")
+    tag = _host_tag()
+    try:
+        same_host = open(tagf).read().strip() == tag
+    except OSError:
+        same_host = False
+    if force or not same_host or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libmelspec_oracle.so"], stdout=subprocess.DEVNULL)
+        with open(tagf, "w") as f:
+            f.write(tag)
     return so
 
 
