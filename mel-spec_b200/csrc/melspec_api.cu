@@ -290,17 +290,16 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const Resolved& c = h->cfg;
     if (n_clips == 0 || frames_per_clip == 0) return MELSPEC_OK;
     if (n_samples > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "n_samples per clip must fit in int32");
-    constexpr int TF = kWarps * p400::FPW;
     KParams p{};
     p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
     p.clip_stride = clip_stride;
     p.out_clip_stride = out_clip_stride ? out_clip_stride : frames_per_clip * c.n_mels;
     p.n_samples = (int)n_samples;
     p.frames_per_clip = (int)frames_per_clip;
-    p.tiles_per_clip = (int)((frames_per_clip + TF - 1) / TF);
-    const int64_t n_tiles = (int64_t)p.tiles_per_clip * n_clips;
-    if (n_tiles > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "too many tiles for one launch");
-    p.n_tiles = (int)n_tiles;
+    p.wtiles_per_clip = (int)((frames_per_clip + p400::FPW - 1) / p400::FPW);
+    const int64_t n_wtiles = (int64_t)p.wtiles_per_clip * n_clips;
+    if (n_wtiles > 0x7fffffff - 148 * 64) return fail(MELSPEC_ERR_INVALID_ARG, "too many frames for one launch");
+    p.n_wtiles = (int)n_wtiles;
     p.hop = c.hop; p.n_mels = c.n_mels; p.fft_size = c.fft; p.layout = layout;
     const bool hop160 = c.hop == 160;
     const bool aligned_in = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (n_samples % 4 == 0) && (c.hop % 4 == 0);
@@ -311,20 +310,20 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.floor_val = (float)c.floor;
     p.log_mul = (float)std::log10(2.0);
     p.normalize = 1;
-    // shared-memory carve-up
+    // shared-memory carve-up: [mbarriers | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
     p.smem_tw = (int)off; off = up(off + sizeof(float4) * p400::TWUNITS, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)h->proj_ktot, 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
-    const size_t pcm_words = hop160 ? (size_t)(TF + 2) * p400::CS160 : (size_t)(TF - 1) * c.hop + 400;
-    p.smem_pcm0 = (int)off; off = up(off + pcm_words * 4, 128);
-    p.smem_pcm1 = (int)off; off = up(off + pcm_words * 4, 128);
+    const size_t pcm_words = hop160 ? (size_t)8 * p400::CS160 : (size_t)(p400::FPW - 1) * c.hop + 400;
     p.smem_warp0 = (int)off;
     p.smem_stage_off = p400::ZBYTES;
-    p.smem_warp_stride = (int)up(p400::ZBYTES + (size_t)p400::FPW * c.n_mels * 4, 128);
+    p.smem_pcm_off = (int)up(p400::ZBYTES + (size_t)p400::FPW * c.n_mels * 4, 128);
+    p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
     off += (size_t)p.smem_warp_stride * kWarps;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
+    const int64_t n_tiles = (n_wtiles + kWarps - 1) / kWarps;
     const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
     int32_t rc;
     if (h->mpl <= 3) rc = hop160 ? launch_inst<3, true>(p, grid, off, st) : launch_inst<3, false>(p, grid, off, st);

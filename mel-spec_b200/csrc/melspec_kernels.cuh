@@ -32,8 +32,8 @@ struct KParams {
     long long out_clip_stride;  // floats
     int n_samples;           // samples per clip (copy limit)
     int frames_per_clip;     // F = num_frames(n_samples)
-    int tiles_per_clip;
-    int n_tiles;
+    int wtiles_per_clip;     // warp tiles (6 frames) per clip
+    int n_wtiles;            // n_clips * wtiles_per_clip
     int hop;
     int n_mels;
     int bulk_in;             // 1: TMA bulk loads allowed (alignment checked on the host)
@@ -50,7 +50,7 @@ struct KParams {
     float log_mul;           // log10(2) (Whisper)
     int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
-    int smem_tw, smem_proj, smem_meta, smem_pcm0, smem_pcm1, smem_warp0, smem_warp_stride, smem_stage_off;
+    int smem_tw, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
 
 constexpr int kMaxMpl = 4;
@@ -164,11 +164,14 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 -
 }  // namespace p400
 
 // ------------------------------------------------------------------------------------------------ the fused kernel
-// NWARPS warps per CTA, one persistent CTA per SM; a tile = NWARPS*6 consecutive frames of one clip.
+// Warp-autonomous pipeline: every warp owns its own shared-memory slab (PCM stage, Z/power slab, output stage) and
+// its own mbarrier, walks its own sequence of "warp tiles" (6 consecutive frames of one clip) and never meets a
+// CTA-wide barrier after setup, so the warps of an SM drift into different phases and the FMA, LSU and TMA pipes
+// overlap.  The PCM stage is single-buffered: a pass reads all of its samples into registers first, so the TMA load
+// of the warp's next tile is issued right after that and lands during the rest of the pass.
 template <int NWARPS, int MPL, bool HOP160>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParams p) {
     using namespace p400;
-    constexpr int TF = NWARPS * FPW;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int warp = threadIdx.x >> 5;
@@ -177,27 +180,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     const int t = l30 / 3;                   // worker within the FFT
     const int g = l30 - 3 * t;               // which of the warp's 3 FFTs
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);   // full[2], empty[2]
-    float4* s_tw = reinterpret_cast<float4*>(smem + p.smem_tw);
-    float2* s_proj = reinterpret_cast<float2*>(smem + p.smem_proj);
-    int* s_meta = reinterpret_cast<int*>(smem + p.smem_meta);
-    float* s_pcm[2] = {reinterpret_cast<float*>(smem + p.smem_pcm0), reinterpret_cast<float*>(smem + p.smem_pcm1)};
+    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw);
+    const float2* s_proj = reinterpret_cast<const float2*>(smem + p.smem_proj);
+    const int* s_meta = reinterpret_cast<const int*>(smem + p.smem_meta);
     unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
     float4* s_z = reinterpret_cast<float4*>(s_warp);          // Z exchange slab, later reused as the power slab
     float2* s_p = reinterpret_cast<float2*>(s_warp);
     float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
-
-    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_empty0 = smem_u32(&bars[2]);
+    float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
+    const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
 
     // ---- one-time setup: tables into shared memory, barriers, per-lane window registers
-    for (int i = threadIdx.x; i < TWUNITS; i += NWARPS * 32) s_tw[i] = p.twiddle[i];
-    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) s_proj[i] = p.proj[i];
-    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) s_meta[i] = p.proj_meta[i];
-    if (threadIdx.x == 0) {
-        mbar_init(bar_full0, 1);
-        mbar_init(bar_full0 + 8, 1);
-        mbar_init(bar_empty0, NWARPS);
-        mbar_init(bar_empty0 + 8, NWARPS);
+    for (int i = threadIdx.x; i < TWUNITS; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
+    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
+    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
+    if (lane == 0) {
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     float w0[20], w1[20];
@@ -210,72 +208,54 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
     const int hop = HOP160 ? 160 : p.hop;
     const int cs = HOP160 ? CS160 : p.hop;   // chunk stride in the staged tile (generic hop: dense)
+    const int need = (FPW - 1) * hop + N;    // samples a warp tile spans
 
-    // Producer (warp 0): stage the PCM of `tile` into buffer `b`.
-    auto issue_load = [&](int tile, int b) {
-        const int clip = tile / p.tiles_per_clip;
-        const int f0 = (tile - clip * p.tiles_per_clip) * TF;
-        const long long s0 = (long long)f0 * hop;
-        const int need = (TF - 1) * hop + N;
+    // Stage the PCM of warp tile `wt` into this warp's buffer (TMA bulk copies issued by one lane).
+    auto issue_load = [&](int wt) {
+        const int clip = wt / p.wtiles_per_clip;
+        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+        const long long s0 = (long long)fw0 * hop;
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
         const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
-        const uint32_t bar = bar_full0 + 8 * b;
         if (p.bulk_in) {
-            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
-            __syncwarp();
-            if (HOP160) {
-                const int nch = (avail + 159) / 160;
-                for (int k = lane; k < nch; k += 32) {
-                    const int n = min(160, avail - 160 * k);
-                    bulk_g2s(smem_u32(s_pcm[b] + k * CS160), src + 160 * k, (uint32_t)n * 4u, bar);
-                }
-            } else {
-                constexpr int PIECE = 4096;   // samples per bulk copy
-                const int npc = (avail + PIECE - 1) / PIECE;
-                for (int k = lane; k < npc; k += 32) {
-                    const int n = min(PIECE, avail - PIECE * k);
-                    bulk_g2s(smem_u32(s_pcm[b] + k * PIECE), src + PIECE * k, (uint32_t)n * 4u, bar);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
+                if (HOP160) {
+                    for (int k = 0; 160 * k < avail; ++k)
+                        bulk_g2s(smem_u32(s_pcm + k * CS160), src + 160 * k, (uint32_t)min(160, avail - 160 * k) * 4u, bar);
+                } else {
+                    bulk_g2s(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar);
                 }
             }
-        } else {   // unaligned input: cooperative copy by warp 0 (same layout), then a plain arrive
-            for (int i = lane; i < avail; i += 32) {
-                const int dst = HOP160 ? i + PAD160 * (i / 160) : i;
-                s_pcm[b][dst] = __ldg(src + i);
-            }
+        } else {   // unaligned input: cooperative copy (same layout), then a plain arrive
+            for (int i = lane; i < avail; i += 32) s_pcm[HOP160 ? i + PAD160 * (i / 160) : i] = __ldg(src + i);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         }
     };
 
-    if (warp == 0 && (int)blockIdx.x < p.n_tiles) issue_load(blockIdx.x, 0);
+    const int wstride = gridDim.x * NWARPS;
+    int wt = blockIdx.x * NWARPS + warp;
+    if (wt < p.n_wtiles) issue_load(wt);
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int next = tile + gridDim.x;
-        if (warp == 0 && next < p.n_tiles) {
-            if (it >= 1) mbar_wait(bar_empty0 + 8 * (buf ^ 1), ((it - 1) >> 1) & 1);   // all warps done reading it
-            issue_load(next, buf ^ 1);
-        }
-
-        const int clip = tile / p.tiles_per_clip;
-        const int f0 = (tile - clip * p.tiles_per_clip) * TF;
+    for (int it = 0; wt < p.n_wtiles; wt += wstride, ++it) {
+        const int clip = wt / p.wtiles_per_clip;
+        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;   // first frame of this pass
         int nfr = p.frames_per_clip;
         if (p.lens) {
             const int len = min(p.lens[clip], p.n_samples);
             nfr = len < p.fft_size ? 0 : (len - p.fft_size) / hop + 1;
         }
-        const int fw0 = f0 + warp * FPW;                       // first frame of this warp's pass
-        const int nvalid = max(0, min(FPW, nfr - fw0));        // warp-uniform
+        const int nvalid = max(0, min(FPW, nfr - fw0));          // warp-uniform
 
-        mbar_wait(bar_full0 + 8 * buf, (it >> 1) & 1);
+        mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1: window + column DFTs
         float ar[20], ai[20], br[20], bi[20];   // column 2t (re = frame A, im = frame B) and column 2t+1
         if (nvalid > 0) {
-            const float* pa = s_pcm[buf] + (warp * FPW + g) * cs + 2 * t;   // frame A = fw0 + g
-            const float* pb = pa + 3 * cs;                                   // frame B = fw0 + g + 3
+            const float* pa = s_pcm + g * cs + 2 * t;   // frame A = fw0 + g
+            const float* pb = pa + 3 * cs;              // frame B = fw0 + g + 3
             if (nvalid == FPW) {
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
@@ -303,8 +283,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty0 + 8 * buf);   // this warp no longer needs the staged PCM
+        __syncwarp();   // every lane has consumed its samples: the stage may be refilled
+        if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
         if (nvalid == 0) continue;
 
         dft20(ar, ai);
@@ -364,6 +344,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 float acc[FPW];
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
+#pragma unroll 2
                 for (int e = 0; e < K; ++e) {
                     const float2 ent = s_proj[(eoff + e) * 32 + lane];
                     const float2* pr = s_p + __float_as_int(ent.y);
@@ -427,6 +408,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     }
                 }
             }
+            __syncwarp();
         }
     }
     if (lane == 0) bulk_wait0();   // all bulk stores of this warp have landed before the CTA retires
