@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -143,11 +144,13 @@ struct melspec_handle {
     int plan = 0;   // 400 or 512
     std::vector<double> dense;   // (n_mels, fft/2+1)
     // device tables
-    float* d_window = nullptr;
+    float2* d_window = nullptr;
     float4* d_twiddle = nullptr;
+    float2* d_rot10 = nullptr;
     float2* d_proj = nullptr;
     int* d_meta = nullptr;
     int proj_ktot = 0;
+    int proj_wavefront_cost = 0;   // half-warp wavefronts per LDS.64 of the projection loop, summed over entries (ideal: 2 per entry)
     int mpl = 0;
     // host-path resources (lazily created)
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -192,17 +195,22 @@ int32_t build_tables(melspec_handle* h) {
     if (h->plan != 400) return fail(MELSPEC_ERR_UNSUPPORTED, "only the 400-point plan is built in this revision");
     const int N = 400, nb = N / 2 + 1;
     // window: periodic Hann (reference src/stft.rs:141-145), computed in f64, rounded once
-    std::vector<float> win(N);
-    for (int i = 0; i < N; ++i) win[i] = (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N)));
-    // twiddles W_400^(row*n2), laid out [slot][unit] with unit i = (n2 = 2i, 2i+1)
-    std::vector<float4> tw((size_t)p400::TWUNITS, make_float4(0, 0, 0, 0));
-    for (int row = 0; row < 20; ++row) {
-        const int slot = p400::slot_of_row(row);
+    std::vector<float2> win(200);   // [n1][t] = (w[20 n1 + 2t], w[20 n1 + 2t + 1])
+    auto hann = [&](int i) { return (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N))); };
+    for (int n1 = 0; n1 < 20; ++n1)
+        for (int t = 0; t < 10; ++t) win[n1 * 10 + t] = make_float2(hann(20 * n1 + 2 * t), hann(20 * n1 + 2 * t + 1));
+    // per-worker twiddles W_400^(t*n2) (kept in registers by the kernel) and the row-10 pre-rotation W_40^(-c)
+    std::vector<float4> tw(100);   // [i][t] = (W^(t*2i), W^(t*(2i+1)))
+    std::vector<float2> rot(20);
+    for (int t = 0; t < 10; ++t)
         for (int i = 0; i < 10; ++i) {
-            const double a0 = -2.0 * M_PI * (double)((row * (2 * i)) % N) / (double)N;
-            const double a1 = -2.0 * M_PI * (double)((row * (2 * i + 1)) % N) / (double)N;
-            tw[(size_t)slot * p400::TWROW + i] = make_float4((float)std::cos(a0), (float)std::sin(a0), (float)std::cos(a1), (float)std::sin(a1));
+            const double a0 = -2.0 * M_PI * (double)((t * 2 * i) % N) / (double)N;
+            const double a1 = -2.0 * M_PI * (double)((t * (2 * i + 1)) % N) / (double)N;
+            tw[i * 10 + t] = make_float4((float)std::cos(a0), (float)std::sin(a0), (float)std::cos(a1), (float)std::sin(a1));
         }
+    for (int c2 = 0; c2 < 20; ++c2) {
+        const double a = 2.0 * M_PI * (double)c2 / 40.0;
+        rot[c2] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     // sparse banded filterbank -> per-lane projection program
     for (int m = 0; m < c.n_mels; ++m)
@@ -233,41 +241,111 @@ int32_t build_tables(melspec_handle* h) {
         meta[s] = K;
         ktot += K;
     }
+    // The kernel's projection loop reads, per entry, three consecutive float2 of one power-slab row per lane
+    // (LDS.64, processed per half-warp): it is bank-conflict free when the 16 lanes of a half-warp hit rows that
+    // differ mod 16.  Which lane of a slot owns which mel, the order of a mel's entries and the rows that padding
+    // entries point at are all free, so a small deterministic hill-climb minimises the number of wavefronts.
     std::vector<float2> proj((size_t)std::max(ktot, 1) * 32, make_float2(0.f, 0.f));
     int eoff = 0;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&rng](int n) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        return (int)((rng >> 33) % (uint64_t)n);
+    };
     for (int s = 0; s < kMaxMpl; ++s) {
+        const int K = meta[s];
+        if (K == 0) {   // mels without a single in-range bin still get their (floor-valued) output row
+            for (int l = 0; l < 32; ++l)
+                if (s * 32 + l < c.n_mels) meta[kMaxMpl + s * 32 + l] = sorted[s * 32 + l].mel;
+            continue;
+        }
+        struct Ent { int row; float w; };
+        std::vector<std::vector<Ent>> lanes(32);
+        std::vector<int> lane_mel(32, -1);
         for (int l = 0; l < 32; ++l) {
             const int r = s * 32 + l;
             if (r >= c.n_mels) continue;
-            meta[kMaxMpl + s * 32 + l] = sorted[r].mel;
-            for (size_t e = 0; e < sorted[r].e.size(); ++e) {
-                const int row = p400_row_of_bin(sorted[r].e[e].first);
-                float2 ent;
-                ent.x = (float)(sorted[r].e[e].second * 0.25);   // the 1/4 of the two-real-frames untangle
-                int off = 3 * row;
-                std::memcpy(&ent.y, &off, sizeof(int));
-                proj[(size_t)(eoff + (int)e) * 32 + l] = ent;
+            lane_mel[l] = sorted[r].mel;
+            for (auto& e : sorted[r].e) lanes[l].push_back({p400_row_of_bin(e.first), (float)(e.second * 0.25)});
+        }
+        auto cost = [&]() {
+            int tot = 0;
+            for (int e = 0; e < K; ++e)
+                for (int hw = 0; hw < 2; ++hw) {
+                    int cnt[16] = {0}, mxc = 0;
+                    for (int l = 16 * hw; l < 16 * hw + 16; ++l)
+                        if (e < (int)lanes[l].size()) mxc = std::max(mxc, ++cnt[lanes[l][e].row & 15]);
+                    tot += mxc;
+                }
+            return tot;
+        };
+        int best = cost();
+        for (int iter = 0; iter < 6000 && best > 0; ++iter) {
+            const int kind = rnd(3), a = rnd(32), b = rnd(32);
+            if (kind == 0) {   // swap the mels of two lanes
+                if (a == b) continue;
+                std::swap(lanes[a], lanes[b]); std::swap(lane_mel[a], lane_mel[b]);
+                const int cst = cost();
+                if (cst <= best) best = cst; else { std::swap(lanes[a], lanes[b]); std::swap(lane_mel[a], lane_mel[b]); }
+            } else {           // swap two entries inside one lane (summation order is irrelevant at 1e-7)
+                if (lanes[a].size() < 2) continue;
+                const int i = rnd((int)lanes[a].size()), j = rnd((int)lanes[a].size());
+                if (i == j) continue;
+                std::swap(lanes[a][i], lanes[a][j]);
+                const int cst = cost();
+                if (cst <= best) best = cst; else std::swap(lanes[a][i], lanes[a][j]);
             }
         }
-        eoff += meta[s];
+        for (int l = 0; l < 32; ++l) {
+            meta[kMaxMpl + s * 32 + l] = lane_mel[l];
+            for (int e = 0; e < K; ++e) {
+                float2 ent;
+                int off;
+                if (e < (int)lanes[l].size()) { ent.x = lanes[l][e].w; off = 3 * lanes[l][e].row; }
+                else {   // padding: zero weight, pointed at a row whose bank group nobody in this half-warp uses
+                    int cnt[16] = {0};
+                    for (int l2 = 16 * (l / 16); l2 < 16 * (l / 16) + 16; ++l2)
+                        if (e < (int)lanes[l2].size()) cnt[lanes[l2][e].row & 15]++;
+                    int pick = 0;
+                    for (int r = 1; r < 16; ++r) if (cnt[r] < cnt[pick]) pick = r;
+                    lanes[l].push_back({pick, 0.f});
+                    ent.x = 0.f; off = 3 * pick;
+                }
+                std::memcpy(&ent.y, &off, sizeof(int));
+                proj[(size_t)(eoff + e) * 32 + l] = ent;
+            }
+        }
+        h->proj_wavefront_cost += best;
+        eoff += K;
     }
     h->proj_ktot = std::max(ktot, 1);
-    MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * N));
+    MS_CUDA(cudaMalloc(&h->d_window, sizeof(float2) * win.size()));
     MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
+    MS_CUDA(cudaMalloc(&h->d_rot10, sizeof(float2) * rot.size()));
     MS_CUDA(cudaMalloc(&h->d_proj, sizeof(float2) * proj.size()));
     MS_CUDA(cudaMalloc(&h->d_meta, sizeof(int) * meta.size()));
-    MS_CUDA(cudaMemcpy(h->d_window, win.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_window, win.data(), sizeof(float2) * win.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_twiddle, tw.data(), sizeof(float4) * tw.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_rot10, rot.data(), sizeof(float2) * rot.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_proj, proj.data(), sizeof(float2) * proj.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice));
     return MELSPEC_OK;
 }
 
-constexpr int kWarps = 8;
+// Warps per CTA (one persistent CTA per SM).  12 is the default (168 registers/thread); MELSPEC_WARPS=8|10|12 selects
+// another build of the same kernel for tuning.
+int warps_per_cta() {
+    static int w = [] {
+        const char* e = std::getenv("MELSPEC_WARPS");
+        const int v = e ? std::atoi(e) : 12;
+        return (v == 8 || v == 10 || v == 12) ? v : 12;
+    }();
+    return w;
+}
 
-template <int MPL, bool HOP160>
+template <int NW, int MPL, bool HOP160>
 int32_t launch_inst(const melspec::KParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = melspec::melspec400_kernel<kWarps, MPL, HOP160>;
+    auto kern = melspec::melspec400_kernel<NW, MPL, HOP160>;
     static bool configured = false;   // per instantiation
     static int configured_dev = -1;
     int dev = 0;
@@ -277,7 +355,7 @@ int32_t launch_inst(const melspec::KParams& p, int grid, size_t smem, cudaStream
         configured = true;
         configured_dev = dev;
     }
-    kern<<<grid, kWarps * 32, smem, st>>>(p);
+    kern<<<grid, NW * 32, smem, st>>>(p);
     MS_CUDA(cudaGetLastError());
     return MELSPEC_OK;
 }
@@ -306,28 +384,34 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.bulk_in = aligned_in ? 1 : 0;
     p.bulk_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) &&
                  (p.out_clip_stride % 4 == 0);
-    p.window = h->d_window; p.twiddle = h->d_twiddle; p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
+    p.window = h->d_window; p.twiddle = h->d_twiddle; p.rot10 = h->d_rot10; p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
     p.log_mul = (float)std::log10(2.0);
     p.normalize = 1;
     // shared-memory carve-up: [mbarriers | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
-    p.smem_tw = (int)off; off = up(off + sizeof(float4) * p400::TWUNITS, 128);
+    p.smem_win = (int)off; off = up(off + sizeof(float2) * 200, 128);
+    p.smem_tw = (int)off; off = up(off + sizeof(float4) * 100, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)h->proj_ktot, 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
-    const size_t pcm_words = hop160 ? (size_t)8 * p400::CS160 : (size_t)(p400::FPW - 1) * c.hop + 400;
+    const size_t pcm_words = hop160 ? (size_t)p400::NCHUNK * p400::CS320 : (size_t)(p400::FPW - 1) * c.hop + 400;
     p.smem_warp0 = (int)off;
-    p.smem_stage_off = p400::ZBYTES;
-    p.smem_pcm_off = (int)up(p400::ZBYTES + (size_t)p400::FPW * c.n_mels * 4, 128);
+    static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
+    p.smem_stage_off = p400::PBYTES;
+    p.smem_pcm_off = (int)up(p400::ZBYTES, 128);
     p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
-    off += (size_t)p.smem_warp_stride * kWarps;
+    const int nw = warps_per_cta();
+    off += (size_t)p.smem_warp_stride * nw;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
-    const int64_t n_tiles = (n_wtiles + kWarps - 1) / kWarps;
+    const int64_t n_tiles = (n_wtiles + nw - 1) / nw;
     const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
     int32_t rc;
-    if (h->mpl <= 3) rc = hop160 ? launch_inst<3, true>(p, grid, off, st) : launch_inst<3, false>(p, grid, off, st);
-    else rc = hop160 ? launch_inst<4, true>(p, grid, off, st) : launch_inst<4, false>(p, grid, off, st);
+#define MS_DISPATCH(NW)                                                                                              \
+    (h->mpl <= 3 ? (hop160 ? launch_inst<NW, 3, true>(p, grid, off, st) : launch_inst<NW, 3, false>(p, grid, off, st)) \
+                 : (hop160 ? launch_inst<NW, 4, true>(p, grid, off, st) : launch_inst<NW, 4, false>(p, grid, off, st)))
+    rc = nw == 8 ? MS_DISPATCH(8) : nw == 10 ? MS_DISPATCH(10) : MS_DISPATCH(12);
+#undef MS_DISPATCH
     if (rc == MELSPEC_OK) h->launches += 1;
     return rc;
 }
@@ -452,6 +536,7 @@ void melspec_destroy(melspec_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_window);
     cudaFree(h->d_twiddle);
+    cudaFree(h->d_rot10);
     cudaFree(h->d_proj);
     cudaFree(h->d_meta);
     for (int i = 0; i < 3; ++i) {

@@ -12,7 +12,10 @@
 // (lane = 3*t + g: t = worker 0..9, g = FFT 0..2; lanes 30,31 shadow lane 29).  N = 400 = 20 x 20:
 //   step 1  worker t transforms columns n2 = 2t, 2t+1 (elements x[20*n1 + n2]) with a 20-point DFT -> Y[n2][k1]
 //   exchange through the warp's private shared-memory slab Z[slot(k1)][n2][g]   (only __syncwarp, no CTA barrier)
-//   step 3  worker t owns rows k1 = t and 20-t (t = 0: rows 0 and 10): twiddle, 20-point DFT over n2 -> X[k1 + 20*k2]
+//   step 3  worker t owns rows k1 = t and 20-t (t = 0: rows 0 and 10): twiddle, 20-point DFT over n2 -> X[k1 + 20*k2].
+//           The twiddles W_400^(t*n2) live in registers; row 20-t uses their conjugates and a rotation of the DFT
+//           outputs by one (W_400^((20-t)n2) = W_20^n2 * conj W_400^(t*n2)); row 10 is pre-rotated by W_40^(-n2) when
+//           it is written, which makes worker 0 (twiddle 1) follow exactly the same code.
 //   untangle: frame A = Re, frame B = Im of the packed input, |A[k]|^2 = |Z[k] + conj Z[N-k]|^2 / 4 (the 1/4 lives
 //   in the mel weights); both Z[k] and Z[N-k] sit in the same worker by construction (rows k1 and 20-k1).
 // Bins 1..200 are produced (DC never is: every supported filterbank has a zero DC column; the host checks).
@@ -41,8 +44,10 @@ struct KParams {
     int layout;              // 0 frame-major, 1 mel-major
     int fft_size;            // for num_frames(lens[clip])
     // constant tables (global memory, staged into shared memory once per CTA)
-    const float* window;     // [400]
-    const float4* twiddle;   // [20 slots][11 units]  (w(2i), w(2i+1)) as (re,im,re,im)
+    const float2* window;    // [20 n1][10 workers]  Hann window of samples 20*n1 + 2t and 20*n1 + 2t + 1
+    const float4* twiddle;   // [10 i][10 workers]  W_400^(t*2i), W_400^(t*(2i+1)) as (re,im,re,im); row 20-t uses the
+                             // conjugates + an output rotation
+    const float2* rot10;     // [20]  W_40^(-c): row 10 is pre-rotated on the write side so worker 0 fits the same scheme
     const float2* proj;      // [proj_ktot][32] (weight, __int_as_float(3*row))
     const int* proj_meta;    // [kMaxMpl] K_s, then [kMaxMpl][32] mel index or -1
     int proj_ktot;
@@ -50,7 +55,7 @@ struct KParams {
     float log_mul;           // log10(2) (Whisper)
     int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
-    int smem_tw, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
+    int smem_win, smem_tw, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
 
 constexpr int kMaxMpl = 4;
@@ -156,10 +161,12 @@ constexpr int FPW = 6;          // frames per warp pass (3 complex FFTs)
 constexpr int ZROW = 35;        // 16-byte units per Z slot row: 20 complex x 3 FFTs = 30 units + 5 pad  (35 = 3 mod 8)
 constexpr int ZSLOTS = 20;
 constexpr int ZBYTES = ZSLOTS * ZROW * 16;   // 11200 per warp
-constexpr int TWROW = 11;       // 16-byte units per twiddle row: 10 + 1 pad
-constexpr int TWUNITS = ZSLOTS * TWROW;
-constexpr int PAD160 = 12;      // words of padding after each 160-sample hop chunk in the staged PCM tile
-constexpr int CS160 = 160 + PAD160;
+constexpr int PBYTES = 200 * 3 * 8;          // power slab: 200 rows x 3 FFTs x (frame A, frame B), reuses the Z slab
+constexpr int STAGE_MAX = ZBYTES - PBYTES;   // room for the 6 x n_mels output rows behind the power rows
+constexpr int CHUNK = 320;      // samples per TMA bulk copy (two hops of 160)
+constexpr int PAD320 = 12;      // words of padding after each chunk in the staged PCM tile (bank spreading)
+constexpr int CS320 = CHUNK + PAD320;
+constexpr int NCHUNK = 4;       // a warp tile spans 5*160 + 400 = 1200 samples = 3.75 chunks
 __host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 - r; }
 }  // namespace p400
 
@@ -178,9 +185,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     const int lane = threadIdx.x & 31;
     const int l30 = lane < 30 ? lane : 29;   // lanes 30,31 shadow lane 29 (same addresses, same values)
     const int t = l30 / 3;                   // worker within the FFT
-    const int g = l30 - 3 * t;               // which of the warp's 3 FFTs
+    const int g = l30 - 3 * t;               // which of the warp's 3 FFTs: frames fw0 + 2g (re) and fw0 + 2g + 1 (im)
 
-    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw);
     const float2* s_proj = reinterpret_cast<const float2*>(smem + p.smem_proj);
     const int* s_meta = reinterpret_cast<const int*>(smem + p.smem_meta);
     unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
@@ -190,24 +196,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
 
-    // ---- one-time setup: tables into shared memory, barriers, per-lane window registers
-    for (int i = threadIdx.x; i < TWUNITS; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
+    // ---- one-time setup: tables into shared memory, barriers, per-lane window / twiddle registers
     for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
     for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    float w0[20], w1[20];
-#pragma unroll
-    for (int n1 = 0; n1 < 20; ++n1) {
-        w0[n1] = __ldg(p.window + 20 * n1 + 2 * t);
-        w1[n1] = __ldg(p.window + 20 * n1 + 2 * t + 1);
-    }
+    // window and twiddle tables are lane-dependent (10 distinct rows, shared by the warp's 3 FFTs); they are read
+    // from shared memory each pass instead of pinning 78 registers, which is what lets 12 warps live on an SM
+    for (int i = threadIdx.x; i < 200; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_win)[i] = p.window[i];
+    for (int i = threadIdx.x; i < 100; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
+    const float2* s_win = reinterpret_cast<const float2*>(smem + p.smem_win) + t;
+    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
+    const float2 r10a = __ldg(p.rot10 + 2 * t), r10b = __ldg(p.rot10 + 2 * t + 1);
     __syncthreads();
 
     const int hop = HOP160 ? 160 : p.hop;
-    const int cs = HOP160 ? CS160 : p.hop;   // chunk stride in the staged tile (generic hop: dense)
     const int need = (FPW - 1) * hop + N;    // samples a warp tile spans
 
     // Stage the PCM of warp tile `wt` into this warp's buffer (TMA bulk copies issued by one lane).
@@ -222,14 +227,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
                 if (HOP160) {
-                    for (int k = 0; 160 * k < avail; ++k)
-                        bulk_g2s(smem_u32(s_pcm + k * CS160), src + 160 * k, (uint32_t)min(160, avail - 160 * k) * 4u, bar);
+#pragma unroll
+                    for (int k = 0; k < NCHUNK; ++k)
+                        if (CHUNK * k < avail)
+                            bulk_g2s(smem_u32(s_pcm + k * CS320), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar);
                 } else {
                     bulk_g2s(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar);
                 }
             }
         } else {   // unaligned input: cooperative copy (same layout), then a plain arrive
-            for (int i = lane; i < avail; i += 32) s_pcm[HOP160 ? i + PAD160 * (i / 160) : i] = __ldg(src + i);
+            for (int i = lane; i < avail; i += 32) s_pcm[HOP160 ? i + PAD320 * (i / CHUNK) : i] = __ldg(src + i);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         }
@@ -254,32 +261,39 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         // ------------------------------------------------------------------ step 1: window + column DFTs
         float ar[20], ai[20], br[20], bi[20];   // column 2t (re = frame A, im = frame B) and column 2t+1
         if (nvalid > 0) {
-            const float* pa = s_pcm + g * cs + 2 * t;   // frame A = fw0 + g
-            const float* pb = pa + 3 * cs;              // frame B = fw0 + g + 3
-            if (nvalid == FPW) {
+            const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
+            if (HOP160) {
+                // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
+                // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16)
+                const float* px = s_pcm + g * CS320 + 2 * t;
+                float2 x[28];
 #pragma unroll
-                for (int n1 = 0; n1 < 20; ++n1) {
-                    const int off = 20 * n1 + (HOP160 ? PAD160 * (n1 / 8) : 0);
-                    float2 a, b;
-                    if (HOP160) {
-                        a = *reinterpret_cast<const float2*>(pa + off);
-                        b = *reinterpret_cast<const float2*>(pb + off);
-                    } else {
-                        a = make_float2(pa[off], pa[off + 1]);
-                        b = make_float2(pb[off], pb[off + 1]);
+                for (int m = 0; m < 28; ++m) x[m] = *reinterpret_cast<const float2*>(px + 20 * m + (m >= 16 ? PAD320 : 0));
+                if (nvalid == FPW) {
+#pragma unroll
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        const float2 w = s_win[10 * n1];
+                        ar[n1] = x[n1].x * w.x; ai[n1] = x[n1 + 8].x * w.x;
+                        br[n1] = x[n1].y * w.y; bi[n1] = x[n1 + 8].y * w.y;
                     }
-                    ar[n1] = a.x * w0[n1]; ai[n1] = b.x * w0[n1];
-                    br[n1] = a.y * w1[n1]; bi[n1] = b.y * w1[n1];
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 20; ++n1) {
+                        const float2 w = s_win[10 * n1];
+                        ar[n1] = va ? x[n1].x * w.x : 0.f; ai[n1] = vb ? x[n1 + 8].x * w.x : 0.f;
+                        br[n1] = va ? x[n1].y * w.y : 0.f; bi[n1] = vb ? x[n1 + 8].y * w.y : 0.f;
+                    }
                 }
-            } else {   // ragged tail: frames past the clip's last frame contribute exact zeros
-                const bool va = g < nvalid, vb = g + 3 < nvalid;
+            } else {
+                const float* pa = s_pcm + 2 * g * hop + 2 * t;
+                const float* pb = pa + hop;
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
-                    const int off = 20 * n1 + (HOP160 ? PAD160 * (n1 / 8) : 0);
-                    const float a0 = va ? pa[off] : 0.f, a1 = va ? pa[off + 1] : 0.f;
-                    const float b0 = vb ? pb[off] : 0.f, b1 = vb ? pb[off + 1] : 0.f;
-                    ar[n1] = a0 * w0[n1]; ai[n1] = b0 * w0[n1];
-                    br[n1] = a1 * w1[n1]; bi[n1] = b1 * w1[n1];
+                    const float2 w = s_win[10 * n1];
+                    const float a0 = va ? pa[20 * n1] : 0.f, a1 = va ? pa[20 * n1 + 1] : 0.f;
+                    const float b0 = vb ? pb[20 * n1] : 0.f, b1 = vb ? pb[20 * n1 + 1] : 0.f;
+                    ar[n1] = a0 * w.x; ai[n1] = b0 * w.x;
+                    br[n1] = a1 * w.y; bi[n1] = b1 * w.y;
                 }
             }
         }
@@ -289,6 +303,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
         dft20(ar, ai);
         dft20(br, bi);
+        {   // row 10 carries an extra W_40^(-c) so that worker 0 can treat it like a "row 20 - t"
+            const float r = ar[10] * r10a.x - ai[10] * r10a.y, i = fmaf(ar[10], r10a.y, ai[10] * r10a.x);
+            ar[10] = r; ai[10] = i;
+            const float r2 = br[10] * r10b.x - bi[10] * r10b.y, i2 = fmaf(br[10], r10b.y, bi[10] * r10b.x);
+            br[10] = r2; bi[10] = i2;
+        }
+        if (lane == 0) bulk_wait_read0();   // the previous pass's bulk store (its rows live inside this slab) is done
+        __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 20; ++k1)
             s_z[ZROW * slot_of_row(k1) + l30] = make_float4(ar[k1], ai[k1], br[k1], bi[k1]);
@@ -299,29 +321,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         {
             const float4* z1 = s_z + ZROW * t + g;
             const float4* z2 = s_z + ZROW * (10 + t) + g;
-            const float4* tw1 = s_tw + TWROW * t;
-            const float4* tw2 = s_tw + TWROW * (10 + t);
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
-                const float4 v = z1[3 * i], w = tw1[i];
-                xr[2 * i] = v.x * w.x - v.y * w.y;     xi[2 * i] = fmaf(v.x, w.y, v.y * w.x);
-                xr[2 * i + 1] = v.z * w.z - v.w * w.w; xi[2 * i + 1] = fmaf(v.z, w.w, v.w * w.z);
-                const float4 u = z2[3 * i], q = tw2[i];
-                yr[2 * i] = u.x * q.x - u.y * q.y;     yi[2 * i] = fmaf(u.x, q.y, u.y * q.x);
-                yr[2 * i + 1] = u.z * q.z - u.w * q.w; yi[2 * i + 1] = fmaf(u.z, q.w, u.w * q.z);
+                const float4 v = z1[3 * i], u = z2[3 * i], w = s_tw[10 * i];
+                const int n = 2 * i, m = 2 * i + 1;
+                xr[n] = v.x * w.x - v.y * w.y;  xi[n] = fmaf(v.x, w.y, v.y * w.x);
+                xr[m] = v.z * w.z - v.w * w.w;  xi[m] = fmaf(v.z, w.w, v.w * w.z);
+                yr[n] = fmaf(u.x, w.x, u.y * w.y);  yi[n] = u.y * w.x - u.x * w.y;   // * conj(tw)
+                yr[m] = fmaf(u.z, w.z, u.w * w.w);  yi[m] = u.w * w.z - u.z * w.w;
             }
         }
         __syncwarp();   // every lane has its rows in registers: the slab may now be overwritten with powers
         dft20(xr, xi);
-        dft20(yr, yi);
+        dft20(yr, yi);   // D; the row's spectrum is Y[m] = D[(m + 1) % 20]
         {
             // Pair slot j: generic worker (rows a, 20-a): (X[j], Y[19-j])  -> bin a+20j (j<10) or its mirror.
             // Worker 0 (rows 0, 10): j<10: (Y[j], Y[19-j]) -> bin 10+20j;  j>=10: (X[j], X[20-j]) -> bin 20(20-j).
             const bool t0 = (t == 0);
 #pragma unroll
             for (int j = 0; j < 20; ++j) {
-                float ur = xr[j], ui = xi[j], vr = yr[19 - j], vi = yi[19 - j];
-                if (j < 10) { ur = t0 ? yr[j] : ur; ui = t0 ? yi[j] : ui; }
+                float ur = xr[j], ui = xi[j], vr = yr[(20 - j) % 20], vi = yi[(20 - j) % 20];
+                if (j < 10) { ur = t0 ? yr[j + 1] : ur; ui = t0 ? yi[j + 1] : ui; }
                 else        { vr = t0 ? xr[20 - j] : vr; vi = t0 ? xi[20 - j] : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 const float pwa = fmaf(sr, sr, di * di);   // 4|A[k]|^2
@@ -349,9 +369,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     const float2 ent = s_proj[(eoff + e) * 32 + lane];
                     const float2* pr = s_p + __float_as_int(ent.y);
                     const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
-                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[3] = fmaf(ent.x, p0.y, acc[3]);
-                    acc[1] = fmaf(ent.x, p1.x, acc[1]); acc[4] = fmaf(ent.x, p1.y, acc[4]);
-                    acc[2] = fmaf(ent.x, p2.x, acc[2]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
+                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[1] = fmaf(ent.x, p0.y, acc[1]);
+                    acc[2] = fmaf(ent.x, p1.x, acc[2]); acc[3] = fmaf(ent.x, p1.y, acc[3]);
+                    acc[4] = fmaf(ent.x, p2.x, acc[4]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
                 }
                 eoff += K;
 #pragma unroll
@@ -368,8 +388,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
         // ------------------------------------------------------------------ store
         if (p.layout == 0) {
-            if (lane == 0) bulk_wait_read0();   // previous pass's bulk store has finished reading the staging rows
-            __syncwarp();
+            // the output rows are staged in the slab right behind the power rows (both dead once the next pass's
+            // Z exchange starts; the wait above orders the bulk store against that)
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int mel = s_meta[kMaxMpl + s * 32 + lane];

@@ -182,7 +182,7 @@ def test_full_size_batch_properties(m, mel400, torch):
     got = ref.cpu().numpy()
     assert np.isfinite(got).all() and got.min() >= -1.5 and got.max() < 3.0          # (2)
     shifted = _device_run(torch, mel400, base[:4, 160 * 7:])
-    assert np.abs(shifted - got[:4, 7:7 + shifted.shape[1]]).max() <= 2e-5                 # (3)
+    assert np.abs(shifted - got[:4, 7:7 + shifted.shape[1]]).max() <= 5e-5                 # (3) Re-slot vs Im-slot rounding
     want = oc.whisper_batch(base[[0, 7, 15]], threads=3)
     assert np.abs(got[[0, 7, 15]] - want).max() <= WHISPER_TOL                              # (4)
 

@@ -31,6 +31,7 @@ def model_pair(fa, fb):
     Z = np.zeros((21, 20), dtype=complex)            # [slot][n2]
     for c in range(C):                               # step 1 (thread t owns columns 2t, 2t+1)
         y = dft20_pfa(z[C * np.arange(R) + c])       # Y[c][k1]
+        y[10] *= np.exp(+2j * np.pi * c / 40.0)      # row 10 is pre-rotated by W_40^-c on the write side
         for k1 in range(R):
             Z[slot(k1), c] = y[k1]
     tw = np.exp(-2j * np.pi * np.outer(np.arange(R + 1), np.arange(C)) / N)   # tw[row][n2]
@@ -43,8 +44,9 @@ def model_pair(fa, fb):
         r2 = (R - a) if t else R // 2
         s1, s2 = t, 10 + t                           # slots read by thread t
         assert s1 == slot(r1) and s2 == slot(r2)
-        X = dft20_pfa(Z[s1] * tw[r1])
-        Y = dft20_pfa(Z[s2] * tw[r2])
+        X = dft20_pfa(Z[s1] * tw[t])                 # per-lane twiddle registers: W_400^(t*n2)
+        D = dft20_pfa(Z[s2] * np.conj(tw[t]))        # second row: conj twiddle, then output rotation by one
+        Y = np.roll(D, -1)                           # Y[m] = D[(m+1) % 20]
         lo_base = (R // 2) if t == 0 else a
         hi_base = R if t == 0 else R - a
         for j in range(C):
