@@ -144,7 +144,7 @@ struct melspec_handle {
     int plan = 0;   // 400 or 512
     std::vector<double> dense;   // (n_mels, fft/2+1)
     // device tables
-    float2* d_window = nullptr;
+    float* d_window = nullptr;
     float4* d_twiddle = nullptr;
     float2* d_rot10 = nullptr;
     float2* d_proj = nullptr;
@@ -178,38 +178,53 @@ struct melspec_stream {
 
 namespace {
 
-// P row (in the kernel's power slab) that holds bin b; see melspec_kernels.cuh (row = 10*j + t).
-int p400_row_of_bin(int b) {
-    const int rr = b % 20, q = b / 20;
+// Power-slab row that holds bin b for a plan N = R x C (R/2 workers per FFT, row = (R/2)*j + t); see
+// melspec_kernels.cuh and tools/model_plan.py.  Plan 400: R = C = 20.  Plan 512: R = 32, C = 16.
+int row_of_bin(int b, int R, int C) {
+    const int rr = b % R, q = b / R;
     int t, j;
-    if (rr == 0) { t = 0; j = 20 - q; }          // worker 0, high half: bin 20*(20-j)
-    else if (rr == 10) { t = 0; j = q; }          // worker 0, low half: bin 10+20j
-    else if (rr < 10) { t = rr; j = q; }          // worker rr, low half: bin rr+20j
-    else { t = 20 - rr; j = 19 - q; }             // worker 20-rr, high half: bin (20-t) + 20(19-j)
-    return 10 * j + t;
+    if (rr == 0) { t = 0; j = C - q; }                 // worker 0, high half: bin R*(C-j)
+    else if (rr == R / 2) { t = 0; j = q; }            // worker 0, low half: bin R/2 + R*j
+    else if (rr < R / 2) { t = rr; j = q; }            // worker rr, low half: bin rr + R*j
+    else { t = R - rr; j = C - 1 - q; }                // worker R-rr, high half: bin (R-t) + R*(C-1-j)
+    return (R / 2) * j + t;
 }
 
 int32_t build_tables(melspec_handle* h) {
     const Resolved& c = h->cfg;
     using namespace melspec;
-    if (h->plan != 400) return fail(MELSPEC_ERR_UNSUPPORTED, "only the 400-point plan is built in this revision");
-    const int N = 400, nb = N / 2 + 1;
-    // window: periodic Hann (reference src/stft.rs:141-145), computed in f64, rounded once
-    std::vector<float2> win(200);   // [n1][t] = (w[20 n1 + 2t], w[20 n1 + 2t + 1])
-    auto hann = [&](int i) { return (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N))); };
-    for (int n1 = 0; n1 < 20; ++n1)
-        for (int t = 0; t < 10; ++t) win[n1 * 10 + t] = make_float2(hann(20 * n1 + 2 * t), hann(20 * n1 + 2 * t + 1));
-    // per-worker twiddles W_400^(t*n2) (kept in registers by the kernel) and the row-10 pre-rotation W_40^(-c)
-    std::vector<float4> tw(100);   // [i][t] = (W^(t*2i), W^(t*(2i+1)))
-    std::vector<float2> rot(20);
-    for (int t = 0; t < 10; ++t)
-        for (int i = 0; i < 10; ++i) {
+    const int N = h->plan, nb = N / 2 + 1;
+    const int R = N == 400 ? 20 : 32, C = N == 400 ? 20 : 16;
+    std::vector<float> win;      // plan 400: [n1][t] float2 pairs; plan 512: [n1][c] floats
+    std::vector<float4> tw;      // [i][t] = (W_N^(t*2i), W_N^(t*(2i+1)))
+    std::vector<float2> rot(C);  // W_{2C}^(-c): pre-rotation of the middle row
+    auto window_at = [&](int i) -> float {
+        if (c.frontend == MELSPEC_FRONTEND_WHISPER)   // periodic Hann, reference src/stft.rs:141-145
+            return (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N)));
+        if (i >= c.frame_len) return 0.f;             // Povey window, zero padded to the FFT size (src/fbank.rs:100-105,184-190)
+        return (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(c.frame_len - 1)), 0.85);
+    };
+    if (N == 400) {
+        win.resize(400);
+        for (int n1 = 0; n1 < 20; ++n1)
+            for (int t = 0; t < 10; ++t) {
+                win[2 * (n1 * 10 + t)] = window_at(20 * n1 + 2 * t);
+                win[2 * (n1 * 10 + t) + 1] = window_at(20 * n1 + 2 * t + 1);
+            }
+    } else {
+        win.resize(512);
+        for (int i = 0; i < 512; ++i) win[i] = window_at(i);   // [n1][c] with i = 16*n1 + c
+    }
+    const int workers = R / 2, pairs = C / 2;
+    tw.resize((size_t)pairs * workers);
+    for (int t = 0; t < workers; ++t)
+        for (int i = 0; i < pairs; ++i) {
             const double a0 = -2.0 * M_PI * (double)((t * 2 * i) % N) / (double)N;
             const double a1 = -2.0 * M_PI * (double)((t * (2 * i + 1)) % N) / (double)N;
-            tw[i * 10 + t] = make_float4((float)std::cos(a0), (float)std::sin(a0), (float)std::cos(a1), (float)std::sin(a1));
+            tw[(size_t)i * workers + t] = make_float4((float)std::cos(a0), (float)std::sin(a0), (float)std::cos(a1), (float)std::sin(a1));
         }
-    for (int c2 = 0; c2 < 20; ++c2) {
-        const double a = 2.0 * M_PI * (double)c2 / 40.0;
+    for (int c2 = 0; c2 < C; ++c2) {
+        const double a = 2.0 * M_PI * (double)c2 / (double)(2 * C);
         rot[c2] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     // sparse banded filterbank -> per-lane projection program
@@ -266,15 +281,18 @@ int32_t build_tables(melspec_handle* h) {
             const int r = s * 32 + l;
             if (r >= c.n_mels) continue;
             lane_mel[l] = sorted[r].mel;
-            for (auto& e : sorted[r].e) lanes[l].push_back({p400_row_of_bin(e.first), (float)(e.second * 0.25)});
+            for (auto& e : sorted[r].e) lanes[l].push_back({row_of_bin(e.first, R, C), (float)(e.second * 0.25)});
         }
+        // plan 400 reads 24-byte rows with LDS.64 (conflicts per half-warp, rows mod 16); plan 512 reads 16-byte rows
+        // with LDS.128 (conflicts per quarter-warp, rows mod 8)
+        const int grp = N == 400 ? 16 : 8;
         auto cost = [&]() {
             int tot = 0;
             for (int e = 0; e < K; ++e)
-                for (int hw = 0; hw < 2; ++hw) {
+                for (int hw = 0; hw < 32 / grp; ++hw) {
                     int cnt[16] = {0}, mxc = 0;
-                    for (int l = 16 * hw; l < 16 * hw + 16; ++l)
-                        if (e < (int)lanes[l].size()) mxc = std::max(mxc, ++cnt[lanes[l][e].row & 15]);
+                    for (int l = grp * hw; l < grp * hw + grp; ++l)
+                        if (e < (int)lanes[l].size()) mxc = std::max(mxc, ++cnt[lanes[l][e].row & (grp - 1)]);
                     tot += mxc;
                 }
             return tot;
@@ -301,15 +319,16 @@ int32_t build_tables(melspec_handle* h) {
             for (int e = 0; e < K; ++e) {
                 float2 ent;
                 int off;
-                if (e < (int)lanes[l].size()) { ent.x = lanes[l][e].w; off = 3 * lanes[l][e].row; }
-                else {   // padding: zero weight, pointed at a row whose bank group nobody in this half-warp uses
+                const int rowmul = N == 400 ? 3 : 1;   // float2 index of a 3-FFT row / float4 index of a 2-FFT row
+                if (e < (int)lanes[l].size()) { ent.x = lanes[l][e].w; off = rowmul * lanes[l][e].row; }
+                else {   // padding: zero weight, pointed at a row whose bank group nobody in this lane group uses
                     int cnt[16] = {0};
-                    for (int l2 = 16 * (l / 16); l2 < 16 * (l / 16) + 16; ++l2)
-                        if (e < (int)lanes[l2].size()) cnt[lanes[l2][e].row & 15]++;
+                    for (int l2 = grp * (l / grp); l2 < grp * (l / grp) + grp; ++l2)
+                        if (e < (int)lanes[l2].size()) cnt[lanes[l2][e].row & (grp - 1)]++;
                     int pick = 0;
-                    for (int r = 1; r < 16; ++r) if (cnt[r] < cnt[pick]) pick = r;
+                    for (int r = 1; r < grp; ++r) if (cnt[r] < cnt[pick]) pick = r;
                     lanes[l].push_back({pick, 0.f});
-                    ent.x = 0.f; off = 3 * pick;
+                    ent.x = 0.f; off = rowmul * pick;
                 }
                 std::memcpy(&ent.y, &off, sizeof(int));
                 proj[(size_t)(eoff + e) * 32 + l] = ent;
@@ -319,12 +338,12 @@ int32_t build_tables(melspec_handle* h) {
         eoff += K;
     }
     h->proj_ktot = std::max(ktot, 1);
-    MS_CUDA(cudaMalloc(&h->d_window, sizeof(float2) * win.size()));
+    MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * win.size()));
     MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
     MS_CUDA(cudaMalloc(&h->d_rot10, sizeof(float2) * rot.size()));
     MS_CUDA(cudaMalloc(&h->d_proj, sizeof(float2) * proj.size()));
     MS_CUDA(cudaMalloc(&h->d_meta, sizeof(int) * meta.size()));
-    MS_CUDA(cudaMemcpy(h->d_window, win.data(), sizeof(float2) * win.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_window, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_twiddle, tw.data(), sizeof(float4) * tw.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_rot10, rot.data(), sizeof(float2) * rot.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(h->d_proj, proj.data(), sizeof(float2) * proj.size(), cudaMemcpyHostToDevice));
@@ -332,30 +351,22 @@ int32_t build_tables(melspec_handle* h) {
     return MELSPEC_OK;
 }
 
-// Warps per CTA (one persistent CTA per SM).  12 is the default (168 registers/thread); MELSPEC_WARPS=8|10|12 selects
+// Warps per CTA (one persistent CTA per SM).  12 is the default (168 registers/thread); MELSPEC_WARPS=8|12 selects
 // another build of the same kernel for tuning.
 int warps_per_cta() {
     static int w = [] {
         const char* e = std::getenv("MELSPEC_WARPS");
         const int v = e ? std::atoi(e) : 12;
-        return (v == 8 || v == 10 || v == 12) ? v : 12;
+        return (v == 8 || v == 12) ? v : 12;   // a multiple of 4: registers are allocated per SM sub-partition
     }();
     return w;
 }
 
-template <int NW, int MPL, bool HOP160>
-int32_t launch_inst(const melspec::KParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = melspec::melspec400_kernel<NW, MPL, HOP160>;
-    static bool configured = false;   // per instantiation
-    static int configured_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured || configured_dev != dev) {
-        MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-        configured_dev = dev;
-    }
-    kern<<<grid, NW * 32, smem, st>>>(p);
+template <typename Kern>
+int32_t launch_kernel(Kern kern, const melspec::KParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
+    // the opt-in for > 48 KB of dynamic shared memory is per function and per device; it is cheap, so set it every time
+    MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, threads, smem, st>>>(p);
     MS_CUDA(cudaGetLastError());
     return MELSPEC_OK;
 }
@@ -368,38 +379,52 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const Resolved& c = h->cfg;
     if (n_clips == 0 || frames_per_clip == 0) return MELSPEC_OK;
     if (n_samples > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "n_samples per clip must fit in int32");
+    const bool kaldi = c.frontend == MELSPEC_FRONTEND_KALDI;
+    if (kaldi && layout != MELSPEC_LAYOUT_FRAME_MAJOR)
+        return fail(MELSPEC_ERR_UNSUPPORTED, "the Kaldi frontend produces (T, n_mels) frame-major output only");
+    const int fpw = h->plan == 400 ? p400::FPW : p512::FPW;
     KParams p{};
     p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
     p.clip_stride = clip_stride;
     p.out_clip_stride = out_clip_stride ? out_clip_stride : frames_per_clip * c.n_mels;
     p.n_samples = (int)n_samples;
     p.frames_per_clip = (int)frames_per_clip;
-    p.wtiles_per_clip = (int)((frames_per_clip + p400::FPW - 1) / p400::FPW);
+    p.wtiles_per_clip = (int)((frames_per_clip + fpw - 1) / fpw);
     const int64_t n_wtiles = (int64_t)p.wtiles_per_clip * n_clips;
     if (n_wtiles > 0x7fffffff - 148 * 64) return fail(MELSPEC_ERR_INVALID_ARG, "too many frames for one launch");
     p.n_wtiles = (int)n_wtiles;
     p.hop = c.hop; p.n_mels = c.n_mels; p.fft_size = c.fft; p.layout = layout;
+    p.frame_len = c.frame_len; p.preemph = (float)c.preemph;
     const bool hop160 = c.hop == 160;
     const bool aligned_in = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (n_samples % 4 == 0) && (c.hop % 4 == 0);
     p.bulk_in = aligned_in ? 1 : 0;
     p.bulk_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) &&
                  (p.out_clip_stride % 4 == 0);
-    p.window = h->d_window; p.twiddle = h->d_twiddle; p.rot10 = h->d_rot10; p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
+    p.window = reinterpret_cast<const float2*>(h->d_window); p.twiddle = h->d_twiddle; p.rot10 = h->d_rot10;
+    p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
-    p.log_mul = (float)std::log10(2.0);
-    p.normalize = 1;
-    // shared-memory carve-up: [mbarriers | twiddles | projection program | meta | per-warp slabs]
+    if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
+    else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
+    // shared-memory carve-up: [mbarriers | window | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
-    p.smem_win = (int)off; off = up(off + sizeof(float2) * 200, 128);
-    p.smem_tw = (int)off; off = up(off + sizeof(float4) * 100, 128);
+    p.smem_win = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
+    p.smem_tw = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)h->proj_ktot, 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
-    const size_t pcm_words = hop160 ? (size_t)p400::NCHUNK * p400::CS320 : (size_t)(p400::FPW - 1) * c.hop + 400;
     p.smem_warp0 = (int)off;
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
-    p.smem_stage_off = p400::PBYTES;
-    p.smem_pcm_off = (int)up(p400::ZBYTES, 128);
+    static_assert(p512::FPW * 32 * kMaxMpl * 4 <= p512::STAGE_MAX, "output rows must fit behind the power rows");
+    size_t pcm_words;
+    if (h->plan == 400) {
+        pcm_words = hop160 ? (size_t)p400::NCHUNK * p400::CS320 : (size_t)(p400::FPW - 1) * c.hop + 400;
+        p.smem_stage_off = p400::PBYTES;
+        p.smem_pcm_off = (int)up(p400::ZBYTES, 128);
+    } else {
+        pcm_words = (size_t)p512::NCHUNK * p512::CS;
+        p.smem_stage_off = p512::PBYTES;
+        p.smem_pcm_off = (int)up(p512::ZBYTES, 128);
+    }
     p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
     const int nw = warps_per_cta();
     off += (size_t)p.smem_warp_stride * nw;
@@ -407,13 +432,33 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;
     const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
     int32_t rc;
-#define MS_DISPATCH(NW)                                                                                              \
-    (h->mpl <= 3 ? (hop160 ? launch_inst<NW, 3, true>(p, grid, off, st) : launch_inst<NW, 3, false>(p, grid, off, st)) \
-                 : (hop160 ? launch_inst<NW, 4, true>(p, grid, off, st) : launch_inst<NW, 4, false>(p, grid, off, st)))
-    rc = nw == 8 ? MS_DISPATCH(8) : nw == 10 ? MS_DISPATCH(10) : MS_DISPATCH(12);
+    const bool m3 = h->mpl <= 3;
+    if (h->plan == 400) {
+#define MS_DISPATCH(NW)                                                                                             \
+    (m3 ? (hop160 ? launch_kernel(melspec400_kernel<NW, 3, true>, p, grid, NW * 32, off, st)                         \
+                  : launch_kernel(melspec400_kernel<NW, 3, false>, p, grid, NW * 32, off, st))                        \
+        : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true>, p, grid, NW * 32, off, st)                         \
+                  : launch_kernel(melspec400_kernel<NW, 4, false>, p, grid, NW * 32, off, st)))
+        rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
-    if (rc == MELSPEC_OK) h->launches += 1;
-    return rc;
+    } else {
+#define MS_DISPATCH(NW)                                                                                             \
+    (m3 ? (kaldi ? launch_kernel(melspec512_kernel<NW, 3, true>, p, grid, NW * 32, off, st)                          \
+                 : launch_kernel(melspec512_kernel<NW, 3, false>, p, grid, NW * 32, off, st))                         \
+        : (kaldi ? launch_kernel(melspec512_kernel<NW, 4, true>, p, grid, NW * 32, off, st)                          \
+                 : launch_kernel(melspec512_kernel<NW, 4, false>, p, grid, NW * 32, off, st)))
+        rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
+#undef MS_DISPATCH
+    }
+    if (rc != MELSPEC_OK) return rc;
+    h->launches += 1;
+    if (kaldi && c.cmn) {   // CMN couples all frames of a clip: second, small kernel over rows that are still in L2
+        melspec_cmn_kernel<<<(unsigned)n_clips, 512, 0, st>>>(d_out, p.out_clip_stride, p.frames_per_clip, c.n_mels, d_lens,
+                                                             p.n_samples, c.frame_len, c.hop);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    return MELSPEC_OK;
 }
 
 int32_t ensure_host_resources(melspec_handle* h, size_t pcm_bytes, size_t out_bytes) {
@@ -512,8 +557,12 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
         return fail(MELSPEC_ERR_NO_DEVICE, "CUDA unavailable: kernels are built for sm_100a (Blackwell) only");
     int plan = 0;
     if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400) plan = 400;
-    else if (r.fft == 512) plan = 512;
-    if (plan != 400) return fail(MELSPEC_ERR_UNSUPPORTED, "this revision implements fft_size 400 (Whisper frontend) only");
+    else if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 512 && r.hop == 160) plan = 512;
+    else if (r.frontend == MELSPEC_FRONTEND_KALDI && r.fft == 512 && r.frame_len == 400 && r.hop == 160 && r.use_power) plan = 512;
+    if (!plan)
+        return fail(MELSPEC_ERR_UNSUPPORTED,
+                    "supported plans: Whisper fft_size 400 (any hop), Whisper fft_size 512 / hop 160, Kaldi 400-sample frames / "
+                    "hop 160 / power spectrum");
     MS_CUDA(cudaSetDevice(device));
     melspec_handle* h = new (std::nothrow) melspec_handle();
     if (!h) return fail(MELSPEC_ERR_CUDA, "out of host memory");

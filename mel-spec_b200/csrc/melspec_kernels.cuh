@@ -54,6 +54,8 @@ struct KParams {
     float floor_val;         // 1e-10 (Whisper) — floor applied to the *unscaled* energy
     float log_mul;           // log10(2) (Whisper)
     int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
+    int frame_len;           // samples per frame before zero padding (fft_size for Whisper, 400 for Kaldi)
+    float preemph;           // Kaldi pre-emphasis coefficient
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
@@ -151,6 +153,73 @@ __device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
             xr[(5 * a + 16 * kb) % 20] = tr[a][kb];
             xi[(5 * a + 16 * kb) % 20] = ti[a][kb];
         }
+    }
+}
+
+// ---- power-of-two codelets for the 512-point plan -------------------------------------------------------------
+// x *= W_32^k = exp(-2*pi*i*k/32), k a compile-time constant after unrolling (trivial factors cost nothing)
+__device__ __forceinline__ void mul_w32(float& r, float& i, const int k) {
+    constexpr float C[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+                             0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f,
+                             -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f,
+                             -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float S[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f, 0.70710678118654746f,
+                             0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.f, 0.98078528040323043f,
+                             0.92387953251128674f, 0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f,
+                             0.38268343236508989f, 0.19509032201612861f};
+    const int kk = k & 31;
+    if (kk == 0) return;
+    if (kk == 8) { const float t = r; r = i; i = -t; return; }            // -i
+    if (kk == 16) { r = -r; i = -i; return; }
+    if (kk == 24) { const float t = r; r = -i; i = t; return; }           // +i
+    const float c = kk < 16 ? C[kk] : -C[kk - 16], sn = kk < 16 ? S[kk] : -S[kk - 16];
+    const float nr = fmaf(i, sn, r * c), ni = fmaf(-r, sn, i * c);       // (r + i*im)(c - i*s)
+    r = nr; i = ni;
+}
+
+__device__ __forceinline__ void dft4(float& r0, float& i0, float& r1, float& i1, float& r2, float& i2, float& r3, float& i3) {
+    const float s02r = r0 + r2, s02i = i0 + i2, d02r = r0 - r2, d02i = i0 - i2;
+    const float s13r = r1 + r3, s13i = i1 + i3, d13r = r1 - r3, d13i = i1 - i3;
+    r0 = s02r + s13r; i0 = s02i + s13i;
+    r2 = s02r - s13r; i2 = s02i - s13i;
+    r1 = d02r + d13i; i1 = d02i - d13r;   // d02 - i*d13
+    r3 = d02r - d13i; i3 = d02i + d13r;   // d02 + i*d13
+}
+
+// 16-point forward DFT on x[S*n], n = 0..15, natural order in and out (4 x 4 Cooley-Tukey, constant twiddles).
+template <int S, int LEN>
+__device__ __forceinline__ void dft16(float (&xr)[LEN], float (&xi)[LEN], const int base) {
+    float tr[4][4], ti[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float r0 = xr[base + S * b], i0 = xi[base + S * b], r1 = xr[base + S * (4 + b)], i1 = xi[base + S * (4 + b)];
+        float r2 = xr[base + S * (8 + b)], i2 = xi[base + S * (8 + b)], r3 = xr[base + S * (12 + b)], i3 = xi[base + S * (12 + b)];
+        dft4(r0, i0, r1, i1, r2, i2, r3, i3);
+        mul_w32(r1, i1, 2 * b); mul_w32(r2, i2, 4 * b); mul_w32(r3, i3, 6 * b);   // W_16^(b*ka)
+        tr[0][b] = r0; ti[0][b] = i0; tr[1][b] = r1; ti[1][b] = i1; tr[2][b] = r2; ti[2][b] = i2; tr[3][b] = r3; ti[3][b] = i3;
+    }
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        dft4(tr[ka][0], ti[ka][0], tr[ka][1], ti[ka][1], tr[ka][2], ti[ka][2], tr[ka][3], ti[ka][3]);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) { xr[base + S * (ka + 4 * kb)] = tr[ka][kb]; xi[base + S * (ka + 4 * kb)] = ti[ka][kb]; }
+    }
+}
+
+// 32-point forward DFT, natural order in and out: two interleaved 16-point DFTs + one radix-2 stage.
+__device__ __forceinline__ void dft32(float (&xr)[32], float (&xi)[32]) {
+    dft16<2, 32>(xr, xi, 0);   // E[ka] lands in x[2*ka]
+    dft16<2, 32>(xr, xi, 1);   // O[ka] lands in x[2*ka + 1]
+    float er[16], ei[16], orr[16], oi[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        er[k] = xr[2 * k]; ei[k] = xi[2 * k]; orr[k] = xr[2 * k + 1]; oi[k] = xi[2 * k + 1];
+        mul_w32(orr[k], oi[k], k);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        xr[k] = er[k] + orr[k]; xi[k] = ei[k] + oi[k];
+        xr[k + 16] = er[k] - orr[k]; xi[k + 16] = ei[k] - oi[k];
     }
 }
 
@@ -432,6 +501,310 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         }
     }
     if (lane == 0) bulk_wait0();   // all bulk stores of this warp have landed before the CTA retires
+}
+
+// ================================================================================================ plan 512
+// N = 512 = 32 x 16: a warp owns 2 complex FFTs = 4 frames per pass, 16 lanes per FFT.
+//   step 1  lane (c, g) = (lane & 15, lane >> 4) transforms column c (elements x[16*n1 + c]) with a 32-point DFT
+//   step 3  lane (t, g) = (lane >> 1, lane & 1) owns rows t and 32-t (t = 0: rows 0 and 16): two 16-point DFTs
+// Same conjugate-twiddle / output-rotation / pre-rotated middle row scheme as plan 400.  KALDI adds the fbank.rs prologue
+// (per-frame DC removal, pre-emphasis with look-back, Povey window, 400 samples zero-padded to 512) and drops the Whisper
+// normalisation (natural log of the floored energies; CMN is a second small kernel).
+namespace p512 {
+constexpr int N = 512;
+constexpr int FPW = 4;
+constexpr int ZROWB = 144;                   // bytes per Z row: 16 complex + 16 B pad  (9 units: odd => conflict-free LDS.128)
+constexpr int ZSLABB = 32 * ZROWB + 64;      // 4672 B per FFT (292 units = 4 mod 8: the two FFTs of a quarter-warp never collide)
+constexpr int ZBYTES = 2 * ZSLABB;           // 9344 per warp
+constexpr int PBYTES = 256 * 16;             // power rows 16*j + t, one float4 (A0, B0, A1, B1) per row
+constexpr int STAGE_MAX = ZBYTES - PBYTES;
+constexpr int CHUNK = 320;
+constexpr int PAD = 16;
+constexpr int CS = CHUNK + PAD;
+constexpr int NCHUNK = 4;                    // 3*160 + 512 = 992 samples
+__host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 - r; }
+}  // namespace p512
+
+template <int NWARPS, int MPL, bool KALDI>
+__global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
+    using namespace p512;
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NLOAD = KALDI ? 35 : 42;     // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
+    constexpr int NROW = KALDI ? 25 : 32;      // non-zero rows of a frame (Kaldi: 400 samples zero-padded to 512)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int c = lane & 15, g1 = lane >> 4;   // step-1 role
+    const int t = lane >> 1, g3 = lane & 1;    // step-3 role
+
+    const float2* s_proj = reinterpret_cast<const float2*>(smem + p.smem_proj);
+    const int* s_meta = reinterpret_cast<const int*>(smem + p.smem_meta);
+    unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
+    float4* s_p4 = reinterpret_cast<float4*>(s_warp);
+    float2* s_p2 = reinterpret_cast<float2*>(s_warp);
+    float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
+    float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
+    const uint32_t bar = smem_u32(smem + 8 * warp);
+
+    // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
+    for (int i = threadIdx.x; i < 512; i += NWARPS * 32) reinterpret_cast<float*>(smem + p.smem_win)[i] = reinterpret_cast<const float*>(p.window)[i];
+    for (int i = threadIdx.x; i < 128; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
+    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
+    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const float* s_win = reinterpret_cast<const float*>(smem + p.smem_win) + c;
+    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
+    const float2 r16 = __ldg(p.rot10 + c);     // W_32^(-c): pre-rotation of row 16
+    __syncthreads();
+
+    const int need = (FPW - 1) * 160 + p.frame_len;
+
+    auto issue_load = [&](int wt) {
+        const int clip = wt / p.wtiles_per_clip;
+        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+        const long long s0 = (long long)fw0 * 160;
+        const long long left = (long long)p.n_samples - s0;
+        const int avail = left < need ? (int)left : need;
+        const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
+        if (p.bulk_in) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
+#pragma unroll
+                for (int k = 0; k < NCHUNK; ++k)
+                    if (CHUNK * k < avail)
+                        bulk_g2s(smem_u32(s_pcm + k * CS), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar);
+            }
+        } else {
+            for (int i = lane; i < avail; i += 32) s_pcm[i + PAD * (i / CHUNK)] = __ldg(src + i);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+    };
+
+    const int wstride = gridDim.x * NWARPS;
+    int wt = blockIdx.x * NWARPS + warp;
+    if (wt < p.n_wtiles) issue_load(wt);
+
+    for (int it = 0; wt < p.n_wtiles; wt += wstride, ++it) {
+        const int clip = wt / p.wtiles_per_clip;
+        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+        int nfr = p.frames_per_clip;
+        if (p.lens) {
+            const int len = min(p.lens[clip], p.n_samples);
+            nfr = len < p.frame_len ? 0 : (len - p.frame_len) / 160 + 1;
+        }
+        const int nvalid = max(0, min(FPW, nfr - fw0));
+
+        // Kaldi look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it)
+        float lead = 0.f;
+        const bool owns_first = KALDI && g1 == 0 && c == 0;
+        if (owns_first && fw0 > 0) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + (long long)fw0 * 160 - 1);
+
+        mbar_wait(bar, it & 1);
+
+        // ------------------------------------------------------------------ step 1
+        float ar[32], ai[32];   // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1)
+        if (nvalid > 0) {
+            const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
+            const float* px = s_pcm + g1 * CS + c;
+            float x[NLOAD];
+#pragma unroll
+            for (int m = 0; m < NLOAD; ++m) x[m] = px[16 * m + PAD * (m / 20)];
+            if (!KALDI) {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float w = s_win[16 * n1];
+                    ar[n1] = va ? x[n1] * w : 0.f;
+                    ai[n1] = vb ? x[n1 + 10] * w : 0.f;
+                }
+            } else {
+                // d[m] = x[m] - preemph * x[m-1]; the previous sample is one word back (one chunk pad further back at a
+                // chunk start); frame sums for the DC removal are reduced over the 16 lanes of the FFT
+                float sa = 0.f, sb = 0.f;
+                const float x0 = x[0];
+#pragma unroll
+                for (int m = 0; m < NLOAD; ++m) {
+                    float xp;
+                    if (m % 20 == 0) {
+                        const int back = (c == 0) ? 1 + PAD : 1;
+                        xp = (m == 0 && owns_first) ? lead : px[16 * m + PAD * (m / 20) - back];
+                    } else {
+                        xp = px[16 * m + PAD * (m / 20) - 1];
+                    }
+                    if (m < 25) sa += x[m];
+                    if (m >= 10) sb += x[m];
+                    x[m] = fmaf(-p.preemph, xp, x[m]);
+                }
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
+                if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
+                const float ka = (1.0f - p.preemph) * mu_a, kb = (1.0f - p.preemph) * mu_b;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    if (n1 < NROW) {
+                        const float w = s_win[16 * n1];
+                        ar[n1] = va ? (x[n1] - ka) * w : 0.f;
+                        ai[n1] = vb ? (x[n1 + 10] - kb) * w : 0.f;
+                    } else {
+                        ar[n1] = 0.f; ai[n1] = 0.f;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
+        if (nvalid == 0) continue;
+
+        dft32(ar, ai);
+        {   // row 16 carries an extra W_32^(-c)
+            const float r = ar[16] * r16.x - ai[16] * r16.y, i = fmaf(ar[16], r16.y, ai[16] * r16.x);
+            ar[16] = r; ai[16] = i;
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        {
+            unsigned char* zw = s_warp + g1 * ZSLABB + 8 * c;
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1)
+                *reinterpret_cast<float2*>(zw + ZROWB * slot_of_row(k1)) = make_float2(ar[k1], ai[k1]);
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ step 3
+        float xr[16], xi[16], yr[16], yi[16];
+        {
+            const float4* z1 = reinterpret_cast<const float4*>(s_warp + g3 * ZSLABB + ZROWB * t);
+            const float4* z2 = reinterpret_cast<const float4*>(s_warp + g3 * ZSLABB + ZROWB * (16 + t));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = z1[i], u = z2[i], w = s_tw[16 * i];
+                const int n = 2 * i, m = 2 * i + 1;
+                xr[n] = v.x * w.x - v.y * w.y;  xi[n] = fmaf(v.x, w.y, v.y * w.x);
+                xr[m] = v.z * w.z - v.w * w.w;  xi[m] = fmaf(v.z, w.w, v.w * w.z);
+                yr[n] = fmaf(u.x, w.x, u.y * w.y);  yi[n] = u.y * w.x - u.x * w.y;
+                yr[m] = fmaf(u.z, w.z, u.w * w.w);  yi[m] = u.w * w.z - u.z * w.w;
+            }
+        }
+        __syncwarp();
+        dft16<1, 16>(xr, xi, 0);
+        dft16<1, 16>(yr, yi, 0);   // D; the row's spectrum is Y[m] = D[(m + 1) % 16]
+        {
+            const bool t0 = (t == 0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float ur = xr[j], ui = xi[j], vr = yr[(16 - j) % 16], vi = yi[(16 - j) % 16];
+                if (j < 8) { ur = t0 ? yr[j + 1] : ur; ui = t0 ? yi[j + 1] : ui; }
+                else       { vr = t0 ? xr[16 - j] : vr; vi = t0 ? xi[16 - j] : vi; }
+                const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
+                s_p2[32 * j + lane] = make_float2(fmaf(sr, sr, di * di), fmaf(si, si, dr * dr));   // row 16j+t, FFT g3
+            }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ projection + log (+ normalise)
+        float lg[MPL][FPW];
+        float mx[FPW];
+#pragma unroll
+        for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
+        {
+            int eoff = 0;
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int K = s_meta[s];
+                float acc[FPW];
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
+#pragma unroll 2
+                for (int e = 0; e < K; ++e) {
+                    const float2 ent = s_proj[(eoff + e) * 32 + lane];
+                    const float4 pw = s_p4[__float_as_int(ent.y)];
+                    acc[0] = fmaf(ent.x, pw.x, acc[0]); acc[1] = fmaf(ent.x, pw.y, acc[1]);
+                    acc[2] = fmaf(ent.x, pw.z, acc[2]); acc[3] = fmaf(ent.x, pw.w, acc[3]);
+                }
+                eoff += K;
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) {
+                    const float e = fmaxf(acc[q], p.floor_val);
+                    lg[s][q] = p.log_mul != 0.f ? p.log_mul * __log2f(e) : e;
+                    mx[q] = fmaxf(mx[q], lg[s][q]);
+                }
+            }
+        }
+        if (p.normalize) {
+#pragma unroll
+            for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
+        }
+        if (p.layout == 0) {
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q)
+                        s_stage[q * p.n_mels + mel] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                }
+            }
+            float* dst = p.out + (long long)clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
+            const int nout = nvalid * p.n_mels;
+            if (p.bulk_out) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
+                    bulk_commit();
+                }
+            } else {
+                __syncwarp();
+                for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
+                __syncwarp();
+            }
+        } else {
+            float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q)
+                        if (q < nvalid)
+                            dst[(long long)mel * p.frames_per_clip + q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) bulk_wait0();
+}
+
+// Cepstral mean normalisation of the Kaldi path (reference src/fbank.rs:226-233): out[clip][f][m] -= mean_f out[clip][f][m].
+// One CTA per clip, 4 frame-groups x n_mels columns; the clip's rows were just written and sit in L2.
+__global__ void __launch_bounds__(512, 1) melspec_cmn_kernel(float* out, long long out_clip_stride, int frames_per_clip, int n_mels,
+                                                             const int32_t* lens, int n_samples, int frame_len, int hop) {
+    __shared__ float part[4][128];
+    const int clip = blockIdx.x;
+    int nfr = frames_per_clip;
+    if (lens) {
+        const int len = min(lens[clip], n_samples);
+        nfr = len < frame_len ? 0 : (len - frame_len) / hop + 1;
+    }
+    if (nfr <= 0) return;
+    float* base = out + (long long)clip * out_clip_stride;
+    const int m = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    float acc = 0.f;
+    if (m < n_mels)
+        for (int f = grp; f < nfr; f += 4) acc += base[(long long)f * n_mels + m];
+    part[grp][m] = acc;
+    __syncthreads();
+    const float mean = (part[0][m] + part[1][m] + part[2][m] + part[3][m]) / (float)nfr;
+    if (m < n_mels)
+        for (int f = grp; f < nfr; f += 4) base[(long long)f * n_mels + m] -= mean;
 }
 
 }  // namespace melspec

@@ -227,3 +227,100 @@ def test_streaming_large_chunks(m, jfk):
     assert got.shape == want.shape == (1098, 80)
     assert np.abs(got - want).max() <= WHISPER_TOL
     rb.close()
+
+
+# ------------------------------------------------------------------------------------------ fft 512 (golden-file config)
+def test_whisper512_matches_rust_golden(m, jfk, golden_dir, torch):
+    """The reference's one numeric golden (src/rb.rs:134-179): fft 512 / hop 160 / 80 mels, stream framing.
+    Equivalent batch form: samples[128:], mel-major (80, 1097).  Reference tolerance 1e-6 (f64 path); ours 1e-4 (fp32)."""
+    gold = np.load(os.path.join(golden_dir, "rust_jfk_golden.npy"))
+    h = m.CudaMelSpectrogram(512, 160, 16000.0, 80)
+    got = h.compute_host(jfk[128:], layout=m.LAYOUT_MEL_MAJOR)
+    assert got.shape == gold.shape == (80, 1097)
+    assert np.abs(got - gold).max() <= WHISPER_TOL, np.abs(got - gold).max()
+    fm = h.compute_mel_spectrogram(jfk[128:])
+    assert np.array_equal(fm.T, got)
+    want = o.whisper_mel_batch(jfk, 512, 160, 80, 16000.0)
+    assert np.abs(h.compute_mel_spectrogram(jfk) - want).max() <= WHISPER_TOL
+    h.close()
+
+
+def test_ringbuffer_512_matches_rust_golden(m, jfk, golden_dir):
+    # the reference test itself: RingBuffer(MelConfig(512,160,80,16k)) fed the whole file, frames interleaved mel-major
+    gold = np.load(os.path.join(golden_dir, "rust_jfk_golden.npy"))
+    rb = m.RingBuffer(m.MelConfig(512, 160, 80, 16000.0), capacity=1 << 22, max_chunk_samples=32000)
+    rb.add_frame(jfk)
+    got = rb.drain()
+    assert got.T.shape == gold.shape
+    assert np.abs(got.T - gold).max() <= WHISPER_TOL
+    rb.close()
+
+
+def test_whisper512_ragged_and_batch(m, torch):
+    h = m.CudaMelSpectrogram(512, 160, 16000.0, 80)
+    for n in (511, 512, 671, 672, 5000, 16003):
+        rng = np.random.default_rng(n)
+        x = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        got = h.compute_mel_spectrogram(x)
+        want = o.whisper_mel_batch(x, 512, 160, 80, 16000.0)
+        assert got.shape == want.shape
+        if want.size:
+            assert np.abs(got - want).max() <= WHISPER_TOL, n
+    pcm = np.stack([o.synth_clip(i, 48000) for i in range(5)])
+    got = _device_run(torch, h, pcm)
+    want = oc.whisper_batch(pcm, 512, 160, 80, 16000.0, threads=4)
+    assert np.abs(got - want).max() <= WHISPER_TOL
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------ Kaldi fbank (src/fbank.rs)
+# fp32 tolerance for the Kaldi path, stated: ln() is not clamped relative to the frame maximum, so low-energy bins carry
+# the fp32 FFT noise floor (SURVEY §7: an all-fp32 pipeline is 2.7e-3 max on JFK).  Bar: max-abs <= 5e-3 and >= 99.5 %
+# of the values within 1e-3 of the f64 oracle of the reference's semantics.
+KALDI_TOL_MAX = 5e-3
+KALDI_TOL_BULK = 1e-3
+
+
+def _kaldi_check(got, want):
+    assert got.shape == want.shape
+    d = np.abs(got - want)
+    assert d.max() <= KALDI_TOL_MAX, d.max()
+    assert (d <= KALDI_TOL_BULK).mean() >= 0.995, (d <= KALDI_TOL_BULK).mean()
+
+
+def test_kaldi_fbank_jfk(m, jfk, golden_dir):
+    fb = m.Fbank(m.FbankConfig())
+    got = fb.compute(jfk)
+    assert got.shape == (1098, 80)                                   # src/fbank.rs:484-490 (the reference's assertion)
+    assert np.isfinite(got).all() and got.var() > 0.1                 # src/fbank.rs:521-534
+    _kaldi_check(got, o.kaldi_fbank(jfk))
+    gold = np.load(os.path.join(golden_dir, "kaldi_fbank_jfk.npy")).T  # kaldi_native_fbank output: the reference itself
+    d = np.abs(got - gold)                                             # is 1.5e-2 away from it (SURVEY §8c)
+    assert d.max() < 2.5e-2 and d.mean() < 4e-3
+    fb.close()
+
+
+def test_kaldi_without_cmn_and_edge_cases(m):
+    cfg = m.FbankConfig(apply_cmn=False)
+    fb = m.Fbank(cfg)
+    rng = np.random.default_rng(1)
+    for n in (399, 400, 559, 560, 4000, 16001):
+        x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+        got = fb.compute(x)
+        want = o.kaldi_fbank(x, apply_cmn=False)
+        assert got.shape == want.shape
+        if want.size:
+            _kaldi_check(got, want)
+    assert fb.compute(np.zeros(16000, np.float32)).shape == (98, 80)   # tests/readme_examples.rs:21-31
+    fb.close()
+
+
+def test_kaldi_batch_vs_oracle(m, torch):
+    # BASELINE config 3 shape at oracle-friendly size
+    pcm = np.stack([o.synth_clip(i, 160000) for i in range(4)])
+    fb = m.Fbank(m.FbankConfig())
+    got = _device_run(torch, fb, pcm)
+    want = oc.kaldi_batch(pcm, threads=4)
+    for i in range(4):
+        _kaldi_check(got[i], want[i])
+    fb.close()
