@@ -156,6 +156,56 @@ __device__ __forceinline__ void dft20(float (&xr)[20], float (&xi)[20]) {
     }
 }
 
+// ---- packed (two transforms at once) codelets: Blackwell's FADD2 / FMUL2 / FFMA2 operate on an aligned register pair,
+// so one instruction advances the same butterfly of two independent DFTs.  Each float2 below holds element n of
+// transform 0 in .x and of transform 1 in .y.  Rounding is per component, identical to the scalar codelets.
+typedef float2 f2;
+__device__ __forceinline__ f2 add2(const f2 a, const f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(const f2 a, const f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 mul2(const f2 a, const f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 mul2c(const float c, const f2 a) { return __fmul2_rn(make_float2(c, c), a); }
+__device__ __forceinline__ f2 fma2(const f2 a, const f2 b, const f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 fma2c(const float c, const f2 a, const f2 b) { return __ffma2_rn(make_float2(c, c), a, b); }
+
+__device__ __forceinline__ void dft5x2(f2& r0, f2& i0, f2& r1, f2& i1, f2& r2, f2& i2, f2& r3, f2& i3, f2& r4, f2& i4) {
+    const f2 t1r = add2(r1, r4), t1i = add2(i1, i4), t2r = add2(r2, r3), t2i = add2(i2, i3);
+    const f2 d1r = sub2(r1, r4), d1i = sub2(i1, i4), d2r = sub2(r2, r3), d2i = sub2(i2, i3);
+    const f2 a1r = fma2c(MS_C2, t2r, fma2c(MS_C1, t1r, r0)), a1i = fma2c(MS_C2, t2i, fma2c(MS_C1, t1i, i0));
+    const f2 a2r = fma2c(MS_C1, t2r, fma2c(MS_C2, t1r, r0)), a2i = fma2c(MS_C1, t2i, fma2c(MS_C2, t1i, i0));
+    const f2 b1r = fma2c(MS_S2, d2r, mul2c(MS_S1, d1r)), b1i = fma2c(MS_S2, d2i, mul2c(MS_S1, d1i));
+    const f2 b2r = fma2c(-MS_S1, d2r, mul2c(MS_S2, d1r)), b2i = fma2c(-MS_S1, d2i, mul2c(MS_S2, d1i));
+    r0 = add2(add2(r0, t1r), t2r);
+    i0 = add2(add2(i0, t1i), t2i);
+    r1 = add2(a1r, b1i); i1 = sub2(a1i, b1r);
+    r4 = sub2(a1r, b1i); i4 = add2(a1i, b1r);
+    r2 = add2(a2r, b2i); i2 = sub2(a2i, b2r);
+    r3 = sub2(a2r, b2i); i3 = add2(a2i, b2r);
+}
+
+// Two 20-point forward DFTs at once (same Good-Thomas 4x5 index maps as dft20).
+__device__ __forceinline__ void dft20x2(f2 (&xr)[20], f2 (&xi)[20]) {
+    f2 tr[4][5], ti[4][5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const int n0 = (4 * b) % 20, n1 = (5 + 4 * b) % 20, n2 = (10 + 4 * b) % 20, n3 = (15 + 4 * b) % 20;
+        const f2 s02r = add2(xr[n0], xr[n2]), s02i = add2(xi[n0], xi[n2]), d02r = sub2(xr[n0], xr[n2]), d02i = sub2(xi[n0], xi[n2]);
+        const f2 s13r = add2(xr[n1], xr[n3]), s13i = add2(xi[n1], xi[n3]), d13r = sub2(xr[n1], xr[n3]), d13i = sub2(xi[n1], xi[n3]);
+        tr[0][b] = add2(s02r, s13r); ti[0][b] = add2(s02i, s13i);
+        tr[2][b] = sub2(s02r, s13r); ti[2][b] = sub2(s02i, s13i);
+        tr[1][b] = add2(d02r, d13i); ti[1][b] = sub2(d02i, d13r);
+        tr[3][b] = sub2(d02r, d13i); ti[3][b] = add2(d02i, d13r);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        dft5x2(tr[a][0], ti[a][0], tr[a][1], ti[a][1], tr[a][2], ti[a][2], tr[a][3], ti[a][3], tr[a][4], ti[a][4]);
+#pragma unroll
+        for (int kb = 0; kb < 5; ++kb) {
+            xr[(5 * a + 16 * kb) % 20] = tr[a][kb];
+            xi[(5 * a + 16 * kb) % 20] = ti[a][kb];
+        }
+    }
+}
+
 // ---- power-of-two codelets for the 512-point plan -------------------------------------------------------------
 // x *= W_32^k = exp(-2*pi*i*k/32), k a compile-time constant after unrolling (trivial factors cost nothing)
 __device__ __forceinline__ void mul_w32(float& r, float& i, const int k) {
@@ -328,7 +378,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1: window + column DFTs
-        float ar[20], ai[20], br[20], bi[20];   // column 2t (re = frame A, im = frame B) and column 2t+1
+        // PR[n] = (re of column 2t, re of column 2t+1), PI[n] = (im, im): the two column transforms advance together in
+        // packed FADD2/FMUL2/FFMA2 instructions (re = frame A, im = frame B)
+        f2 PR[20], PI[20];
         if (nvalid > 0) {
             const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
             if (HOP160) {
@@ -342,15 +394,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
                         const float2 w = s_win[10 * n1];
-                        ar[n1] = x[n1].x * w.x; ai[n1] = x[n1 + 8].x * w.x;
-                        br[n1] = x[n1].y * w.y; bi[n1] = x[n1 + 8].y * w.y;
+                        PR[n1] = mul2(x[n1], w);
+                        PI[n1] = mul2(x[n1 + 8], w);
                     }
                 } else {
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
                         const float2 w = s_win[10 * n1];
-                        ar[n1] = va ? x[n1].x * w.x : 0.f; ai[n1] = vb ? x[n1 + 8].x * w.x : 0.f;
-                        br[n1] = va ? x[n1].y * w.y : 0.f; bi[n1] = vb ? x[n1 + 8].y * w.y : 0.f;
+                        PR[n1] = va ? mul2(x[n1], w) : make_float2(0.f, 0.f);
+                        PI[n1] = vb ? mul2(x[n1 + 8], w) : make_float2(0.f, 0.f);
                     }
                 }
             } else {
@@ -359,10 +411,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
                     const float2 w = s_win[10 * n1];
-                    const float a0 = va ? pa[20 * n1] : 0.f, a1 = va ? pa[20 * n1 + 1] : 0.f;
-                    const float b0 = vb ? pb[20 * n1] : 0.f, b1 = vb ? pb[20 * n1 + 1] : 0.f;
-                    ar[n1] = a0 * w.x; ai[n1] = b0 * w.x;
-                    br[n1] = a1 * w.y; bi[n1] = b1 * w.y;
+                    const float2 a = va ? make_float2(pa[20 * n1], pa[20 * n1 + 1]) : make_float2(0.f, 0.f);
+                    const float2 b = vb ? make_float2(pb[20 * n1], pb[20 * n1 + 1]) : make_float2(0.f, 0.f);
+                    PR[n1] = mul2(a, w);
+                    PI[n1] = mul2(b, w);
                 }
             }
         }
@@ -370,48 +422,47 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
         if (nvalid == 0) continue;
 
-        dft20(ar, ai);
-        dft20(br, bi);
+        dft20x2(PR, PI);
         {   // row 10 carries an extra W_40^(-c) so that worker 0 can treat it like a "row 20 - t"
-            const float r = ar[10] * r10a.x - ai[10] * r10a.y, i = fmaf(ar[10], r10a.y, ai[10] * r10a.x);
-            ar[10] = r; ai[10] = i;
-            const float r2 = br[10] * r10b.x - bi[10] * r10b.y, i2 = fmaf(br[10], r10b.y, bi[10] * r10b.x);
-            br[10] = r2; bi[10] = i2;
+            const f2 rx = make_float2(r10a.x, r10b.x), ry = make_float2(r10a.y, r10b.y);
+            const f2 nr = fma2(make_float2(-PI[10].x, -PI[10].y), ry, mul2(PR[10], rx));
+            const f2 ni = fma2(PR[10], ry, mul2(PI[10], rx));
+            PR[10] = nr; PI[10] = ni;
         }
         if (lane == 0) bulk_wait_read0();   // the previous pass's bulk store (its rows live inside this slab) is done
         __syncwarp();
 #pragma unroll
-        for (int k1 = 0; k1 < 20; ++k1)
-            s_z[ZROW * slot_of_row(k1) + l30] = make_float4(ar[k1], ai[k1], br[k1], bi[k1]);
+        for (int k1 = 0; k1 < 20; ++k1)     // unit = (re col 2t, re col 2t+1, im col 2t, im col 2t+1)
+            s_z[ZROW * slot_of_row(k1) + l30] = make_float4(PR[k1].x, PR[k1].y, PI[k1].x, PI[k1].y);
         __syncwarp();
 
         // ------------------------------------------------------------------ step 3: twiddle + row DFTs
-        float xr[20], xi[20], yr[20], yi[20];   // rows t and 20-t (t = 0: rows 0 and 10) = slots t and 10+t
+        // XR[n] = (row t, row 20-t) real parts, XI[n] = imaginary parts: again two transforms per packed instruction
+        f2 XR[20], XI[20];
         {
             const float4* z1 = s_z + ZROW * t + g;
             const float4* z2 = s_z + ZROW * (10 + t) + g;
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
-                const float4 v = z1[3 * i], u = z2[3 * i], w = s_tw[10 * i];
+                const float4 v = z1[3 * i], u = z2[3 * i], w = s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
                 const int n = 2 * i, m = 2 * i + 1;
-                xr[n] = v.x * w.x - v.y * w.y;  xi[n] = fmaf(v.x, w.y, v.y * w.x);
-                xr[m] = v.z * w.z - v.w * w.w;  xi[m] = fmaf(v.z, w.w, v.w * w.z);
-                yr[n] = fmaf(u.x, w.x, u.y * w.y);  yi[n] = u.y * w.x - u.x * w.y;   // * conj(tw)
-                yr[m] = fmaf(u.z, w.z, u.w * w.w);  yi[m] = u.w * w.z - u.z * w.w;
+                XR[n] = make_float2(v.x * w.x - v.z * w.y, fmaf(u.x, w.x, u.z * w.y));         // x * tw ,  y * conj(tw)
+                XI[n] = make_float2(fmaf(v.x, w.y, v.z * w.x), u.z * w.x - u.x * w.y);
+                XR[m] = make_float2(v.y * w.z - v.w * w.w, fmaf(u.y, w.z, u.w * w.w));
+                XI[m] = make_float2(fmaf(v.y, w.w, v.w * w.z), u.w * w.z - u.y * w.w);
             }
         }
         __syncwarp();   // every lane has its rows in registers: the slab may now be overwritten with powers
-        dft20(xr, xi);
-        dft20(yr, yi);   // D; the row's spectrum is Y[m] = D[(m + 1) % 20]
+        dft20x2(XR, XI);   // .x = X (row t); .y = D with the row's spectrum Y[m] = D[(m + 1) % 20]
         {
             // Pair slot j: generic worker (rows a, 20-a): (X[j], Y[19-j])  -> bin a+20j (j<10) or its mirror.
             // Worker 0 (rows 0, 10): j<10: (Y[j], Y[19-j]) -> bin 10+20j;  j>=10: (X[j], X[20-j]) -> bin 20(20-j).
             const bool t0 = (t == 0);
 #pragma unroll
             for (int j = 0; j < 20; ++j) {
-                float ur = xr[j], ui = xi[j], vr = yr[(20 - j) % 20], vi = yi[(20 - j) % 20];
-                if (j < 10) { ur = t0 ? yr[j + 1] : ur; ui = t0 ? yi[j + 1] : ui; }
-                else        { vr = t0 ? xr[20 - j] : vr; vi = t0 ? xi[20 - j] : vi; }
+                float ur = XR[j].x, ui = XI[j].x, vr = XR[(20 - j) % 20].y, vi = XI[(20 - j) % 20].y;
+                if (j < 10) { ur = t0 ? XR[j + 1].y : ur; ui = t0 ? XI[j + 1].y : ui; }
+                else        { vr = t0 ? XR[20 - j].x : vr; vi = t0 ? XI[20 - j].x : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 const float pwa = fmaf(sr, sr, di * di);   // 4|A[k]|^2
                 const float pwb = fmaf(si, si, dr * dr);   // 4|B[k]|^2
