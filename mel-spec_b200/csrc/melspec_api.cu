@@ -204,13 +204,13 @@ int32_t build_tables(melspec_handle* h) {
         if (i >= c.frame_len) return 0.f;             // Povey window, zero padded to the FFT size (src/fbank.rs:100-105,184-190)
         return (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(c.frame_len - 1)), 0.85);
     };
-    if (N == 400) {
-        win.resize(400);
-        for (int n1 = 0; n1 < 20; ++n1)
-            for (int t = 0; t < 10; ++t) {
-                win[2 * (n1 * 10 + t)] = window_at(20 * n1 + 2 * t);
-                win[2 * (n1 * 10 + t) + 1] = window_at(20 * n1 + 2 * t + 1);
-            }
+    if (N == 400) {   // the kernel evaluates the periodic Hann window from these per-worker phase factors
+        win.resize(40);
+        for (int t = 0; t < 10; ++t) {
+            const double th0 = 2.0 * M_PI * (double)(2 * t) / 400.0, th1 = 2.0 * M_PI * (double)(2 * t + 1) / 400.0;
+            win[4 * t] = (float)std::cos(th0); win[4 * t + 1] = (float)std::cos(th1);
+            win[4 * t + 2] = (float)std::sin(th0); win[4 * t + 3] = (float)std::sin(th1);
+        }
     } else {
         win.resize(512);
         for (int i = 0; i < 512; ++i) win[i] = window_at(i);   // [n1][c] with i = 16*n1 + c
@@ -226,6 +226,14 @@ int32_t build_tables(melspec_handle* h) {
     for (int c2 = 0; c2 < C; ++c2) {
         const double a = 2.0 * M_PI * (double)c2 / (double)(2 * C);
         rot[c2] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    if (N == 400) {   // plan 400 reads one float4 per worker: (re c=2t, re c=2t+1, im c=2t, im c=2t+1)
+        std::vector<float2> r4(20);
+        for (int t = 0; t < 10; ++t) {
+            r4[2 * t] = make_float2(rot[2 * t].x, rot[2 * t + 1].x);
+            r4[2 * t + 1] = make_float2(rot[2 * t].y, rot[2 * t + 1].y);
+        }
+        rot = r4;
     }
     // sparse banded filterbank -> per-lane projection program
     for (int m = 0; m < c.n_mels; ++m)
@@ -260,7 +268,7 @@ int32_t build_tables(melspec_handle* h) {
     // (LDS.64, processed per half-warp): it is bank-conflict free when the 16 lanes of a half-warp hit rows that
     // differ mod 16.  Which lane of a slot owns which mel, the order of a mel's entries and the rows that padding
     // entries point at are all free, so a small deterministic hill-climb minimises the number of wavefronts.
-    std::vector<float2> proj((size_t)std::max(ktot, 1) * 32, make_float2(0.f, 0.f));
+    std::vector<float2> proj((size_t)(std::max(ktot, 1) + 1) * 32, make_float2(0.f, 0.f));   // + one padding row (prefetch)
     int eoff = 0;
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     auto rnd = [&rng](int n) {
@@ -298,7 +306,7 @@ int32_t build_tables(melspec_handle* h) {
             return tot;
         };
         int best = cost();
-        for (int iter = 0; iter < 6000 && best > 0; ++iter) {
+        for (int iter = 0; iter < 40000 && best > 2 * K; ++iter) {
             const int kind = rnd(3), a = rnd(32), b = rnd(32);
             if (kind == 0) {   // swap the mels of two lanes
                 if (a == b) continue;
@@ -410,7 +418,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     size_t off = 128;
     p.smem_win = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
     p.smem_tw = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
-    p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)h->proj_ktot, 128);
+    p.smem_rot = (int)off; off = up(off + 256, 128);
+    p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
     p.smem_warp0 = (int)off;
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");

@@ -44,7 +44,8 @@ struct KParams {
     int layout;              // 0 frame-major, 1 mel-major
     int fft_size;            // for num_frames(lens[clip])
     // constant tables (global memory, staged into shared memory once per CTA)
-    const float2* window;    // [20 n1][10 workers]  Hann window of samples 20*n1 + 2t and 20*n1 + 2t + 1
+    const float2* window;    // plan 400: [10 workers] float4 (cos th_2t, cos th_2t+1, sin th_2t, sin th_2t+1), th_c = 2 pi c/400
+                             // plan 512: [32 n1][16 c] floats, the (Hann or zero-padded Povey) window itself
     const float4* twiddle;   // [10 i][10 workers]  W_400^(t*2i), W_400^(t*(2i+1)) as (re,im,re,im); row 20-t uses the
                              // conjugates + an output rotation
     const float2* rot10;     // [20]  W_40^(-c): row 10 is pre-rotated on the write side so worker 0 fits the same scheme
@@ -57,7 +58,7 @@ struct KParams {
     int frame_len;           // samples per frame before zero padding (fft_size for Whisper, 400 for Kaldi)
     float preemph;           // Kaldi pre-emphasis coefficient
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
-    int smem_win, smem_tw, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
+    int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
 
 constexpr int kMaxMpl = 4;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
 
     // ---- one-time setup: tables into shared memory, barriers, per-lane window / twiddle registers
-    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
+    for (int i = threadIdx.x; i < (p.proj_ktot + 1) * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
     for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -324,20 +325,30 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     }
     // window and twiddle tables are lane-dependent (10 distinct rows, shared by the warp's 3 FFTs); they are read
     // from shared memory each pass instead of pinning 78 registers, which is what lets 12 warps live on an SM
-    for (int i = threadIdx.x; i < 200; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_win)[i] = p.window[i];
     for (int i = threadIdx.x; i < 100; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
-    const float2* s_win = reinterpret_cast<const float2*>(smem + p.smem_win) + t;
+    // Periodic Hann window of columns 2t, 2t+1, evaluated on the fly (two packed FFMA2 per row instead of a table read):
+    //   w[20*n1 + c] = 0.5 - 0.5 cos(2 pi n1/20 + th_c) = 0.5 + WC[n1] cos(th_c) + WS[n1] sin(th_c),  th_c = 2 pi c/400
+    const float4 wth = __ldg(reinterpret_cast<const float4*>(p.window) + t);   // (cos th_2t, cos th_2t+1, sin th_2t, sin th_2t+1)
+    const f2 w_cos0 = make_float2(wth.x, wth.y), w_sin0 = make_float2(wth.z, wth.w);
+    constexpr float WC[20] = {-0.5f, -0.47552825814757677f, -0.40450849718747373f, -0.29389262614623657f, -0.15450849718747373f,
+                              0.f, 0.15450849718747367f, 0.29389262614623651f, 0.40450849718747367f, 0.47552825814757677f,
+                              0.5f, 0.47552825814757688f, 0.40450849718747378f, 0.29389262614623662f, 0.15450849718747378f,
+                              0.f, -0.15450849718747361f, -0.29389262614623646f, -0.40450849718747367f, -0.47552825814757677f};
+    constexpr float WS[20] = {0.f, 0.1545084971874737f, 0.29389262614623657f, 0.40450849718747373f, 0.47552825814757677f,
+                              0.5f, 0.47552825814757682f, 0.40450849718747373f, 0.29389262614623662f, 0.15450849718747375f,
+                              0.f, -0.15450849718747345f, -0.29389262614623651f, -0.40450849718747367f, -0.47552825814757677f,
+                              -0.5f, -0.47552825814757682f, -0.40450849718747378f, -0.29389262614623668f, -0.15450849718747381f};
     const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
-    const float2 r10a = __ldg(p.rot10 + 2 * t), r10b = __ldg(p.rot10 + 2 * t + 1);
+    for (int i = threadIdx.x; i < 10; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i];
+    const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + t;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
     __syncthreads();
 
     const int hop = HOP160 ? 160 : p.hop;
     const int need = (FPW - 1) * hop + N;    // samples a warp tile spans
 
     // Stage the PCM of warp tile `wt` into this warp's buffer (TMA bulk copies issued by one lane).
-    auto issue_load = [&](int wt) {
-        const int clip = wt / p.wtiles_per_clip;
-        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+    auto issue_load = [&](int clip, int tin) {
+        const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * hop;
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
@@ -361,13 +372,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         }
     };
 
-    const int wstride = gridDim.x * NWARPS;
-    int wt = blockIdx.x * NWARPS + warp;
-    if (wt < p.n_wtiles) issue_load(wt);
+    // every warp owns a contiguous range of warp tiles (no division in the loop, neighbouring tiles share their
+    // 240-sample halo through L2)
+    int clip, tin, cnt;
+    {
+        const int nwt = gridDim.x * NWARPS, gw = blockIdx.x * NWARPS + warp;
+        const int base = p.n_wtiles / nwt, rem = p.n_wtiles - base * nwt;
+        const int lo = gw * base + min(gw, rem);
+        cnt = base + (gw < rem ? 1 : 0);
+        clip = lo / p.wtiles_per_clip;
+        tin = lo - clip * p.wtiles_per_clip;
+    }
+    if (cnt > 0) issue_load(clip, tin);
 
-    for (int it = 0; wt < p.n_wtiles; wt += wstride, ++it) {
-        const int clip = wt / p.wtiles_per_clip;
-        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;   // first frame of this pass
+    for (int it = 0; it < cnt; ++it) {
+        const int fw0 = tin * FPW;   // first frame of this pass
         int nfr = p.frames_per_clip;
         if (p.lens) {
             const int len = min(p.lens[clip], p.n_samples);
@@ -383,6 +402,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         f2 PR[20], PI[20];
         if (nvalid > 0) {
             const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
+            f2 w_cos = w_cos0, w_sin = w_sin0;
+            // opaque copy: keeps the 20 window pairs from being hoisted out of the tile loop into 40 live registers
+            asm volatile("" : "+f"(w_cos.x), "+f"(w_cos.y), "+f"(w_sin.x), "+f"(w_sin.y));
             if (HOP160) {
                 // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
                 // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16)
@@ -393,14 +415,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 if (nvalid == FPW) {
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
-                        const float2 w = s_win[10 * n1];
+                        const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
                         PR[n1] = mul2(x[n1], w);
                         PI[n1] = mul2(x[n1 + 8], w);
                     }
                 } else {
 #pragma unroll
                     for (int n1 = 0; n1 < 20; ++n1) {
-                        const float2 w = s_win[10 * n1];
+                        const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
                         PR[n1] = va ? mul2(x[n1], w) : make_float2(0.f, 0.f);
                         PI[n1] = vb ? mul2(x[n1 + 8], w) : make_float2(0.f, 0.f);
                     }
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 const float* pb = pa + hop;
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
-                    const float2 w = s_win[10 * n1];
+                    const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
                     const float2 a = va ? make_float2(pa[20 * n1], pa[20 * n1 + 1]) : make_float2(0.f, 0.f);
                     const float2 b = vb ? make_float2(pb[20 * n1], pb[20 * n1 + 1]) : make_float2(0.f, 0.f);
                     PR[n1] = mul2(a, w);
@@ -419,12 +441,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             }
         }
         __syncwarp();   // every lane has consumed its samples: the stage may be refilled
-        if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
+        const int cur_clip = clip;
+        if (++tin == p.wtiles_per_clip) { tin = 0; ++clip; }
+        if (it + 1 < cnt) issue_load(clip, tin);
         if (nvalid == 0) continue;
 
         dft20x2(PR, PI);
         {   // row 10 carries an extra W_40^(-c) so that worker 0 can treat it like a "row 20 - t"
-            const f2 rx = make_float2(r10a.x, r10b.x), ry = make_float2(r10a.y, r10b.y);
+            const float4 rot = *s_rot;
+            const f2 rx = make_float2(rot.x, rot.y), ry = make_float2(rot.z, rot.w);
             const f2 nr = fma2(make_float2(-PI[10].x, -PI[10].y), ry, mul2(PR[10], rx));
             const f2 ni = fma2(PR[10], ry, mul2(PI[10], rx));
             PR[10] = nr; PI[10] = ni;
@@ -477,7 +502,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
         {
-            int eoff = 0;
+            const float2* tab = s_proj + lane;
+            float2 nxt = tab[0];   // software-pipelined: the (weight, row) entry of step e+1 is fetched during step e
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int K = s_meta[s];
@@ -486,14 +512,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
 #pragma unroll 2
                 for (int e = 0; e < K; ++e) {
-                    const float2 ent = s_proj[(eoff + e) * 32 + lane];
+                    const float2 ent = nxt;
+                    tab += 32;
+                    nxt = tab[0];      // the table carries one padding row at its end
                     const float2* pr = s_p + __float_as_int(ent.y);
                     const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
                     acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[1] = fmaf(ent.x, p0.y, acc[1]);
                     acc[2] = fmaf(ent.x, p1.x, acc[2]); acc[3] = fmaf(ent.x, p1.y, acc[3]);
                     acc[4] = fmaf(ent.x, p2.x, acc[4]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
                 }
-                eoff += K;
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
                     lg[s][q] = p.log_mul * __log2f(fmaxf(acc[q], p.floor_val));
@@ -521,7 +548,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     }
                 }
             }
-            float* dst = p.out + (long long)clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
+            float* dst = p.out + (long long)cur_clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
             const int nout = nvalid * p.n_mels;
             if (p.bulk_out) {
                 fence_proxy_async();
@@ -536,7 +563,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 __syncwarp();
             }
         } else {   // mel-major: out[clip][mel][frame]
-            float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
+            float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int mel = s_meta[kMaxMpl + s * 32 + lane];
@@ -600,7 +627,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
     for (int i = threadIdx.x; i < 512; i += NWARPS * 32) reinterpret_cast<float*>(smem + p.smem_win)[i] = reinterpret_cast<const float*>(p.window)[i];
     for (int i = threadIdx.x; i < 128; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
-    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
+    for (int i = threadIdx.x; i < (p.proj_ktot + 1) * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
     for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
