@@ -359,15 +359,16 @@ int32_t build_tables(melspec_handle* h) {
     return MELSPEC_OK;
 }
 
-// Warps per CTA (one persistent CTA per SM).  12 is the default (168 registers/thread); MELSPEC_WARPS=8|12 selects
-// another build of the same kernel for tuning.
-int warps_per_cta() {
-    static int w = [] {
+// Warps per CTA (one persistent CTA per SM).  Measured best: 8 for plan 400 (no spills, twiddles stay in registers),
+// 12 for plan 512 (168 registers/thread).  MELSPEC_WARPS=8|12 overrides for tuning; the count must be a multiple of 4
+// (registers are allocated per SM sub-partition).
+int warps_per_cta(int plan) {
+    static int forced = [] {
         const char* e = std::getenv("MELSPEC_WARPS");
-        const int v = e ? std::atoi(e) : 12;
-        return (v == 8 || v == 12) ? v : 12;   // a multiple of 4: registers are allocated per SM sub-partition
+        const int v = e ? std::atoi(e) : 0;
+        return (v == 8 || v == 12) ? v : 0;
     }();
-    return w;
+    return forced ? forced : (plan == 400 ? 8 : 12);
 }
 
 template <typename Kern>
@@ -435,7 +436,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         p.smem_pcm_off = (int)up(p512::ZBYTES, 128);
     }
     p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
-    const int nw = warps_per_cta();
+    const int nw = warps_per_cta(h->plan);
     off += (size_t)p.smem_warp_stride * nw;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;

@@ -339,6 +339,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                               0.f, -0.15450849718747345f, -0.29389262614623651f, -0.40450849718747367f, -0.47552825814757677f,
                               -0.5f, -0.47552825814757682f, -0.40450849718747378f, -0.29389262614623668f, -0.15450849718747381f};
     const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
+    // with 8 warps per SM there are registers to spare: keep the worker's 10 twiddle quads resident (saves 10 LDS.128/pass)
+    constexpr bool TW_IN_REGS = (NWARPS <= 8);
+    float4 twreg[10];
+    if (TW_IN_REGS) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) twreg[i] = __ldg(p.twiddle + 10 * i + t);
+    }
     for (int i = threadIdx.x; i < 10; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i];
     const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + t;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
     __syncthreads();
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const float4* z2 = s_z + ZROW * (10 + t) + g;
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
-                const float4 v = z1[3 * i], u = z2[3 * i], w = s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
+                const float4 v = z1[3 * i], u = z2[3 * i], w = TW_IN_REGS ? twreg[i] : s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
                 const int n = 2 * i, m = 2 * i + 1;
                 XR[n] = make_float2(v.x * w.x - v.z * w.y, fmaf(u.x, w.x, u.z * w.y));         // x * tw ,  y * conj(tw)
                 XI[n] = make_float2(fmaf(v.x, w.y, v.z * w.x), u.z * w.x - u.x * w.y);
