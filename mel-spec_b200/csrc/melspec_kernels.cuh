@@ -588,6 +588,66 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     if (lane == 0) bulk_wait0();   // all bulk stores of this warp have landed before the CTA retires
 }
 
+// ---- packed power-of-two codelets (two transforms per instruction, see the f2 helpers above) ----------------------
+__device__ __forceinline__ void mul_w32x2(f2& r, f2& i, const int k) {
+    constexpr float C[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+                             0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f,
+                             -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f,
+                             -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float S[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f, 0.70710678118654746f,
+                             0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.f, 0.98078528040323043f,
+                             0.92387953251128674f, 0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f,
+                             0.38268343236508989f, 0.19509032201612861f};
+    const int kk = k & 31;
+    if (kk == 0) return;
+    if (kk == 8) { const f2 t = r; r = i; i = make_float2(-t.x, -t.y); return; }
+    if (kk == 16) { r = make_float2(-r.x, -r.y); i = make_float2(-i.x, -i.y); return; }
+    if (kk == 24) { const f2 t = r; r = make_float2(-i.x, -i.y); i = t; return; }
+    const float c = kk < 16 ? C[kk] : -C[kk - 16], sn = kk < 16 ? S[kk] : -S[kk - 16];
+    const f2 nr = fma2c(sn, i, mul2c(c, r)), ni = fma2c(-sn, r, mul2c(c, i));
+    r = nr; i = ni;
+}
+
+__device__ __forceinline__ void dft4x2(f2& r0, f2& i0, f2& r1, f2& i1, f2& r2, f2& i2, f2& r3, f2& i3) {
+    const f2 s02r = add2(r0, r2), s02i = add2(i0, i2), d02r = sub2(r0, r2), d02i = sub2(i0, i2);
+    const f2 s13r = add2(r1, r3), s13i = add2(i1, i3), d13r = sub2(r1, r3), d13i = sub2(i1, i3);
+    r0 = add2(s02r, s13r); i0 = add2(s02i, s13i);
+    r2 = sub2(s02r, s13r); i2 = sub2(s02i, s13i);
+    r1 = add2(d02r, d13i); i1 = sub2(d02i, d13r);
+    r3 = sub2(d02r, d13i); i3 = add2(d02i, d13r);
+}
+
+// Two 16-point forward DFTs at once, natural order in and out.
+__device__ __forceinline__ void dft16x2(f2 (&xr)[16], f2 (&xi)[16]) {
+    f2 tr[4][4], ti[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        f2 r0 = xr[b], i0 = xi[b], r1 = xr[4 + b], i1 = xi[4 + b], r2 = xr[8 + b], i2 = xi[8 + b], r3 = xr[12 + b], i3 = xi[12 + b];
+        dft4x2(r0, i0, r1, i1, r2, i2, r3, i3);
+        mul_w32x2(r1, i1, 2 * b); mul_w32x2(r2, i2, 4 * b); mul_w32x2(r3, i3, 6 * b);
+        tr[0][b] = r0; ti[0][b] = i0; tr[1][b] = r1; ti[1][b] = i1; tr[2][b] = r2; ti[2][b] = i2; tr[3][b] = r3; ti[3][b] = i3;
+    }
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        dft4x2(tr[ka][0], ti[ka][0], tr[ka][1], ti[ka][1], tr[ka][2], ti[ka][2], tr[ka][3], ti[ka][3]);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) { xr[ka + 4 * kb] = tr[ka][kb]; xi[ka + 4 * kb] = ti[ka][kb]; }
+    }
+}
+
+// 32-point forward DFT of one sequence: its even and odd halves run as the two lanes of a packed 16-point DFT.
+//   in : er[a] = (x[2a], x[2a+1]) real parts, ei[a] imaginary parts;  out: xr/xi natural order
+__device__ __forceinline__ void dft32_packed(f2 (&er)[16], f2 (&ei)[16], float (&xr)[32], float (&xi)[32]) {
+    dft16x2(er, ei);   // .x = E[k], .y = O[k]
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        float orr = er[k].y, oi = ei[k].y;
+        mul_w32(orr, oi, k);
+        xr[k] = er[k].x + orr; xi[k] = ei[k].x + oi;
+        xr[k + 16] = er[k].x - orr; xi[k + 16] = ei[k].x - oi;
+    }
+}
+
 // ================================================================================================ plan 512
 // N = 512 = 32 x 16: a warp owns 2 complex FFTs = 4 frames per pass, 16 lanes per FFT.
 //   step 1  lane (c, g) = (lane & 15, lane >> 4) transforms column c (elements x[16*n1 + c]) with a 32-point DFT
@@ -691,7 +751,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1
-        float ar[32], ai[32];   // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1)
+        // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet
+        f2 er[16], ei[16];
         if (nvalid > 0) {
             const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
             const float* px = s_pcm + g1 * CS + c;
@@ -700,10 +761,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             for (int m = 0; m < NLOAD; ++m) x[m] = px[16 * m + PAD * (m / 20)];
             if (!KALDI) {
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float w = s_win[16 * n1];
-                    ar[n1] = va ? x[n1] * w : 0.f;
-                    ai[n1] = vb ? x[n1 + 10] * w : 0.f;
+                for (int a = 0; a < 16; ++a) {
+                    const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
+                    er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
+                    ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
                 }
             } else {
                 // d[m] = x[m] - preemph * x[m-1]; the previous sample is one word back (one chunk pad further back at a
@@ -732,14 +793,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
                 const float ka = (1.0f - p.preemph) * mu_a, kb = (1.0f - p.preemph) * mu_b;
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    if (n1 < NROW) {
-                        const float w = s_win[16 * n1];
-                        ar[n1] = va ? (x[n1] - ka) * w : 0.f;
-                        ai[n1] = vb ? (x[n1 + 10] - kb) * w : 0.f;
-                    } else {
-                        ar[n1] = 0.f; ai[n1] = 0.f;
+                for (int a = 0; a < 16; ++a) {
+                    float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
+                    if (2 * a < NROW) {
+                        const float w0 = s_win[32 * a];
+                        r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
+                        i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
                     }
+                    if (2 * a + 1 < NROW) {
+                        const float w1 = s_win[32 * a + 16];
+                        r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
+                        i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
+                    }
+                    er[a] = make_float2(r0, r1);
+                    ei[a] = make_float2(i0, i1);
                 }
             }
         }
@@ -747,7 +814,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
         if (nvalid == 0) continue;
 
-        dft32(ar, ai);
+        float ar[32], ai[32];
+        dft32_packed(er, ei, ar, ai);
         {   // row 16 carries an extra W_32^(-c)
             const float r = ar[16] * r16.x - ai[16] * r16.y, i = fmaf(ar[16], r16.y, ai[16] * r16.x);
             ar[16] = r; ai[16] = i;
@@ -763,7 +831,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         __syncwarp();
 
         // ------------------------------------------------------------------ step 3
-        float xr[16], xi[16], yr[16], yi[16];
+        f2 XR[16], XI[16];   // .x = row t, .y = row 32-t (conjugate twiddles; spectrum rotated by one)
         {
             const float4* z1 = reinterpret_cast<const float4*>(s_warp + g3 * ZSLABB + ZROWB * t);
             const float4* z2 = reinterpret_cast<const float4*>(s_warp + g3 * ZSLABB + ZROWB * (16 + t));
@@ -771,22 +839,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             for (int i = 0; i < 8; ++i) {
                 const float4 v = z1[i], u = z2[i], w = s_tw[16 * i];
                 const int n = 2 * i, m = 2 * i + 1;
-                xr[n] = v.x * w.x - v.y * w.y;  xi[n] = fmaf(v.x, w.y, v.y * w.x);
-                xr[m] = v.z * w.z - v.w * w.w;  xi[m] = fmaf(v.z, w.w, v.w * w.z);
-                yr[n] = fmaf(u.x, w.x, u.y * w.y);  yi[n] = u.y * w.x - u.x * w.y;
-                yr[m] = fmaf(u.z, w.z, u.w * w.w);  yi[m] = u.w * w.z - u.z * w.w;
+                XR[n] = make_float2(v.x * w.x - v.y * w.y, fmaf(u.x, w.x, u.y * w.y));
+                XI[n] = make_float2(fmaf(v.x, w.y, v.y * w.x), u.y * w.x - u.x * w.y);
+                XR[m] = make_float2(v.z * w.z - v.w * w.w, fmaf(u.z, w.z, u.w * w.w));
+                XI[m] = make_float2(fmaf(v.z, w.w, v.w * w.z), u.w * w.z - u.z * w.w);
             }
         }
         __syncwarp();
-        dft16<1, 16>(xr, xi, 0);
-        dft16<1, 16>(yr, yi, 0);   // D; the row's spectrum is Y[m] = D[(m + 1) % 16]
+        dft16x2(XR, XI);   // .x = X; .y = D with the row's spectrum Y[m] = D[(m + 1) % 16]
         {
             const bool t0 = (t == 0);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float ur = xr[j], ui = xi[j], vr = yr[(16 - j) % 16], vi = yi[(16 - j) % 16];
-                if (j < 8) { ur = t0 ? yr[j + 1] : ur; ui = t0 ? yi[j + 1] : ui; }
-                else       { vr = t0 ? xr[16 - j] : vr; vi = t0 ? xi[16 - j] : vi; }
+                float ur = XR[j].x, ui = XI[j].x, vr = XR[(16 - j) % 16].y, vi = XI[(16 - j) % 16].y;
+                if (j < 8) { ur = t0 ? XR[j + 1].y : ur; ui = t0 ? XI[j + 1].y : ui; }
+                else       { vr = t0 ? XR[16 - j].x : vr; vi = t0 ? XI[16 - j].x : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 s_p2[32 * j + lane] = make_float2(fmaf(sr, sr, di * di), fmaf(si, si, dr * dr));   // row 16j+t, FFT g3
             }
@@ -869,10 +936,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 }
 
 // Cepstral mean normalisation of the Kaldi path (reference src/fbank.rs:226-233): out[clip][f][m] -= mean_f out[clip][f][m].
-// One CTA per clip, 4 frame-groups x n_mels columns; the clip's rows were just written and sit in L2.
-__global__ void __launch_bounds__(512, 1) melspec_cmn_kernel(float* out, long long out_clip_stride, int frames_per_clip, int n_mels,
+// One CTA per clip.  Vector path (n_mels % 4 == 0, 16-byte aligned rows): thread = (row group, column quad), float4
+// loads with 4 independent accumulators; the column sums are reduced in a fixed order (deterministic).
+__global__ void __launch_bounds__(512, 2) melspec_cmn_kernel(float* out, long long out_clip_stride, int frames_per_clip, int n_mels,
                                                              const int32_t* lens, int n_samples, int frame_len, int hop) {
-    __shared__ float part[4][128];
+    __shared__ float4 part4[512];
+    __shared__ float mean_s[128];
     const int clip = blockIdx.x;
     int nfr = frames_per_clip;
     if (lens) {
@@ -881,15 +950,63 @@ __global__ void __launch_bounds__(512, 1) melspec_cmn_kernel(float* out, long lo
     }
     if (nfr <= 0) return;
     float* base = out + (long long)clip * out_clip_stride;
-    const int m = threadIdx.x & 127, grp = threadIdx.x >> 7;
-    float acc = 0.f;
-    if (m < n_mels)
-        for (int f = grp; f < nfr; f += 4) acc += base[(long long)f * n_mels + m];
-    part[grp][m] = acc;
-    __syncthreads();
-    const float mean = (part[0][m] + part[1][m] + part[2][m] + part[3][m]) / (float)nfr;
-    if (m < n_mels)
-        for (int f = grp; f < nfr; f += 4) base[(long long)f * n_mels + m] -= mean;
+    const bool vec = (n_mels % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    if (vec) {
+        const int quads = n_mels / 4;                 // <= 32
+        const int rows = 512 / quads;                 // row groups working in parallel
+        const int q = threadIdx.x % quads, r = threadIdx.x / quads;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        if (r < rows) {
+            const float4* src = reinterpret_cast<const float4*>(base) + q;
+            int f = r;
+            for (; f + 3 * rows < nfr; f += 4 * rows) {
+                const float4 v0 = src[(long long)f * quads], v1 = src[(long long)(f + rows) * quads];
+                const float4 v2 = src[(long long)(f + 2 * rows) * quads], v3 = src[(long long)(f + 3 * rows) * quads];
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+                a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+                a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+            }
+            for (; f < nfr; f += rows) {
+                const float4 v0 = src[(long long)f * quads];
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            }
+        }
+        part4[threadIdx.x] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                         (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+        __syncthreads();
+        if (threadIdx.x < quads) {
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int rr = 0; rr < rows; ++rr) {
+                const float4 v = part4[rr * quads + threadIdx.x];
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const float inv = 1.0f / (float)nfr;
+            mean_s[4 * threadIdx.x] = sum.x * inv; mean_s[4 * threadIdx.x + 1] = sum.y * inv;
+            mean_s[4 * threadIdx.x + 2] = sum.z * inv; mean_s[4 * threadIdx.x + 3] = sum.w * inv;
+        }
+        __syncthreads();
+        if (r < rows) {
+            const float4 mu = make_float4(mean_s[4 * q], mean_s[4 * q + 1], mean_s[4 * q + 2], mean_s[4 * q + 3]);
+            float4* dst = reinterpret_cast<float4*>(base) + q;
+            for (int f = r; f < nfr; f += rows) {
+                float4 v = dst[(long long)f * quads];
+                v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
+                dst[(long long)f * quads] = v;
+            }
+        }
+    } else {
+        float* part = reinterpret_cast<float*>(part4);   // [4][128]
+        const int m = threadIdx.x & 127, grp = threadIdx.x >> 7;
+        float acc = 0.f;
+        if (m < n_mels)
+            for (int f = grp; f < nfr; f += 4) acc += base[(long long)f * n_mels + m];
+        part[grp * 128 + m] = acc;
+        __syncthreads();
+        const float mean = (part[m] + part[128 + m] + part[256 + m] + part[384 + m]) / (float)nfr;
+        if (m < n_mels)
+            for (int f = grp; f < nfr; f += 4) base[(long long)f * n_mels + m] -= mean;
+    }
 }
 
 }  // namespace melspec
