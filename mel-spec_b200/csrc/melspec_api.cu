@@ -150,6 +150,7 @@ struct melspec_handle {
     float2* d_proj = nullptr;
     int* d_meta = nullptr;
     int proj_ktot = 0;
+    int kspec = 0;                 // compile-time projection schedule the table matches (1: Whisper-80/fft-400: 14,4,2)
     int proj_wavefront_cost = 0;   // half-warp wavefronts per LDS.64 of the projection loop, summed over entries (ideal: 2 per entry)
     int mpl = 0;
     // host-path resources (lazily created)
@@ -346,6 +347,7 @@ int32_t build_tables(melspec_handle* h) {
         eoff += K;
     }
     h->proj_ktot = std::max(ktot, 1);
+    h->kspec = (N == 400 && h->mpl == 3 && meta[0] == 14 && meta[1] == 4 && meta[2] == 2 && meta[3] == 0) ? 1 : 0;
     MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * win.size()));
     MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
     MS_CUDA(cudaMalloc(&h->d_rot10, sizeof(float2) * rot.size()));
@@ -445,10 +447,11 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const bool m3 = h->mpl <= 3;
     if (h->plan == 400) {
 #define MS_DISPATCH(NW)                                                                                             \
-    (m3 ? (hop160 ? launch_kernel(melspec400_kernel<NW, 3, true>, p, grid, NW * 32, off, st)                         \
-                  : launch_kernel(melspec400_kernel<NW, 3, false>, p, grid, NW * 32, off, st))                        \
-        : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true>, p, grid, NW * 32, off, st)                         \
-                  : launch_kernel(melspec400_kernel<NW, 4, false>, p, grid, NW * 32, off, st)))
+    (h->kspec == 1 && hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 1>, p, grid, NW * 32, off, st)           \
+     : m3 ? (hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 0>, p, grid, NW * 32, off, st)                    \
+                    : launch_kernel(melspec400_kernel<NW, 3, false, 0>, p, grid, NW * 32, off, st))                   \
+          : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true, 0>, p, grid, NW * 32, off, st)                    \
+                    : launch_kernel(melspec400_kernel<NW, 4, false, 0>, p, grid, NW * 32, off, st)))
         rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
     } else {

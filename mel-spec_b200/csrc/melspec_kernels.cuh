@@ -296,7 +296,10 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 -
 // CTA-wide barrier after setup, so the warps of an SM drift into different phases and the FMA, LSU and TMA pipes
 // overlap.  The PCM stage is single-buffered: a pass reads all of its samples into registers first, so the TMA load
 // of the warp's next tile is issued right after that and lands during the rest of the pass.
-template <int NWARPS, int MPL, bool HOP160>
+// KSPEC selects a compile-time projection schedule: 0 = entry counts per slot read from the table (any filterbank),
+// 1 = the Whisper 80-mel / fft-400 bank, whose slots hold 14, 4 and 2 entries (loops fully unrolled: no loop control,
+// no register rotation, all table and power loads of a slot in flight together).  The host picks it by comparing counts.
+template <int NWARPS, int MPL, bool HOP160, int KSPEC>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParams p) {
     using namespace p400;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -508,7 +511,32 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         float mx[FPW];
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
-        {
+        if (KSPEC == 1) {
+            constexpr int KS[4] = {14, 4, 2, 0};
+            const float2* tab = s_proj + lane;
+            int eoff = 0;
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                float acc[FPW];
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
+#pragma unroll
+                for (int e = 0; e < KS[s]; ++e) {
+                    const float2 ent = tab[(eoff + e) * 32];
+                    const float2* pr = s_p + __float_as_int(ent.y);
+                    const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
+                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[1] = fmaf(ent.x, p0.y, acc[1]);
+                    acc[2] = fmaf(ent.x, p1.x, acc[2]); acc[3] = fmaf(ent.x, p1.y, acc[3]);
+                    acc[4] = fmaf(ent.x, p2.x, acc[4]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
+                }
+                eoff += KS[s];
+#pragma unroll
+                for (int q = 0; q < FPW; ++q) {
+                    lg[s][q] = p.log_mul * __log2f(fmaxf(acc[q], p.floor_val));
+                    mx[q] = fmaxf(mx[q], lg[s][q]);
+                }
+            }
+        } else {
             const float2* tab = s_proj + lane;
             float2 nxt = tab[0];   // software-pipelined: the (weight, row) entry of step e+1 is fetched during step e
 #pragma unroll
