@@ -163,18 +163,22 @@ struct melspec_handle {
 
 struct melspec_stream {
     melspec_handle* h = nullptr;
-    int64_t max_chunk = 0;
+    int64_t max_chunk = 0;  // largest push the caller announced
+    int64_t piece = 0;      // samples per internal pipeline piece
     float* d_buf[2] = {nullptr, nullptr};
     int cur = 0;
     int64_t cap = 0;        // samples per device buffer
-    int64_t buffered = 0;   // valid samples in d_buf[cur]
+    int64_t buffered = 0;   // valid samples at the start of d_buf[cur] (the carried tail)
     int64_t to_skip = 0;    // samples still to drop before the first frame (the stream offset c)
-    float* h_pin_in = nullptr;
-    float* h_pin_out = nullptr;
-    float* d_out = nullptr;
-    int64_t out_cap_frames = 0;
+    float* h_pin_in[2] = {nullptr, nullptr};
+    float* h_pin_out[2] = {nullptr, nullptr};
+    float* d_out[2] = {nullptr, nullptr};
+    int64_t out_cap_frames = 0;   // per piece
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};    // staging slot consumed by its H2D copy
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};   // device buffer no longer read by a kernel / tail copy
+    cudaEvent_t ev_d2h[2] = {nullptr, nullptr};    // output staging slot landed on the host
+    bool used_free[2] = {false, false};
 };
 
 namespace {
@@ -700,17 +704,24 @@ int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, mels
     s->h = h;
     s->max_chunk = max_chunk_samples;
     const Resolved& c = h->cfg;
-    s->cap = (max_chunk_samples + c.frame_len + c.hop + 8 + 3) / 4 * 4;
+    // a push is cut into pieces of <= 4 s of 16 kHz audio; piece k+1's H2D copy overlaps piece k's kernel and D2H copy
+    s->piece = std::min<int64_t>(max_chunk_samples, 1 << 16);
+    s->cap = (s->piece + c.frame_len + c.hop + 8 + 3) / 4 * 4;
     s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;   // c = ceil(N/H)*H - N
     s->out_cap_frames = s->cap / c.hop + 2;
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&s->d_buf[i], (size_t)s->cap * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_out, (size_t)s->out_cap_frames * c.n_mels * 4);
-    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_in, (size_t)max_chunk_samples * 4, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_out, (size_t)s->out_cap_frames * c.n_mels * 4, cudaHostAllocDefault);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&s->d_buf[i], (size_t)s->cap * 4);
+        if (e == cudaSuccess) e = cudaMemset(s->d_buf[i], 0, (size_t)s->cap * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_out[i], (size_t)s->out_cap_frames * c.n_mels * 4);
+        if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_in[i], (size_t)s->piece * 4, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pin_out[i], (size_t)s->out_cap_frames * c.n_mels * 4, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_d2h[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->compute_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         melspec_stream_destroy(s);
         return fail_cuda(e, "melspec_stream_create");
@@ -722,8 +733,12 @@ int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, mels
 int32_t melspec_stream_reset(melspec_stream* s) {
     if (!s) return fail(MELSPEC_ERR_INVALID_ARG, "stream is null");
     const Resolved& c = s->h->cfg;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamSynchronize(s->compute_stream);
     s->buffered = 0;
     s->cur = 0;
+    s->used_free[0] = s->used_free[1] = false;
     s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;
     return MELSPEC_OK;
 }
@@ -744,47 +759,94 @@ int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n
     h_samples += skip;
     n -= skip;
     if (n == 0) return MELSPEC_OK;
+    // frames are emitted on whole-hop boundaries: frame k ends at stream offset k*hop + N past the carried tail
     const int64_t total = s->buffered + n;
-    // frames are emitted on whole-hop boundaries: frame k ends at buffer offset k*hop + N
-    const int64_t nf = total >= c.frame_len ? (total - c.frame_len) / c.hop + 1 : 0;
-    if (nf > out_capacity_frames) return fail(MELSPEC_ERR_INVALID_ARG, "out_capacity_frames too small for this push");
-    if (nf > 0 && !h_out) return fail(MELSPEC_ERR_INVALID_ARG, "null output");
-    std::memcpy(s->h_pin_in, h_samples, (size_t)n * 4);
-    float* buf = s->d_buf[s->cur];
-    MS_CUDA(cudaMemcpyAsync(buf + s->buffered, s->h_pin_in, (size_t)n * 4, cudaMemcpyHostToDevice, s->copy_stream));
-    MS_CUDA(cudaEventRecord(s->ev, s->copy_stream));
-    MS_CUDA(cudaStreamWaitEvent(s->compute_stream, s->ev, 0));
-    if (nf > 0) {
-        const int64_t ns4 = std::min<int64_t>((total + 3) / 4 * 4, s->cap);
-        int32_t rc = launch_device(h, buf, 1, s->cap, ns4, nf, nullptr, s->d_out, 0, MELSPEC_LAYOUT_FRAME_MAJOR, s->compute_stream);
-        if (rc) return rc;
-        MS_CUDA(cudaMemcpyAsync(s->h_pin_out, s->d_out, (size_t)nf * c.n_mels * 4, cudaMemcpyDeviceToHost, s->compute_stream));
-        // carry the tail (everything from the start of the next frame) into the other buffer
-        const int64_t consumed = nf * c.hop;
-        const int64_t keep = total - consumed;
-        MS_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, (size_t)keep * 4, cudaMemcpyDeviceToDevice, s->compute_stream));
-        s->cur ^= 1;
-        s->buffered = keep;
-    } else {
-        s->buffered = total;
+    const int64_t nf_total = total >= c.frame_len ? (total - c.frame_len) / c.hop + 1 : 0;
+    if (nf_total > out_capacity_frames) return fail(MELSPEC_ERR_INVALID_ARG, "out_capacity_frames too small for this push");
+    if (nf_total > 0 && !h_out) return fail(MELSPEC_ERR_INVALID_ARG, "null output");
+    // pinned (or registered) caller buffers are DMA'd directly; pageable ones go through the stream's own pinned slots
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool pin_in = is_pinned(h_samples), pin_out = nf_total > 0 && is_pinned(h_out);
+    struct Pending { int slot; int64_t frames, at; };
+    Pending pend[2] = {{-1, 0, 0}, {-1, 0, 0}};
+    int64_t done_frames = 0;
+    int k = 0;
+    for (int64_t off = 0; off < n; off += s->piece, ++k) {
+        const int64_t m = std::min(s->piece, n - off);
+        const int slot = k & 1;
+        float* buf = s->d_buf[s->cur];
+        // the pageable path reuses staging slot `slot`: its previous H2D (two pieces ago) must be done, and the output slot
+        // must have been copied out to the caller
+        const float* src = h_samples + off;
+        if (!pin_in) {
+            if (k >= 2) MS_CUDA(cudaEventSynchronize(s->ev_h2d[slot]));
+            std::memcpy(s->h_pin_in[slot], h_samples + off, (size_t)m * 4);
+            src = s->h_pin_in[slot];
+        }
+        if (!pin_out && pend[slot].slot >= 0) {
+            MS_CUDA(cudaEventSynchronize(s->ev_d2h[slot]));
+            std::memcpy(h_out + pend[slot].at * c.n_mels, s->h_pin_out[slot], (size_t)pend[slot].frames * c.n_mels * 4);
+            pend[slot].slot = -1;
+        }
+        // H2D of this piece behind the carried tail of the current device buffer (side stream); the buffer was last read
+        // by the kernel two pieces ago
+        if (s->used_free[s->cur]) MS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_free[s->cur], 0));
+        MS_CUDA(cudaMemcpyAsync(buf + s->buffered, src, (size_t)m * 4, cudaMemcpyHostToDevice, s->copy_stream));
+        MS_CUDA(cudaEventRecord(s->ev_h2d[slot], s->copy_stream));
+        MS_CUDA(cudaStreamWaitEvent(s->compute_stream, s->ev_h2d[slot], 0));
+        const int64_t have = s->buffered + m;
+        const int64_t nf = have >= c.frame_len ? (have - c.frame_len) / c.hop + 1 : 0;
+        if (nf > 0) {
+            const int64_t ns4 = std::min<int64_t>((have + 3) / 4 * 4, s->cap);
+            int32_t rc = launch_device(h, buf, 1, s->cap, ns4, nf, nullptr, s->d_out[slot], 0, MELSPEC_LAYOUT_FRAME_MAJOR, s->compute_stream);
+            if (rc) return rc;
+            float* dst = pin_out ? h_out + done_frames * c.n_mels : s->h_pin_out[slot];
+            MS_CUDA(cudaMemcpyAsync(dst, s->d_out[slot], (size_t)nf * c.n_mels * 4, cudaMemcpyDeviceToHost, s->compute_stream));
+            MS_CUDA(cudaEventRecord(s->ev_d2h[slot], s->compute_stream));
+            if (!pin_out) pend[slot] = {slot, nf, done_frames};
+            // carry the tail (everything from the start of the next frame) into the other buffer
+            const int64_t consumed = nf * c.hop, keep = have - consumed;
+            const int other = s->cur ^ 1;
+            if (s->used_free[other]) MS_CUDA(cudaStreamWaitEvent(s->compute_stream, s->ev_free[other], 0));
+            MS_CUDA(cudaMemcpyAsync(s->d_buf[other], buf + consumed, (size_t)keep * 4, cudaMemcpyDeviceToDevice, s->compute_stream));
+            MS_CUDA(cudaEventRecord(s->ev_free[s->cur], s->compute_stream));
+            s->used_free[s->cur] = true;
+            s->cur = other;
+            s->buffered = keep;
+            done_frames += nf;
+        } else {
+            s->buffered = have;
+        }
     }
     MS_CUDA(cudaStreamSynchronize(s->compute_stream));
-    if (nf > 0) std::memcpy(h_out, s->h_pin_out, (size_t)nf * c.n_mels * 4);
-    if (frames_emitted) *frames_emitted = nf;
+    MS_CUDA(cudaStreamSynchronize(s->copy_stream));
+    for (int i = 0; i < 2; ++i)
+        if (pend[i].slot >= 0)
+            std::memcpy(h_out + pend[i].at * c.n_mels, s->h_pin_out[i], (size_t)pend[i].frames * c.n_mels * 4);
+    if (frames_emitted) *frames_emitted = done_frames;
     return MELSPEC_OK;
 }
 
 void melspec_stream_destroy(melspec_stream* s) {
     if (!s) return;
     cudaSetDevice(s->h->device);
-    for (int i = 0; i < 2; ++i)
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    if (s->compute_stream) cudaStreamSynchronize(s->compute_stream);
+    for (int i = 0; i < 2; ++i) {
         if (s->d_buf[i]) cudaFree(s->d_buf[i]);
-    if (s->d_out) cudaFree(s->d_out);
-    if (s->h_pin_in) cudaFreeHost(s->h_pin_in);
-    if (s->h_pin_out) cudaFreeHost(s->h_pin_out);
+        if (s->d_out[i]) cudaFree(s->d_out[i]);
+        if (s->h_pin_in[i]) cudaFreeHost(s->h_pin_in[i]);
+        if (s->h_pin_out[i]) cudaFreeHost(s->h_pin_out[i]);
+        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+        if (s->ev_free[i]) cudaEventDestroy(s->ev_free[i]);
+        if (s->ev_d2h[i]) cudaEventDestroy(s->ev_d2h[i]);
+    }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->compute_stream) cudaStreamDestroy(s->compute_stream);
-    if (s->ev) cudaEventDestroy(s->ev);
     delete s;
 }
 

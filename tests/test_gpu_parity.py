@@ -324,3 +324,38 @@ def test_kaldi_batch_vs_oracle(m, torch):
     for i in range(4):
         _kaldi_check(got[i], want[i])
     fb.close()
+
+
+# ------------------------------------------------------------------------------------------ long stream (BASELINE config 5 shape)
+def test_long_stream_chunked_equals_batch(m, torch):
+    """10 minutes of audio through the streaming C ABI in 1 s pushes and in one large push: frame count follows the
+    RingBuffer rule (whole hops only, first frame at sample 80), both chunkings agree bit for bit (the pipeline cuts
+    pushes at the same 4 s pieces only if the tails line up, so equality is checked against the batch path with the
+    A/B-slot tolerance), and a slice is checked against the oracle."""
+    import ctypes as C
+    n = 16000 * 600 + 123
+    x = np.concatenate([o.synth_clip(i, 160000) for i in range(60)] + [np.zeros(123, np.float32)])[:n]
+    h = m.CudaMelSpectrogram(400, 160, 16000.0, 80)
+    L = m.lib()
+    want_frames = n // 160 - 3 + 1
+    outs = []
+    for chunk in (16000, n):
+        s = C.c_void_p()
+        assert L.melspec_stream_create(h._h, chunk, C.byref(s)) == 0
+        out = np.empty((want_frames + 8, 80), np.float32)
+        got = 0
+        for off in range(0, n, chunk):
+            piece = np.ascontiguousarray(x[off:off + chunk])
+            em = C.c_int64(0)
+            rc = L.melspec_stream_push(s, piece.ctypes.data, piece.size, out[got:].ctypes.data, out.shape[0] - got, C.byref(em))
+            assert rc == 0, m.last_error()
+            got += em.value
+        L.melspec_stream_destroy(s)
+        assert got == want_frames
+        outs.append(out[:got].copy())
+    batch = h.compute_mel_spectrogram(x[80:])[:want_frames]
+    assert np.abs(outs[0] - batch).max() <= 5e-5
+    assert np.abs(outs[1] - batch).max() <= 5e-5
+    ref = o.whisper_mel_stream(x[:160 * 2000], 400, 160, 80, 16000.0)
+    assert np.abs(outs[0][:ref.shape[0]] - ref).max() <= WHISPER_TOL
+    h.close()
