@@ -41,8 +41,12 @@ enum {
 enum {
     MELSPEC_FRONTEND_WHISPER = 0, /* Hann -> FFT -> |X|^2 (bins < N/2) -> Slaney mel -> log10/1e-10 -> per-frame max-8, (x+4)/4
                                      src/stft.rs:89-169 + src/mel.rs:148-168,645-654                                         */
-    MELSPEC_FRONTEND_KALDI = 1    /* DC removal, pre-emphasis, Povey, zero-pad to 2^k, FFT, power, Kaldi mel (Hz triangles),
+    MELSPEC_FRONTEND_KALDI = 1,   /* DC removal, pre-emphasis, Povey, zero-pad to 2^k, FFT, power, Kaldi mel (Hz triangles),
                                      ln(max(e, FLT_EPSILON)), optional CMN.  src/fbank.rs:141-236                            */
+    MELSPEC_FRONTEND_NEMO = 2     /* BatchLogMelSpectrogram (NeMo/Parakeet style): whole-waveform pre-emphasis, centre zero
+                                     padding, symmetric Hann of win_length centred in n_fft, power over bins 0..n_fft/2,
+                                     Slaney mel, ln(e + guard), feature-major output padded to a multiple of pad_to, optional
+                                     per-feature mean/std normalisation.  src/mel.rs:171-418, 656-756                        */
 };
 
 /* ---- output layouts ---- */
@@ -70,6 +74,17 @@ typedef struct melspec_config {
     double low_freq;       /* 20 Hz                                                                            */
     double high_freq;      /* 0 => Nyquist                                                                     */
     double energy_floor;   /* <= 0 => FLT_EPSILON                                                              */
+    /* NeMo-only fields (BatchLogMelConfig, src/mel.rs:171-208).  fft_size = n_fft, hop_size = hop_length,
+       preemphasis is shared with the Kaldi block.  Ignored for the other frontends. */
+    int32_t win_length;            /* 400                                                                      */
+    int32_t center;                /* 1: pad n_fft/2 zeros on both sides, frames = len/hop + 1                 */
+    int32_t pad_to;                /* output columns padded (with zeros) to a multiple of this; 0 = none       */
+    int32_t normalize_per_feature; /* (x - mean) / (std + 1e-5) per mel row over the valid frames              */
+    int32_t htk;                   /* mel scale: 0 Slaney, 1 HTK                                               */
+    int32_t slaney_norm;           /* area-normalise the triangles                                             */
+    double log_zero_guard;         /* added to the mel energy before ln(); must be finite and > 0              */
+    double f_min;                  /* Hz                                                                       */
+    double f_max;                  /* Hz, 0 => sampling_rate / 2                                               */
 } melspec_config;
 
 typedef struct melspec_handle melspec_handle;
@@ -87,8 +102,12 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
 void melspec_destroy(melspec_handle* h);
 
 /* Frames produced for a clip of `n_samples`: 0 if shorter than one frame, else (n - frame)/hop + 1
- * (src/stft.rs:153-157, src/fbank.rs:147-151). */
+ * (src/stft.rs:153-157, src/fbank.rs:147-151); NeMo frontend: n/hop + 1 when centred (src/mel.rs:387-395). */
 int64_t melspec_num_frames(const melspec_handle* h, int64_t n_samples);
+
+/* Output columns per clip for the NeMo frontend: melspec_num_frames rounded up to a multiple of pad_to
+ * (src/mel.rs:751-756); equals melspec_num_frames for the other frontends. */
+int64_t melspec_padded_frames(const melspec_handle* h, int64_t n_samples);
 
 /* The reference's batching knob (src/cuda.rs:150-155: min(8192, 64 MiB / bytes-per-frame)); kept for API
  * parity.  This implementation has no such limit on the device path; the value is what the reference returns. */
@@ -118,7 +137,8 @@ int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacit
  *   d_pcm            n_clips rows of f32 samples, row r at d_pcm + r*clip_stride
  *   n_samples        samples per row (rows shorter than that: pass d_lens)
  *   d_lens           optional DEVICE array of n_clips int32 valid lengths (<= n_samples); NULL = all n_samples
- *   d_out            frame-major: [n_clips][F][n_mels], mel-major: [n_clips][n_mels][F], F = melspec_num_frames(n_samples);
+ *   d_out            frame-major: [n_clips][F][n_mels], mel-major: [n_clips][n_mels][F], F = melspec_num_frames(n_samples)
+ *                    (NeMo frontend: mel-major [n_clips][n_mels][melspec_padded_frames(n_samples)], padding columns zeroed);
  *                    clip r at d_out + r*out_clip_stride (floats; 0 = dense F*n_mels).  Frames past a short clip's
  *                    own frame count are left untouched.
  * Fast path (TMA bulk copies) needs 16-byte aligned d_pcm/d_out, clip_stride % 4 == 0 and n_samples % 4 == 0;

@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # every symbol include/melspec_b200.h declares
 EXPORTS = [
     "melspec_abi_version", "melspec_last_error", "melspec_default_config", "melspec_build_filterbank",
-    "melspec_num_frames_cfg", "melspec_create", "melspec_destroy", "melspec_num_frames",
+    "melspec_num_frames_cfg", "melspec_create", "melspec_destroy", "melspec_num_frames", "melspec_padded_frames",
     "melspec_max_frames_per_batch", "melspec_n_mels", "melspec_fft_size", "melspec_hop_size", "melspec_filterbank",
     "melspec_compute_device", "melspec_compute_host", "melspec_stream_create", "melspec_stream_push",
     "melspec_stream_reset", "melspec_stream_destroy", "melspec_launch_count",
@@ -34,6 +34,9 @@ class MelspecConfig(C.Structure):
         ("sampling_rate", C.c_double),
         ("frame_length", C.c_int32), ("apply_cmn", C.c_int32), ("use_log_fbank", C.c_int32), ("use_power", C.c_int32),
         ("preemphasis", C.c_double), ("low_freq", C.c_double), ("high_freq", C.c_double), ("energy_floor", C.c_double),
+        ("win_length", C.c_int32), ("center", C.c_int32), ("pad_to", C.c_int32), ("normalize_per_feature", C.c_int32),
+        ("htk", C.c_int32), ("slaney_norm", C.c_int32),
+        ("log_zero_guard", C.c_double), ("f_min", C.c_double), ("f_max", C.c_double),
     ]
 
 
@@ -82,6 +85,8 @@ def lib() -> C.CDLL:
     L.melspec_destroy.argtypes = [vp]
     L.melspec_num_frames.restype = i64
     L.melspec_num_frames.argtypes = [vp, i64]
+    L.melspec_padded_frames.restype = i64
+    L.melspec_padded_frames.argtypes = [vp, i64]
     for name in ("melspec_max_frames_per_batch", "melspec_n_mels", "melspec_fft_size", "melspec_hop_size"):
         getattr(L, name).restype = i32
         getattr(L, name).argtypes = [vp]

@@ -25,6 +25,7 @@ from . import _lib
 
 FRONTEND_WHISPER = 0
 FRONTEND_KALDI = 1
+FRONTEND_NEMO = 2
 LAYOUT_FRAME_MAJOR = 0
 LAYOUT_MEL_MAJOR = 1
 
@@ -101,6 +102,48 @@ def _kaldi_cfg(fc: FbankConfig) -> _lib.MelspecConfig:
     c.fft_size, c.n_mels, c.sampling_rate = fc.fft_size(), int(fc.num_mel_bins), float(fc.sample_rate)
     c.apply_cmn, c.use_log_fbank, c.use_power = int(fc.apply_cmn), int(fc.use_log_fbank), int(fc.use_power)
     c.preemphasis, c.low_freq, c.high_freq, c.energy_floor = fc.preemphasis, fc.low_freq, fc.high_freq, fc.energy_floor
+    return c
+
+
+@dataclass
+class BatchLogMelConfig:
+    """reference src/mel.rs:171-208 with its Default."""
+    sample_rate: int = 16000
+    n_fft: int = 512
+    win_length: int = 400
+    hop_length: int = 160
+    n_mels: int = 80
+    f_min: float = 0.0
+    f_max: float | None = None
+    htk: bool = False
+    norm: bool = True
+    preemphasis: float = 0.0
+    center: bool = True
+    log_zero_guard: float = float(np.finfo(np.float32).eps)
+    pad_to: int = 0
+    normalize_per_feature: bool = False
+
+
+class BatchLogMelError(ValueError):
+    """reference src/mel.rs:210-231 (`InvalidConfig`)."""
+
+
+@dataclass
+class BatchLogMelOutput:
+    """reference src/mel.rs:233-237: flat feature-major data with its shape."""
+    data: np.ndarray
+    rows: int
+    cols: int
+
+
+def _nemo_cfg(bc: BatchLogMelConfig) -> _lib.MelspecConfig:
+    c = _lib.MelspecConfig()
+    c.frontend = FRONTEND_NEMO
+    c.fft_size, c.win_length, c.frame_length, c.hop_size = int(bc.n_fft), int(bc.win_length), int(bc.win_length), int(bc.hop_length)
+    c.n_mels, c.sampling_rate = int(bc.n_mels), float(bc.sample_rate)
+    c.preemphasis, c.center, c.pad_to = float(bc.preemphasis), int(bc.center), int(bc.pad_to)
+    c.normalize_per_feature, c.htk, c.slaney_norm = int(bc.normalize_per_feature), int(bc.htk), int(bc.norm)
+    c.log_zero_guard, c.f_min, c.f_max = float(bc.log_zero_guard), float(bc.f_min), float(bc.f_max or 0.0)
     return c
 
 
@@ -236,6 +279,45 @@ class Fbank(_Handle):
 
     def dense_filterbank(self) -> np.ndarray:
         return kaldi_mel_filterbank(self.config)
+
+
+class BatchLogMelSpectrogram(_Handle):
+    """reference src/mel.rs:239-396: `BatchLogMelSpectrogram(BatchLogMelConfig()).compute(samples)` ->
+    (n_mels, padded_frames) f32, feature-major; `compute_flat` returns the flat data with rows/cols."""
+
+    def __init__(self, config: BatchLogMelConfig | None = None, device: int = 0):
+        self.config = config or BatchLogMelConfig()
+        c = self.config
+        for bad, msg in ((c.sample_rate == 0, "sample_rate must be > 0"), (c.n_fft == 0, "n_fft must be > 0"),
+                         (c.win_length == 0, "win_length must be > 0"), (c.win_length > c.n_fft, "win_length must be <= n_fft"),
+                         (c.hop_length == 0, "hop_length must be > 0"), (c.n_mels == 0, "n_mels must be > 0"),
+                         (not np.isfinite(c.log_zero_guard) or c.log_zero_guard <= 0.0, "log_zero_guard must be finite and > 0")):
+            if bad:
+                raise BatchLogMelError(f"invalid log-mel config: {msg}")      # src/mel.rs:656-683
+        super().__init__(_nemo_cfg(c), device)
+
+    def padded_frames(self, n_samples: int) -> int:
+        return int(self._L.melspec_padded_frames(self._h, int(n_samples)))
+
+    def compute(self, samples) -> np.ndarray:
+        x = np.ascontiguousarray(np.asarray(samples, dtype=np.float32).reshape(-1))
+        cols = self.padded_frames(x.size)
+        out = np.zeros((self.n_mels, cols), dtype=np.float32)
+        if cols:
+            frames = C.c_int64(0)
+            _check(self._L.melspec_compute_host(self._h, x.ctypes.data, 1, x.size, x.size, out.ctypes.data,
+                                                LAYOUT_MEL_MAJOR, C.byref(frames)))
+        return out
+
+    def compute_flat(self, samples) -> BatchLogMelOutput:
+        f = self.compute(samples)
+        return BatchLogMelOutput(f.reshape(-1), f.shape[0], f.shape[1])
+
+    def filters(self) -> np.ndarray:
+        c = _nemo_cfg(self.config)
+        out = np.zeros((self.config.n_mels, self.config.n_fft // 2 + 1), dtype=np.float64)
+        _check(_lib.lib().melspec_build_filterbank(C.byref(c), out.ctypes.data_as(C.POINTER(C.c_double)), out.size), True)
+        return out
 
 
 class RingBuffer:

@@ -38,25 +38,27 @@ int32_t fail_cuda(cudaError_t e, const char* what) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ filterbanks (f64)
-// Slaney scale, the math of SURVEY Appendix A.1 / reference src/mel.rs:547-643 (htk = false, norm = true, 0..sr/2).
-double slaney_hz_to_mel(double f) {
+// Slaney / HTK mel scales and librosa-style triangles: the math of SURVEY Appendix A.1 / reference src/mel.rs:547-643.
+double mel_from_hz(double f, bool htk) {
+    if (htk) return 2595.0 * std::log10(1.0 + f / 700.0);
     const double f_sp = 200.0 / 3.0, brk = 1000.0, brk_mel = brk / f_sp, step = std::log(6.4) / 27.0;
     return f >= brk ? brk_mel + std::log(f / brk) / step : f / f_sp;
 }
-double slaney_mel_to_hz(double m) {
+double hz_from_mel(double m, bool htk) {
+    if (htk) return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
     const double f_sp = 200.0 / 3.0, brk = 1000.0, brk_mel = brk / f_sp, step = std::log(6.4) / 27.0;
     return m >= brk_mel ? brk * std::exp(step * (m - brk_mel)) : f_sp * m;
 }
-void build_slaney(double sr, int n_fft, int n_mels, std::vector<double>& w) {
+void build_slaney(double sr, int n_fft, int n_mels, double f_min, double f_max, bool htk, bool norm, std::vector<double>& w) {
     const int nb = n_fft / 2 + 1;
     w.assign((size_t)n_mels * nb, 0.0);
     std::vector<double> edge(n_mels + 2);
-    const double lo = slaney_hz_to_mel(0.0), hi = slaney_hz_to_mel(sr / 2.0);
+    const double lo = mel_from_hz(f_min, htk), hi = mel_from_hz(f_max, htk);
     const double step = (hi - lo) / (double)(n_mels + 1);
-    for (int i = 0; i < n_mels + 2; ++i) edge[i] = slaney_mel_to_hz(lo + step * (double)i);
+    for (int i = 0; i < n_mels + 2; ++i) edge[i] = hz_from_mel(lo + step * (double)i, htk);
     for (int m = 0; m < n_mels; ++m) {
         const double up = edge[m + 1] - edge[m], dn = edge[m + 2] - edge[m + 1];
-        const double area = 2.0 / (edge[m + 2] - edge[m]);
+        const double area = norm ? 2.0 / (edge[m + 2] - edge[m]) : 1.0;
         for (int b = 0; b < nb; ++b) {
             const double f = (sr / (double)n_fft) * (double)b;
             const double rise = std::min(std::max((f - edge[m]) / up, 0.0), 1.0);
@@ -95,6 +97,9 @@ struct Resolved {
     int frontend, fft, hop, n_mels, frame_len;
     double sr, preemph, low, high, floor;
     int cmn, use_log, use_power;
+    // NeMo frontend
+    int center = 0, pad_to = 0, norm_feat = 0, htk = 0, slaney_norm = 1;
+    double guard = 0.0;
 };
 
 int32_t resolve(const melspec_config* c, Resolved& r) {
@@ -117,6 +122,20 @@ int32_t resolve(const melspec_config* c, Resolved& r) {
         r.preemph = c->preemphasis; r.low = c->low_freq; r.high = c->high_freq == 0.0 ? r.sr / 2.0 : c->high_freq;
         r.floor = c->energy_floor > 0.0 ? c->energy_floor : (double)1.1920928955078125e-07f;
         r.cmn = c->apply_cmn; r.use_log = c->use_log_fbank; r.use_power = c->use_power;
+    } else if (c->frontend == MELSPEC_FRONTEND_NEMO) {   // validate_batch_config, src/mel.rs:656-683
+        r.fft = c->fft_size;
+        r.frame_len = c->win_length;
+        if (r.fft <= 0) return fail(MELSPEC_ERR_INVALID_CONFIG, "n_fft must be > 0");
+        if (r.frame_len <= 0) return fail(MELSPEC_ERR_INVALID_CONFIG, "win_length must be > 0");
+        if (r.frame_len > r.fft) return fail(MELSPEC_ERR_INVALID_CONFIG, "win_length must be <= n_fft");
+        if (r.hop <= 0) return fail(MELSPEC_ERR_INVALID_CONFIG, "hop_length must be > 0");
+        if (r.n_mels <= 0) return fail(MELSPEC_ERR_INVALID_CONFIG, "n_mels must be > 0");
+        if (!std::isfinite(c->log_zero_guard) || c->log_zero_guard <= 0.0)
+            return fail(MELSPEC_ERR_INVALID_CONFIG, "log_zero_guard must be finite and > 0");
+        r.preemph = c->preemphasis; r.low = c->f_min; r.high = c->f_max == 0.0 ? c->sampling_rate / 2.0 : c->f_max;
+        r.floor = 0.0; r.cmn = 0; r.use_log = 1; r.use_power = 1;
+        r.center = c->center; r.pad_to = c->pad_to < 0 ? 0 : c->pad_to; r.norm_feat = c->normalize_per_feature;
+        r.htk = c->htk; r.slaney_norm = c->slaney_norm; r.guard = c->log_zero_guard;
     } else {
         return fail(MELSPEC_ERR_INVALID_CONFIG, "unknown frontend");
     }
@@ -126,12 +145,24 @@ int32_t resolve(const melspec_config* c, Resolved& r) {
 }
 
 void build_filterbank(const Resolved& r, std::vector<double>& w) {
-    if (r.frontend == MELSPEC_FRONTEND_WHISPER) build_slaney(r.sr, r.fft, r.n_mels, w);
+    if (r.frontend == MELSPEC_FRONTEND_WHISPER) build_slaney(r.sr, r.fft, r.n_mels, 0.0, r.sr / 2.0, false, true, w);
+    else if (r.frontend == MELSPEC_FRONTEND_NEMO) build_slaney(r.sr, r.fft, r.n_mels, r.low, r.high, r.htk != 0, r.slaney_norm != 0, w);
     else build_kaldi(r.sr, r.fft, r.n_mels, r.low, r.high, w);
 }
 
 int64_t frames_for(const Resolved& r, int64_t n) {
+    if (r.frontend == MELSPEC_FRONTEND_NEMO) {   // src/mel.rs:321-328, 387-395 (empty input => no columns)
+        if (n <= 0) return 0;
+        if (r.center) return n / r.hop + 1;
+        return n < r.fft ? 0 : (n - r.fft) / r.hop + 1;
+    }
     return n < r.frame_len ? 0 : (n - r.frame_len) / r.hop + 1;
+}
+
+int64_t padded_frames_for(const Resolved& r, int64_t n) {
+    const int64_t f = frames_for(r, n);
+    if (r.frontend != MELSPEC_FRONTEND_NEMO || r.pad_to <= 0) return f;
+    return (f + r.pad_to - 1) / r.pad_to * r.pad_to;   // src/mel.rs:751-756
 }
 
 }  // namespace
@@ -206,7 +237,10 @@ int32_t build_tables(melspec_handle* h) {
     auto window_at = [&](int i) -> float {
         if (c.frontend == MELSPEC_FRONTEND_WHISPER)   // periodic Hann, reference src/stft.rs:141-145
             return (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N)));
-        if (i >= c.frame_len) return 0.f;             // Povey window, zero padded to the FFT size (src/fbank.rs:100-105,184-190)
+        if (i >= c.frame_len) return 0.f;
+        if (c.frontend == MELSPEC_FRONTEND_NEMO)      // symmetric Hann of win_length (src/mel.rs:708-719); its position inside
+            return (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(c.frame_len - 1)));   // n_fft only shifts phase
+        // Povey window, zero padded to the FFT size (src/fbank.rs:100-105,184-190)
         return (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(c.frame_len - 1)), 0.85);
     };
     if (N == 400) {   // the kernel evaluates the periodic Hann window from these per-worker phase factors
@@ -394,14 +428,21 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const Resolved& c = h->cfg;
     if (n_clips == 0 || frames_per_clip == 0) return MELSPEC_OK;
     if (n_samples > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "n_samples per clip must fit in int32");
-    const bool kaldi = c.frontend == MELSPEC_FRONTEND_KALDI;
+    const bool kaldi = c.frontend == MELSPEC_FRONTEND_KALDI, nemo = c.frontend == MELSPEC_FRONTEND_NEMO;
     if (kaldi && layout != MELSPEC_LAYOUT_FRAME_MAJOR)
         return fail(MELSPEC_ERR_UNSUPPORTED, "the Kaldi frontend produces (T, n_mels) frame-major output only");
+    if (nemo && layout != MELSPEC_LAYOUT_MEL_MAJOR)
+        return fail(MELSPEC_ERR_UNSUPPORTED, "the NeMo frontend produces (n_mels, frames) feature-major output only");
+    if (nemo && d_lens) return fail(MELSPEC_ERR_UNSUPPORTED, "per-clip lengths are not supported by the NeMo frontend yet");
+    const int64_t row_stride = nemo ? padded_frames_for(c, n_samples) : frames_per_clip;
     const int fpw = h->plan == 400 ? p400::FPW : p512::FPW;
     KParams p{};
     p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
     p.clip_stride = clip_stride;
-    p.out_clip_stride = out_clip_stride ? out_clip_stride : frames_per_clip * c.n_mels;
+    p.out_clip_stride = out_clip_stride ? out_clip_stride : row_stride * c.n_mels;
+    p.out_row_stride = (int)row_stride;
+    p.frame_offset = nemo ? (c.fft - c.frame_len) / 2 - (c.center ? c.fft / 2 : 0) : 0;
+    p.log_add = nemo ? (float)c.guard : 0.f;
     p.n_samples = (int)n_samples;
     p.frames_per_clip = (int)frames_per_clip;
     p.wtiles_per_clip = (int)((frames_per_clip + fpw - 1) / fpw);
@@ -419,6 +460,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
+    else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
     // shared-memory carve-up: [mbarriers | window | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
@@ -459,16 +501,31 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
     } else {
-#define MS_DISPATCH(NW)                                                                                             \
-    (m3 ? (kaldi ? launch_kernel(melspec512_kernel<NW, 3, true>, p, grid, NW * 32, off, st)                          \
-                 : launch_kernel(melspec512_kernel<NW, 3, false>, p, grid, NW * 32, off, st))                         \
-        : (kaldi ? launch_kernel(melspec512_kernel<NW, 4, true>, p, grid, NW * 32, off, st)                          \
-                 : launch_kernel(melspec512_kernel<NW, 4, false>, p, grid, NW * 32, off, st)))
-        rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
+#define MS_DISPATCH(NW, MODE)                                                                                       \
+    (m3 ? launch_kernel(melspec512_kernel<NW, 3, MODE>, p, grid, NW * 32, off, st)                                   \
+        : launch_kernel(melspec512_kernel<NW, 4, MODE>, p, grid, NW * 32, off, st))
+        if (nemo) {
+            // padding columns (pad_to) are zeros in the reference's feature matrix (src/mel.rs:336)
+            if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
+                MS_CUDA(cudaMemset2DAsync(d_out + frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - frames_per_clip) * 4,
+                                          (size_t)n_clips * c.n_mels, st));
+            rc = nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
+        } else if (kaldi) {
+            rc = nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
+        } else {
+            rc = nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
+        }
 #undef MS_DISPATCH
     }
     if (rc != MELSPEC_OK) return rc;
     h->launches += 1;
+    if (nemo && c.norm_feat) {   // per-feature mean/std couples all frames of a clip: second kernel (src/mel.rs:721-749)
+        const long long rows = (long long)n_clips * c.n_mels;
+        melspec_featnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_out, p.out_clip_stride, p.out_row_stride,
+                                                                          p.frames_per_clip, c.n_mels, (int)rows);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
     if (kaldi && c.cmn) {   // CMN couples all frames of a clip: second, small kernel over rows that are still in L2
         melspec_cmn_kernel<<<(unsigned)n_clips, 512, 0, st>>>(d_out, p.out_clip_stride, p.frames_per_clip, c.n_mels, d_lens,
                                                              p.n_samples, c.frame_len, c.hop);
@@ -533,6 +590,15 @@ int32_t melspec_default_config(int32_t frontend, melspec_config* cfg) {
         cfg->energy_floor = 0.0;
         return MELSPEC_OK;
     }
+    if (frontend == MELSPEC_FRONTEND_NEMO) {    // BatchLogMelConfig::default(), src/mel.rs:189-208
+        cfg->fft_size = 512;
+        cfg->win_length = 400;
+        cfg->frame_length = 400;
+        cfg->center = 1;
+        cfg->slaney_norm = 1;
+        cfg->log_zero_guard = (double)1.1920928955078125e-07f;
+        return MELSPEC_OK;
+    }
     return fail(MELSPEC_ERR_INVALID_ARG, "unknown frontend");
 }
 
@@ -576,10 +642,11 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
     if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400) plan = 400;
     else if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 512 && r.hop == 160) plan = 512;
     else if (r.frontend == MELSPEC_FRONTEND_KALDI && r.fft == 512 && r.frame_len == 400 && r.hop == 160 && r.use_power) plan = 512;
+    else if (r.frontend == MELSPEC_FRONTEND_NEMO && r.fft == 512 && r.frame_len == 400 && r.hop == 160) plan = 512;
     if (!plan)
         return fail(MELSPEC_ERR_UNSUPPORTED,
                     "supported plans: Whisper fft_size 400 (any hop), Whisper fft_size 512 / hop 160, Kaldi 400-sample frames / "
-                    "hop 160 / power spectrum");
+                    "hop 160 / power spectrum, NeMo n_fft 512 / win_length 400 / hop 160");
     MS_CUDA(cudaSetDevice(device));
     melspec_handle* h = new (std::nothrow) melspec_handle();
     if (!h) return fail(MELSPEC_ERR_CUDA, "out of host memory");
@@ -614,6 +681,7 @@ void melspec_destroy(melspec_handle* h) {
 }
 
 int64_t melspec_num_frames(const melspec_handle* h, int64_t n_samples) { return h ? frames_for(h->cfg, n_samples) : -1; }
+int64_t melspec_padded_frames(const melspec_handle* h, int64_t n_samples) { return h ? padded_frames_for(h->cfg, n_samples) : -1; }
 
 int32_t melspec_max_frames_per_batch(const melspec_handle* h) {
     if (!h) return 0;
@@ -666,7 +734,7 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     // Clips are cut into chunks that rotate over 3 (stream, device slot) pairs, so the H2D copy of chunk i+1, the
     // kernel of chunk i and the D2H copy of chunk i-1 overlap when the host buffers are pinned.
     const int64_t ns4 = (n_samples + 3) / 4 * 4;   // device rows are padded to 16 bytes so the TMA path applies
-    const int64_t clip_out = F * h->cfg.n_mels;
+    const int64_t clip_out = padded_frames_for(h->cfg, n_samples) * h->cfg.n_mels;
     const int64_t target = 32ll << 20;             // ~32 MiB of PCM per chunk
     int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
     per_chunk = std::min(per_chunk, n_clips);

@@ -55,8 +55,11 @@ struct KParams {
     float floor_val;         // 1e-10 (Whisper) — floor applied to the *unscaled* energy
     float log_mul;           // log10(2) (Whisper)
     int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
-    int frame_len;           // samples per frame before zero padding (fft_size for Whisper, 400 for Kaldi)
-    float preemph;           // Kaldi pre-emphasis coefficient
+    int frame_len;           // samples per frame before zero padding (fft_size for Whisper, 400 for Kaldi / NeMo)
+    float preemph;           // Kaldi / NeMo pre-emphasis coefficient
+    int frame_offset;        // NeMo: first sample of frame 0 relative to the clip (-200 when centred, +56 otherwise)
+    float log_add;           // NeMo: log_zero_guard added to the energy before ln()
+    int out_row_stride;      // mel-major output: floats between mel rows (NeMo: padded frame count)
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
                     for (int q = 0; q < FPW; ++q) {
                         const float v = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
-                        if (q < nvalid) dst[(long long)mel * p.frames_per_clip + q] = v;
+                        if (q < nvalid) dst[(long long)mel * p.out_row_stride + q] = v;
                     }
                 }
             }
@@ -698,12 +701,15 @@ constexpr int NCHUNK = 4;                    // 3*160 + 512 = 992 samples
 __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 - r; }
 }  // namespace p512
 
-template <int NWARPS, int MPL, bool KALDI>
+// MODE 0: Whisper fft 512.  MODE 1: Kaldi fbank.  MODE 2: NeMo BatchLogMel (whole-waveform pre-emphasis, frames may
+// hang over both ends of the clip: the missing samples are zero-filled in the stage, reference src/mel.rs:344-348,685-706).
+template <int NWARPS, int MPL, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NLOAD = KALDI ? 35 : 42;     // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
-    constexpr int NROW = KALDI ? 25 : 32;      // non-zero rows of a frame (Kaldi: 400 samples zero-padded to 512)
+    constexpr bool KALDI = MODE == 1, NEMO = MODE == 2, FRAME400 = MODE != 0;
+    constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
+    constexpr int NROW = FRAME400 ? 25 : 32;   // non-zero rows of a frame (400 samples zero-padded to 512)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -742,7 +748,32 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
         const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
-        if (p.bulk_in) {
+        if (NEMO) {
+            // tile-relative range [lo, hi) that exists in the clip; everything else of [0, need) is zero (centre padding,
+            // frames hanging over the end)
+            const long long t0 = s0 + p.frame_offset;
+            const int lo = t0 < 0 ? (int)(-t0) : 0;
+            const long long endl = (long long)p.n_samples - t0;
+            const int hi = endl < need ? (endl < lo ? lo : (int)endl) : need;
+            const float* tsrc = p.pcm + (long long)clip * p.clip_stride + t0;
+            if (lo > 0 || hi < need)
+                for (int i = lane; i < need; i += 32)
+                    if (i < lo || i >= hi) s_pcm[i + PAD * (i / CHUNK)] = 0.f;
+            if (p.bulk_in && hi > lo) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)(hi - lo) * 4u);
+#pragma unroll
+                    for (int k = 0; k < NCHUNK; ++k) {
+                        const int a = max(lo, CHUNK * k), b = min(hi, CHUNK * (k + 1));
+                        if (a < b) bulk_g2s(smem_u32(s_pcm + k * CS + (a - CHUNK * k)), tsrc + a, (uint32_t)(b - a) * 4u, bar);
+                    }
+                }
+            } else {
+                for (int i = lo + lane; i < hi; i += 32) s_pcm[i + PAD * (i / CHUNK)] = __ldg(tsrc + i);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);
+            }
+        } else if (p.bulk_in) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
 #pragma unroll
@@ -765,16 +796,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const int clip = wt / p.wtiles_per_clip;
         const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
         int nfr = p.frames_per_clip;
-        if (p.lens) {
+        if (!NEMO && p.lens) {
             const int len = min(p.lens[clip], p.n_samples);
             nfr = len < p.frame_len ? 0 : (len - p.frame_len) / 160 + 1;
         }
         const int nvalid = max(0, min(FPW, nfr - fw0));
 
-        // Kaldi look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it)
+        // pre-emphasis look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it)
         float lead = 0.f;
-        const bool owns_first = KALDI && g1 == 0 && c == 0;
-        if (owns_first && fw0 > 0) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + (long long)fw0 * 160 - 1);
+        const bool owns_first = FRAME400 && g1 == 0 && c == 0;
+        const long long tile0 = (long long)fw0 * 160 + (NEMO ? p.frame_offset : 0);   // clip index of tile sample 0
+        if (owns_first && tile0 > 0) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + tile0 - 1);
 
         mbar_wait(bar, it & 1);
 
@@ -787,7 +819,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             float x[NLOAD];
 #pragma unroll
             for (int m = 0; m < NLOAD; ++m) x[m] = px[16 * m + PAD * (m / 20)];
-            if (!KALDI) {
+            if (!FRAME400) {
 #pragma unroll
                 for (int a = 0; a < 16; ++a) {
                     const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
@@ -808,18 +840,31 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     } else {
                         xp = px[16 * m + PAD * (m / 20) - 1];
                     }
-                    if (m < 25) sa += x[m];
-                    if (m >= 10) sb += x[m];
+                    if (KALDI && m < 25) sa += x[m];
+                    if (KALDI && m >= 10) sb += x[m];
                     x[m] = fmaf(-p.preemph, xp, x[m]);
                 }
+                float ka = 0.f, kb = 0.f;
+                if (KALDI) {
 #pragma unroll
-                for (int o = 8; o >= 1; o >>= 1) {
-                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    for (int o = 8; o >= 1; o >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    }
+                    const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
+                    if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
+                    ka = (1.0f - p.preemph) * mu_a; kb = (1.0f - p.preemph) * mu_b;
+                } else {
+                    // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
+                    // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
+                    const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
+                    if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
+#pragma unroll
+                        for (int m = 0; m < NLOAD; ++m)
+                            if (rel == 16 * m) x[m] = 0.f;
+                    }
+                    (void)x0;
                 }
-                const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
-                if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
-                const float ka = (1.0f - p.preemph) * mu_a, kb = (1.0f - p.preemph) * mu_b;
 #pragma unroll
                 for (int a = 0; a < 16; ++a) {
                     float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
@@ -911,7 +956,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 eoff += K;
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
-                    const float e = fmaxf(acc[q], p.floor_val);
+                    const float e = fmaxf(acc[q], p.floor_val) + p.log_add;
                     lg[s][q] = p.log_mul != 0.f ? p.log_mul * __log2f(e) : e;
                     mx[q] = fmaxf(mx[q], lg[s][q]);
                 }
@@ -954,7 +999,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                     for (int q = 0; q < FPW; ++q)
                         if (q < nvalid)
-                            dst[(long long)mel * p.frames_per_clip + q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                            dst[(long long)mel * p.out_row_stride + q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
                 }
             }
             __syncwarp();
@@ -1035,6 +1080,28 @@ __global__ void __launch_bounds__(512, 2) melspec_cmn_kernel(float* out, long lo
         if (m < n_mels)
             for (int f = grp; f < nfr; f += 4) base[(long long)f * n_mels + m] -= mean;
     }
+}
+
+// Per-feature normalisation of the NeMo frontend (reference src/mel.rs:721-749): for every mel row of a clip,
+// x <- (x - mean) / (sqrt(sum (x - mean)^2 / max(F - 1, 1)) + 1e-5) over the F valid frames.  One warp per row
+// (mel-major rows are contiguous), fixed-order lane-strided sums + xor-shuffle tree: deterministic.
+__global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long long out_clip_stride, int row_stride, int frames,
+                                                               int n_mels, int n_rows_total) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_rows_total || frames <= 0) return;
+    const int clip = row / n_mels, mel = row - clip * n_mels;
+    float* r = out + (long long)clip * out_clip_stride + (long long)mel * row_stride;
+    float sum = 0.f;
+    for (int f = lane; f < frames; f += 32) sum += r[f];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)frames;
+    float var = 0.f;
+    for (int f = lane; f < frames; f += 32) { const float d = r[f] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float inv = 1.0f / (sqrtf(var / fmaxf((float)frames - 1.0f, 1.0f)) + 1e-5f);
+    for (int f = lane; f < frames; f += 32) r[f] = (r[f] - mean) * inv;
 }
 
 }  // namespace melspec

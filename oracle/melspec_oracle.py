@@ -332,3 +332,87 @@ def reference_test_signal(n_samples: int = 16000, sample_rate: float = 16000.0) 
          + np.float32(0.10) * np.sin(two_pi * np.float32(880.0) * t)
          + np.float32(0.05) * np.sin(two_pi * np.float32(1760.0) * t))
     return x.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# BatchLogMelSpectrogram — the NeMo/Parakeet-style whole-utterance frontend (src/mel.rs:171-418, 656-756)
+# The reference computes this path in f32 (f32 window, rustfft<f32>, f32 projection and ln).  `batch_log_mel` below is
+# the same arithmetic in f64 (the semantics); `dtype=np.float32` reruns it with an f32 FFT (scipy pocketfft) to show
+# the reference's own f32 noise level.  PARITY UNPINNED for the feature values: the reference's tests hold no output
+# vector for this path (only the (128, 101) shape, src/mel.rs:943-961, and the filterbank golden nemo_mel_filters.npz,
+# src/mel.rs:852-871, which pins slaney_mel_filterbank(16000, 512, 80)).
+# --------------------------------------------------------------------------------------------
+def general_mel_filterbank(sr, n_fft, n_mels, f_min=0.0, f_max=None, htk=False, norm=True):
+    """`SparseMelFilterbank::from_mel` -> `mel()` (src/mel.rs:73-85, 547-589) with explicit f_min/f_max/htk/norm."""
+    return slaney_mel_filterbank(sr, n_fft, n_mels, f_min, f_max, htk, norm)
+
+
+def centered_hann_window(n_fft: int, win_length: int, dtype=np.float64) -> np.ndarray:
+    """src/mel.rs:708-719: symmetric Hann of win_length centred in n_fft (f32 in the reference)."""
+    w = np.zeros(n_fft, dtype=dtype)
+    if win_length <= 1:
+        return w
+    off = (n_fft - win_length) // 2
+    i = np.arange(win_length, dtype=dtype)
+    w[off:off + win_length] = dtype(0.5) - dtype(0.5) * np.cos((dtype(2.0) * dtype(math.pi) * i) / dtype(win_length - 1.0))
+    return w
+
+
+def batch_num_frames(n: int, n_fft: int, hop: int, center: bool) -> int:
+    """src/mel.rs:387-395."""
+    if center:
+        return n // hop + 1
+    return 0 if n < n_fft else (n - n_fft) // hop + 1
+
+
+def pad_len(n: int, pad_to: int) -> int:
+    """src/mel.rs:751-756."""
+    return n if pad_to == 0 else -(-n // pad_to) * pad_to
+
+
+def batch_log_mel(samples, sample_rate=16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, f_min=0.0,
+                  f_max=None, htk=False, norm=True, preemphasis=0.0, center=True, log_zero_guard=F32_EPS, pad_to=0,
+                  normalize_per_feature=False, dtype=np.float64) -> np.ndarray:
+    """src/mel.rs:321-385 `compute_flat_with_scratch`.  Returns (n_mels, padded_frames) f32, feature-major."""
+    x = np.asarray(samples, dtype=np.float32)
+    if x.size == 0:
+        return np.zeros((n_mels, 0), dtype=np.float32)
+    valid = batch_num_frames(x.size, n_fft, hop_length, center)
+    padded_frames = pad_len(valid, pad_to)
+    wave = x.astype(dtype)
+    if preemphasis != 0.0:                                   # src/mel.rs:696-706
+        wave = np.concatenate([wave[:1], wave[1:] - dtype(preemphasis) * wave[:-1]])
+    if center:                                               # src/mel.rs:685-694
+        pad = n_fft // 2
+        wave = np.concatenate([np.zeros(pad, dtype), wave, np.zeros(pad, dtype)])
+    need = (valid - 1) * hop_length + n_fft if valid else 0
+    if wave.size < need:                                     # .get(start+i).unwrap_or(0.0), src/mel.rs:346-347
+        wave = np.concatenate([wave, np.zeros(need - wave.size, dtype)])
+    window = centered_hann_window(n_fft, win_length, dtype)
+    filt = general_mel_filterbank(float(sample_rate), n_fft, n_mels, f_min,
+                                  float(sample_rate) / 2.0 if f_max is None else f_max, htk, norm)
+    feats = np.zeros((n_mels, padded_frames), dtype=np.float32)
+    if valid:
+        idx = (np.arange(valid) * hop_length)[:, None] + np.arange(n_fft)[None, :]
+        fr = wave[idx] * window[None, :]
+        if dtype == np.float32:
+            import scipy.fft as sfft
+            spec = sfft.fft(fr.astype(np.complex64), axis=1)[:, :n_fft // 2 + 1]
+        else:
+            spec = np.fft.fft(fr, axis=1)[:, :n_fft // 2 + 1]
+        power = (spec.real ** 2 + spec.imag ** 2).astype(dtype)
+        e = np.zeros((valid, n_mels), dtype=dtype)
+        for m, (bins, wts) in enumerate(sparse_rows(filt)):            # project_power_f32, src/mel.rs:127-146
+            acc = np.zeros(valid, dtype=dtype)
+            for b, w in zip(bins, wts):
+                acc = acc + dtype(w) * power[:, b]
+            e[:, m] = acc
+        feats[:, :valid] = np.log(e + dtype(log_zero_guard)).T.astype(np.float32)
+    if normalize_per_feature and valid:                      # src/mel.rs:721-749
+        v = feats[:, :valid].astype(dtype)
+        mean = v.sum(axis=1, keepdims=True) / dtype(valid)
+        denom = max(float(valid) - 1.0, 1.0)
+        var = ((v - mean) ** 2).sum(axis=1, keepdims=True) / dtype(denom)
+        std = np.sqrt(var) + dtype(1e-5)
+        feats[:, :valid] = ((v - mean) / std).astype(np.float32)
+    return feats

@@ -116,3 +116,36 @@ def test_kaldi_config_known_answers():
     assert abs(o.kaldi_mel_to_hz(o.kaldi_hz_to_mel(1000.0)) - 1000.0) < 1e-9
     assert o.kaldi_fbank(np.zeros(16000, np.float32)).shape == (98, 80)
     assert o.kaldi_fbank(np.zeros(399, np.float32)).shape == (0, 80)
+
+
+# ------------------------------------------------------------------------------------------ NeMo BatchLogMel
+def test_nemo_oracle_shape_contract_and_framing():
+    # src/mel.rs:943-961: 16000 zeros, 128 mels, pre-emphasis 0.97, guard 2^-24, per-feature normalisation => (128, 101)
+    f = o.batch_log_mel(np.zeros(16000, np.float32), n_mels=128, preemphasis=0.97, log_zero_guard=2.0 ** -24,
+                        normalize_per_feature=True)
+    assert f.shape == (128, 101) and np.isfinite(f).all()
+    assert o.batch_log_mel(np.zeros(0, np.float32)).shape == (80, 0)
+    # src/mel.rs:387-395, 751-756
+    assert o.batch_num_frames(16000, 512, 160, True) == 101 and o.batch_num_frames(16000, 512, 160, False) == 97
+    assert o.batch_num_frames(511, 512, 160, False) == 0 and o.batch_num_frames(1, 512, 160, True) == 1
+    assert o.pad_len(101, 0) == 101 and o.pad_len(101, 16) == 112 and o.pad_len(112, 16) == 112
+    # silence: every valid column is ln(guard); pad_to columns stay zero (src/mel.rs:336)
+    g = o.batch_log_mel(np.zeros(1600, np.float32), log_zero_guard=2.0 ** -24, pad_to=16)
+    assert g.shape == (80, 16) and np.allclose(g[:, :11], np.log(2.0 ** -24)) and np.all(g[:, 11:] == 0.0)
+
+
+def test_nemo_oracle_filterbank_and_window(golden_dir):
+    # src/mel.rs:852-871: slaney_mel_filterbank(16000, 512, 80) vs nemo_mel_filters.npz within 1e-7
+    gold = np.load(os.path.join(golden_dir, "nemo_filters_80x257.npy"))
+    assert np.abs(o.general_mel_filterbank(16000.0, 512, 80) - gold).max() <= 1e-7
+    w = o.centered_hann_window(512, 400)
+    assert np.all(w[:56] == 0.0) and np.all(w[456:] == 0.0) and abs(w[56 + 199] - w[56 + 200]) < 1e-12
+    assert w[56] == 0.0 and abs(w.max() - 1.0) < 1e-4
+
+
+def test_nemo_oracle_f32_pipeline_distance(jfk):
+    # the reference runs this path in f32 (src/mel.rs:321-385); the f64 restatement is within the f32 pipeline's noise
+    a = o.batch_log_mel(jfk[:48000], n_mels=128, preemphasis=0.97, log_zero_guard=2.0 ** -24)
+    b = o.batch_log_mel(jfk[:48000], n_mels=128, preemphasis=0.97, log_zero_guard=2.0 ** -24, dtype=np.float32)
+    assert a.shape == b.shape == (128, 301)
+    assert np.abs(a - b).max() < 5e-3
