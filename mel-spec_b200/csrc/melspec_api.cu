@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "melspec_kernels.cuh"
@@ -289,10 +290,127 @@ int32_t build_tables(melspec_handle* h) {
             if (w != 0.0) bands[m].e.push_back({b, w});
         }
     }
+    std::vector<float2> proj;
+    std::vector<int> meta(kMetaInts, -1);
+    h->mpl = (c.n_mels + 31) / 32;
+    if (N == 400) {
+        // ---- plan 400: windowed projection program (melspec400_kernel).  A lane's slot-s entries are K_s consecutive bins
+        // [start, start + K_s) of the bin-ordered power planes; the table holds the weights only.
+        struct Piece { int mel, b0, len; };
+        std::vector<Piece> pcs;
+        for (int m = 0; m < c.n_mels; ++m) {
+            Piece pc{m, 1, 0};
+            if (!bands[m].e.empty()) { pc.b0 = bands[m].e.front().first; pc.len = bands[m].e.back().first - pc.b0 + 1; }
+            pcs.push_back(pc);
+        }
+        std::stable_sort(pcs.begin(), pcs.end(), [](const Piece& a, const Piece& b) { return a.len > b.len; });
+        while ((int)pcs.size() < 32 * h->mpl) pcs.push_back(Piece{-1, 1, 0});   // idle lanes of the last slot
+        int K[kMaxMpl] = {0, 0, 0, 0}, ktot = 0;
+        for (int s = 0; s < h->mpl; ++s) { K[s] = pcs[(size_t)32 * s].len; ktot += K[s]; meta[s] = K[s]; }
+        for (int s = h->mpl; s < kMaxMpl; ++s) meta[s] = 0;
+        // (1) The output rows are staged with one 32-bit store per (slot, frame): conflict-free when the 32 mels of a slot
+        // differ mod 32.  Pieces may change slots as long as they still fit (len <= K of the new slot).
+        auto stage_cost = [&]() {
+            int tot = 0;
+            for (int s = 0; s < h->mpl; ++s) {
+                int cnt[32] = {0};
+                for (int l = 0; l < 32; ++l) if (pcs[(size_t)32 * s + l].mel >= 0) tot += cnt[pcs[(size_t)32 * s + l].mel & 31]++;
+            }
+            return tot;
+        };
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        auto rnd = [&rng](int n) {
+            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+            return (int)((rng >> 33) % (uint64_t)n);
+        };
+        int sc = stage_cost();
+        for (int iter = 0; iter < 20000 && sc > 0; ++iter) {
+            const int a = rnd(32 * h->mpl), b = rnd(32 * h->mpl);
+            if (a / 32 == b / 32 || pcs[a].len > K[b / 32] || pcs[b].len > K[a / 32]) continue;
+            std::swap(pcs[a], pcs[b]);
+            const int nc = stage_cost();
+            if (nc <= sc) sc = nc; else std::swap(pcs[a], pcs[b]);
+        }
+        // (2) Window starts: piece i may start anywhere in [max(1, b0 + len - K), min(b0, 201 - K)] (rows 1..200 are the ones
+        // the kernel writes every pass).  The three LDS.64 of an entry are conflict-free when the 16 lanes of a half-warp
+        // start at 16 different rows mod 16: a perfect matching of the slot's 32 pieces onto (half-warp, residue) pairs
+        // (Kuhn's augmenting paths; whatever stays unmatched is placed anyway and merely costs a wavefront).
+        const int ktot4 = std::max(4, (ktot + 3) / 4 * 4);
+        std::vector<float> wtab((size_t)2 * ktot4 * 32, 0.f);
+        int eoff = 0;
+        h->proj_wavefront_cost = 0;
+        for (int s = 0; s < h->mpl; ++s) {
+            const int Ks = K[s];
+            int lo[32], hi[32];
+            for (int i = 0; i < 32; ++i) {
+                const Piece& pc = pcs[(size_t)32 * s + i];
+                lo[i] = std::max(1, pc.b0 + pc.len - Ks);
+                hi[i] = std::min(pc.b0, 201 - Ks);
+                if (pc.len == 0) { lo[i] = 1; hi[i] = std::max(1, 201 - Ks); }
+                if (hi[i] < lo[i]) hi[i] = lo[i];
+            }
+            int owner[32];   // (half-warp, residue) -> piece
+            std::fill(owner, owner + 32, -1);
+            std::function<bool(int, std::vector<char>&)> augment = [&](int i, std::vector<char>& seen) {
+                for (int st = lo[i]; st <= hi[i] && st < lo[i] + 16; ++st)
+                    for (int hw = 0; hw < 2; ++hw) {
+                        const int node = 16 * hw + (st & 15);
+                        if (seen[node]) continue;
+                        seen[node] = 1;
+                        if (owner[node] < 0 || augment(owner[node], seen)) { owner[node] = i; return true; }
+                    }
+                return false;
+            };
+            std::vector<int> order(32);
+            for (int i = 0; i < 32; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hi[a] - lo[a] < hi[b] - lo[b]; });
+            std::vector<int> unmatched;
+            for (int i : order) {
+                std::vector<char> seen(32, 0);
+                if (!augment(i, seen)) unmatched.push_back(i);
+            }
+            int lane_piece[32], lane_start[32];
+            std::fill(lane_piece, lane_piece + 32, -1);
+            int fill[2] = {0, 0};
+            for (int node = 0; node < 32; ++node) {
+                const int i = owner[node];
+                if (i < 0) continue;
+                const int hw = node / 16, l = 16 * hw + fill[hw]++;
+                int st = lo[i];
+                while ((st & 15) != (node & 15)) ++st;
+                lane_piece[l] = i; lane_start[l] = st;
+            }
+            for (int i : unmatched) {
+                const int hw = fill[0] < 16 ? 0 : 1, l = 16 * hw + fill[hw]++;
+                lane_piece[l] = i; lane_start[l] = lo[i];
+                h->proj_wavefront_cost += 3 * Ks;
+            }
+            for (int l = 0; l < 32; ++l) {
+                const Piece& pc = pcs[(size_t)32 * s + lane_piece[l]];
+                meta[kMaxMpl + s * 32 + l] = pc.mel;
+                const int plane_unit = lane_start[l];
+                meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = plane_unit;
+                for (int e = 0; e < Ks; ++e) {
+                    const int bin = lane_start[l] + e;
+                    const float w = (pc.mel >= 0 && bin < nb) ? (float)(h->dense[(size_t)pc.mel * nb + bin] * 0.25) : 0.f;
+                    const bool inband = pc.len > 0 && bin >= pc.b0 && bin < pc.b0 + pc.len;
+                    const int ge = eoff + e;
+                    wtab[(size_t)ge * 32 + l] = inband ? w : 0.f;
+                    wtab[(size_t)ktot4 * 32 + ((size_t)(ge >> 2) * 32 + l) * 4 + (ge & 3)] = inband ? w : 0.f;
+                }
+            }
+            h->proj_wavefront_cost += 2 * 3 * Ks;
+            eoff += Ks;
+        }
+        for (int s = h->mpl; s < kMaxMpl; ++s)
+            for (int l = 0; l < 32; ++l) meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = 1;
+        h->proj_ktot = ktot4;
+        h->kspec = (h->mpl == 3 && K[0] == 14 && K[1] == 4 && K[2] == 2) ? 1 : 0;
+        proj.resize(wtab.size() / 2);
+        std::memcpy(proj.data(), wtab.data(), wtab.size() * sizeof(float));
+    } else {
     std::vector<Band> sorted = bands;
     std::stable_sort(sorted.begin(), sorted.end(), [](const Band& a, const Band& b) { return a.e.size() > b.e.size(); });
-    h->mpl = (c.n_mels + 31) / 32;
-    std::vector<int> meta(kMaxMpl + kMaxMpl * 32, -1);
     int ktot = 0;
     for (int s = 0; s < kMaxMpl; ++s) {
         int K = 0;
@@ -307,7 +425,7 @@ int32_t build_tables(melspec_handle* h) {
     // (LDS.64, processed per half-warp): it is bank-conflict free when the 16 lanes of a half-warp hit rows that
     // differ mod 16.  Which lane of a slot owns which mel, the order of a mel's entries and the rows that padding
     // entries point at are all free, so a small deterministic hill-climb minimises the number of wavefronts.
-    std::vector<float2> proj((size_t)(std::max(ktot, 1) + 1) * 32, make_float2(0.f, 0.f));   // + one padding row (prefetch)
+    proj.assign((size_t)(std::max(ktot, 1) + 1) * 32, make_float2(0.f, 0.f));   // + one padding row (prefetch)
     int eoff = 0;
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     auto rnd = [&rng](int n) {
@@ -385,7 +503,8 @@ int32_t build_tables(melspec_handle* h) {
         eoff += K;
     }
     h->proj_ktot = std::max(ktot, 1);
-    h->kspec = (N == 400 && h->mpl == 3 && meta[0] == 14 && meta[1] == 4 && meta[2] == 2 && meta[3] == 0) ? 1 : 0;
+    h->kspec = 0;
+    }
     MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * win.size()));
     MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
     MS_CUDA(cudaMalloc(&h->d_rot10, sizeof(float2) * rot.size()));
@@ -459,6 +578,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.window = reinterpret_cast<const float2*>(h->d_window); p.twiddle = h->d_twiddle; p.rot10 = h->d_rot10;
     p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
+    if (p.floor_val > 0.f && p.floor_val < 1.17549435e-38f) p.floor_val = 1.17549435e-38f;   // lg2_normal() flushes denormals
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
@@ -469,7 +589,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.smem_tw = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
     p.smem_rot = (int)off; off = up(off + 256, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
-    p.smem_meta = (int)off; off = up(off + sizeof(int) * (kMaxMpl + kMaxMpl * 32), 128);
+    p.smem_meta = (int)off; off = up(off + sizeof(int) * kMetaInts, 128);
     p.smem_warp0 = (int)off;
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
     static_assert(p512::FPW * 32 * kMaxMpl * 4 <= p512::STAGE_MAX, "output rows must fit behind the power rows");

@@ -9,7 +9,7 @@
 // so PCM is read once from HBM (TMA bulk copies into shared memory) and mel frames are written once.
 //
 // Thread organisation ("plan 400"): a warp owns 3 complex FFTs = 6 frames per pass; 10 lanes cooperate on one FFT
-// (lane = 3*t + g: t = worker 0..9, g = FFT 0..2; lanes 30,31 shadow lane 29).  N = 400 = 20 x 20:
+// (lane = 10*g + t: t = worker 0..9, g = FFT 0..2; lanes 30,31 shadow lane 29).  N = 400 = 20 x 20:
 //   step 1  worker t transforms columns n2 = 2t, 2t+1 (elements x[20*n1 + n2]) with a 20-point DFT -> Y[n2][k1]
 //   exchange through the warp's private shared-memory slab Z[slot(k1)][n2][g]   (only __syncwarp, no CTA barrier)
 //   step 3  worker t owns rows k1 = t and 20-t (t = 0: rows 0 and 10): twiddle, 20-point DFT over n2 -> X[k1 + 20*k2].
@@ -49,9 +49,11 @@ struct KParams {
     const float4* twiddle;   // [10 i][10 workers]  W_400^(t*2i), W_400^(t*(2i+1)) as (re,im,re,im); row 20-t uses the
                              // conjugates + an output rotation
     const float2* rot10;     // [20]  W_40^(-c): row 10 is pre-rotated on the write side so worker 0 fits the same scheme
-    const float2* proj;      // [proj_ktot][32] (weight, __int_as_float(3*row))
-    const int* proj_meta;    // [kMaxMpl] K_s, then [kMaxMpl][32] mel index or -1
-    int proj_ktot;
+    const float2* proj;      // plan 512: [proj_ktot][32] (weight, __int_as_float(row))
+                             // plan 400: floats, [proj_ktot4][32] weights (entry-major) then [proj_ktot4/4][32][4] (lane-major quads)
+    const int* proj_meta;    // [kMaxMpl] K_s, then [kMaxMpl][32] mel index or -1, then (plan 400) [kMaxMpl][32] first bin of the
+                             // lane's window (the K_s consecutive power rows its entries multiply)
+    int proj_ktot;           // plan 400: entries rounded up to a multiple of 4
     float floor_val;         // 1e-10 (Whisper) — floor applied to the *unscaled* energy
     float log_mul;           // log10(2) (Whisper)
     int normalize;           // 1: per-frame max-8 clamp and (x+4)/4
@@ -65,6 +67,7 @@ struct KParams {
 };
 
 constexpr int kMaxMpl = 4;
+constexpr int kMetaInts = kMaxMpl + 2 * kMaxMpl * 32;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +107,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// log2 of a normal, positive number: the energies are floored (>= 1e-10 / FLT_EPSILON / log_zero_guard) before the
+// logarithm, so the denormal fix-up that __log2f() carries (FSETP + 2 predicated FMUL/FADD per call) is dead weight
+__device__ __forceinline__ float lg2_normal(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ float warp_max_f32(float v) {
     float r;
@@ -281,13 +292,18 @@ __device__ __forceinline__ void dft32(float (&xr)[32], float (&xi)[32]) {
 namespace p400 {
 constexpr int N = 400;
 constexpr int FPW = 6;          // frames per warp pass (3 complex FFTs)
-constexpr int ZROW = 35;        // 16-byte units per Z slot row: 20 complex x 3 FFTs = 30 units + 5 pad  (35 = 3 mod 8)
+constexpr int ZROW = 33;        // 16-byte units per Z slot row: 20 complex x 3 FFTs = 30 units + 3 pad  (33 = 1 mod 8)
 constexpr int ZSLOTS = 20;
-constexpr int ZBYTES = ZSLOTS * ZROW * 16;   // 11200 per warp
-constexpr int PBYTES = 200 * 3 * 8;          // power slab: 200 rows x 3 FFTs x (frame A, frame B), reuses the Z slab
+constexpr int ZBYTES = ZSLOTS * ZROW * 16;   // 10560 per warp
+// power slab (reuses the Z slab): one plane per FFT, plane[bin] = float2(|A|^2, |B|^2), bins in natural order so that a mel
+// band is a run of consecutive rows.  Plane origins (in float2 units) are 0, 6, 0 mod 16: with lane = 10 g + t that is
+// the best a 64-bit store can do (3 wavefronts instead of 2; see tools/smem_model.py), reads are conflict-free.
+constexpr int PPLANE1 = 214, PPLANE2 = 416;
+constexpr int PBYTES = (PPLANE2 + 201 + 1) * 8;   // 4944
 constexpr int STAGE_MAX = ZBYTES - PBYTES;   // room for the 6 x n_mels output rows behind the power rows
 constexpr int CHUNK = 320;      // samples per TMA bulk copy (two hops of 160)
-constexpr int PAD320 = 12;      // words of padding after each chunk in the staged PCM tile (bank spreading)
+constexpr int PAD320 = 20;      // words of padding after each chunk in the staged PCM tile: with lane = 10 g + t the 64-bit
+                                // loads of a half-warp then fall into 16 distinct bank pairs
 constexpr int CS320 = CHUNK + PAD320;
 constexpr int NCHUNK = 4;       // a warp tile spans 5*160 + 400 = 1200 samples = 3.75 chunks
 __host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 - r; }
@@ -310,10 +326,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int l30 = lane < 30 ? lane : 29;   // lanes 30,31 shadow lane 29 (same addresses, same values)
-    const int t = l30 / 3;                   // worker within the FFT
-    const int g = l30 - 3 * t;               // which of the warp's 3 FFTs: frames fw0 + 2g (re) and fw0 + 2g + 1 (im)
+    const int g = l30 / 10;                  // which of the warp's 3 FFTs: frames fw0 + 2g (re) and fw0 + 2g + 1 (im)
+    const int t = l30 - 10 * g;              // worker within the FFT
 
-    const float2* s_proj = reinterpret_cast<const float2*>(smem + p.smem_proj);
+    const float* s_projw = reinterpret_cast<const float*>(smem + p.smem_proj);
     const int* s_meta = reinterpret_cast<const int*>(smem + p.smem_meta);
     unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
     float4* s_z = reinterpret_cast<float4*>(s_warp);          // Z exchange slab, later reused as the power slab
@@ -323,8 +339,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
 
     // ---- one-time setup: tables into shared memory, barriers, per-lane window / twiddle registers
-    for (int i = threadIdx.x; i < (p.proj_ktot + 1) * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
-    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
+    for (int i = threadIdx.x; i < 2 * p.proj_ktot * 32; i += NWARPS * 32)
+        reinterpret_cast<float*>(smem + p.smem_proj)[i] = reinterpret_cast<const float*>(p.proj)[i];
+    for (int i = threadIdx.x; i < kMetaInts; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -420,7 +437,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             asm volatile("" : "+f"(w_cos.x), "+f"(w_cos.y), "+f"(w_sin.x), "+f"(w_sin.y));
             if (HOP160) {
                 // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
-                // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16)
+                // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16).  Conflict-free: a half-warp's 16 float2
+                // addresses are 10 consecutive units of one FFT + 6 of the next, 170 = 10 (mod 16) units further on
                 const float* px = s_pcm + g * CS320 + 2 * t;
                 float2 x[28];
 #pragma unroll
@@ -478,11 +496,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         // XR[n] = (row t, row 20-t) real parts, XI[n] = imaginary parts: again two transforms per packed instruction
         f2 XR[20], XI[20];
         {
-            const float4* z1 = s_z + ZROW * t + g;
-            const float4* z2 = s_z + ZROW * (10 + t) + g;
+            const float4* z1 = s_z + ZROW * t + 10 * g;          // row stride 33 = 1 (mod 8) units: a quarter-warp's 8 loads
+            const float4* z2 = s_z + ZROW * (10 + t) + 10 * g;   // (t + 2g mod 8 all different) never share a bank group
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
-                const float4 v = z1[3 * i], u = z2[3 * i], w = TW_IN_REGS ? twreg[i] : s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
+                const float4 v = z1[i], u = z2[i], w = TW_IN_REGS ? twreg[i] : s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
                 const int n = 2 * i, m = 2 * i + 1;
                 XR[n] = make_float2(v.x * w.x - v.z * w.y, fmaf(u.x, w.x, u.z * w.y));         // x * tw ,  y * conj(tw)
                 XI[n] = make_float2(fmaf(v.x, w.y, v.z * w.x), u.z * w.x - u.x * w.y);
@@ -495,7 +513,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         {
             // Pair slot j: generic worker (rows a, 20-a): (X[j], Y[19-j])  -> bin a+20j (j<10) or its mirror.
             // Worker 0 (rows 0, 10): j<10: (Y[j], Y[19-j]) -> bin 10+20j;  j>=10: (X[j], X[20-j]) -> bin 20(20-j).
+            // The powers go to this FFT's plane in natural bin order: slot j < 10 is bin 20j + t (worker 0: 20j + 10),
+            // slot j >= 10 is the mirror bin 20(20-j) - t, so the ten workers of an FFT store ten consecutive rows.
             const bool t0 = (t == 0);
+            float2* const pl = s_p + (g == 0 ? 0 : g == 1 ? PPLANE1 : PPLANE2);
+            float2* const p_lo = pl + (t0 ? 10 : t);
+            float2* const p_hi = pl - t;
 #pragma unroll
             for (int j = 0; j < 20; ++j) {
                 float ur = XR[j].x, ui = XI[j].x, vr = XR[(20 - j) % 20].y, vi = XI[(20 - j) % 20].y;
@@ -504,64 +527,59 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 const float pwa = fmaf(sr, sr, di * di);   // 4|A[k]|^2
                 const float pwb = fmaf(si, si, dr * dr);   // 4|B[k]|^2
-                s_p[30 * j + l30] = make_float2(pwa, pwb);
+                if (j < 10) p_lo[20 * j] = make_float2(pwa, pwb);
+                else        p_hi[20 * (20 - j)] = make_float2(pwa, pwb);
             }
         }
         __syncwarp();
 
         // ------------------------------------------------------------------ banded mel projection + log (+ normalise)
+        // Lane l owns up to MPL mels (slot s: mel meta[s][l]).  A mel's non-zero weights are a run of consecutive bins, so
+        // its entries are K_s consecutive rows of the three power planes starting at the lane's window start (immediate
+        // offsets, no per-entry address); the host places the windows so that the 16 lanes of a half-warp start at 16
+        // different rows mod 16 (conflict-free LDS.64).  acc[g] = (frame 2g, frame 2g+1) advances as one packed FFMA2.
         float lg[MPL][FPW];
         float mx[FPW];
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
-        if (KSPEC == 1) {
-            constexpr int KS[4] = {14, 4, 2, 0};
-            const float2* tab = s_proj + lane;
+        {
+            constexpr int KS[4] = {14, 4, 2, 0};   // KSPEC == 1: the Whisper 80-mel / fft-400 bank
+            const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
+            const float* wt = s_projw + lane;                                                          // [entry][lane]
             int eoff = 0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                float acc[FPW];
+                const float2* pr = s_p + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
+                f2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0;
+                if (KSPEC == 1) {
+                    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
-#pragma unroll
-                for (int e = 0; e < KS[s]; ++e) {
-                    const float2 ent = tab[(eoff + e) * 32];
-                    const float2* pr = s_p + __float_as_int(ent.y);
-                    const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
-                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[1] = fmaf(ent.x, p0.y, acc[1]);
-                    acc[2] = fmaf(ent.x, p1.x, acc[2]); acc[3] = fmaf(ent.x, p1.y, acc[3]);
-                    acc[4] = fmaf(ent.x, p2.x, acc[4]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
-                }
-                eoff += KS[s];
-#pragma unroll
-                for (int q = 0; q < FPW; ++q) {
-                    lg[s][q] = p.log_mul * __log2f(fmaxf(acc[q], p.floor_val));
-                    mx[q] = fmaxf(mx[q], lg[s][q]);
-                }
-            }
-        } else {
-            const float2* tab = s_proj + lane;
-            float2 nxt = tab[0];   // software-pipelined: the (weight, row) entry of step e+1 is fetched during step e
-#pragma unroll
-            for (int s = 0; s < MPL; ++s) {
-                const int K = s_meta[s];
-                float acc[FPW];
-#pragma unroll
-                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
+                    for (int e = 0; e < KS[s]; ++e) {
+                        const int ge = eoff + e;
+                        if ((ge & 3) == 0 || e == 0) w4 = wq[(ge >> 2) * 32];
+                        const float w = (ge & 3) == 0 ? w4.x : (ge & 3) == 1 ? w4.y : (ge & 3) == 2 ? w4.z : w4.w;
+                        const f2 ww = make_float2(w, w);
+                        acc0 = fma2(ww, pr[e], acc0);
+                        acc1 = fma2(ww, pr[PPLANE1 + e], acc1);
+                        acc2 = fma2(ww, pr[PPLANE2 + e], acc2);
+                    }
+                    eoff += KS[s];
+                } else {
+                    const int K = s_meta[s];
 #pragma unroll 2
-                for (int e = 0; e < K; ++e) {
-                    const float2 ent = nxt;
-                    tab += 32;
-                    nxt = tab[0];      // the table carries one padding row at its end
-                    const float2* pr = s_p + __float_as_int(ent.y);
-                    const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
-                    acc[0] = fmaf(ent.x, p0.x, acc[0]); acc[1] = fmaf(ent.x, p0.y, acc[1]);
-                    acc[2] = fmaf(ent.x, p1.x, acc[2]); acc[3] = fmaf(ent.x, p1.y, acc[3]);
-                    acc[4] = fmaf(ent.x, p2.x, acc[4]); acc[5] = fmaf(ent.x, p2.y, acc[5]);
+                    for (int e = 0; e < K; ++e) {
+                        const float w = wt[(eoff + e) * 32];
+                        const f2 ww = make_float2(w, w);
+                        acc0 = fma2(ww, pr[e], acc0);
+                        acc1 = fma2(ww, pr[PPLANE1 + e], acc1);
+                        acc2 = fma2(ww, pr[PPLANE2 + e], acc2);
+                    }
+                    eoff += K;
                 }
+                const float a[FPW] = {acc0.x, acc0.y, acc1.x, acc1.y, acc2.x, acc2.y};
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
-                    lg[s][q] = p.log_mul * __log2f(fmaxf(acc[q], p.floor_val));
+                    lg[s][q] = p.log_mul * lg2_normal(fmaxf(a[q], p.floor_val));
                     mx[q] = fmaxf(mx[q], lg[s][q]);
                 }
             }
@@ -957,7 +975,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
                     const float e = fmaxf(acc[q], p.floor_val) + p.log_add;
-                    lg[s][q] = p.log_mul != 0.f ? p.log_mul * __log2f(e) : e;
+                    lg[s][q] = p.log_mul != 0.f ? p.log_mul * lg2_normal(e) : e;
                     mx[q] = fmaxf(mx[q], lg[s][q]);
                 }
             }
