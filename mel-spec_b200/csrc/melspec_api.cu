@@ -518,8 +518,8 @@ int32_t build_tables(melspec_handle* h) {
     return MELSPEC_OK;
 }
 
-// Warps per CTA (one persistent CTA per SM).  Measured best: 8 for plan 400 (no spills, twiddles stay in registers),
-// 12 for plan 512 (168 registers/thread).  MELSPEC_WARPS=8|12 overrides for tuning; the count must be a multiple of 4
+// Warps per CTA (one persistent CTA per SM).  Measured best: 12 for both plans (168 registers/thread, three warps per
+// scheduler hide the fixed 2-cycle issue cadence of the packed FADD2/FFMA2 stream better than two).  MELSPEC_WARPS=8|12 overrides for tuning; the count must be a multiple of 4
 // (registers are allocated per SM sub-partition).
 int warps_per_cta(int plan) {
     static int forced = [] {
@@ -527,7 +527,8 @@ int warps_per_cta(int plan) {
         const int v = e ? std::atoi(e) : 0;
         return (v == 8 || v == 12) ? v : 0;
     }();
-    return forced ? forced : (plan == 400 ? 8 : 12);
+    (void)plan;
+    return forced ? forced : 12;
 }
 
 template <typename Kern>

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     using namespace p400;
     extern __shared__ __align__(128) unsigned char smem[];
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the tile-loop state lives in uniform registers
     const int lane = threadIdx.x & 31;
     const int l30 = lane < 30 ? lane : 29;   // lanes 30,31 shadow lane 29 (same addresses, same values)
     const int g = l30 / 10;                  // which of the warp's 3 FFTs: frames fw0 + 2g (re) and fw0 + 2g + 1 (im)
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
     constexpr int NROW = FRAME400 ? 25 : 32;   // non-zero rows of a frame (400 samples zero-padded to 512)
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the tile-loop state lives in uniform registers
     const int lane = threadIdx.x & 31;
     const int c = lane & 15, g1 = lane >> 4;   // step-1 role
     const int t = lane >> 1, g3 = lane & 1;    // step-3 role
