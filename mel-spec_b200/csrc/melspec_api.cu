@@ -587,8 +587,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
     p.smem_win = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
-    p.smem_tw = (int)off; off = up(off + (h->plan == 400 ? 1600 : 2048), 128);
-    p.smem_rot = (int)off; off = up(off + 256, 128);
+    p.smem_tw = (int)off; off = up(off + (h->plan == 400 ? 4800 : 2048), 128);   // plan 400: one copy per FFT of the warp
+    p.smem_rot = (int)off; off = up(off + 512, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * kMetaInts, 128);
     p.smem_warp0 = (int)off;

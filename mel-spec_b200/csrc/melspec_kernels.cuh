@@ -348,11 +348,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     }
     // window and twiddle tables are lane-dependent (10 distinct rows, shared by the warp's 3 FFTs); they are read
     // from shared memory each pass instead of pinning 78 registers, which is what lets 12 warps live on an SM
-    for (int i = threadIdx.x; i < 100; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
+    // three copies (one per FFT of the warp), [i][g][t]: a warp's LDS.128 then covers 30 consecutive 16-byte units instead of
+    // 10 units read three times in a lane order that collides inside the quarter-warps
+    for (int i = threadIdx.x; i < 300; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[10 * (i / 30) + (i % 30) % 10];
     // Periodic Hann window of columns 2t, 2t+1, evaluated on the fly (two packed FFMA2 per row instead of a table read):
     //   w[20*n1 + c] = 0.5 - 0.5 cos(2 pi n1/20 + th_c) = 0.5 + WC[n1] cos(th_c) + WS[n1] sin(th_c),  th_c = 2 pi c/400
-    const float4 wth = __ldg(reinterpret_cast<const float4*>(p.window) + t);   // (cos th_2t, cos th_2t+1, sin th_2t, sin th_2t+1)
-    const f2 w_cos0 = make_float2(wth.x, wth.y), w_sin0 = make_float2(wth.z, wth.w);
+    // the per-worker phase factors (cos th_2t, cos th_2t+1, sin th_2t, sin th_2t+1) sit in shared memory, one copy per lane:
+    // with 12 warps per SM there is no register to park them in between passes (one conflict-free LDS.128 per pass)
+    for (int i = threadIdx.x; i < 30; i += NWARPS * 32)
+        reinterpret_cast<float4*>(smem + p.smem_win)[i] = __ldg(reinterpret_cast<const float4*>(p.window) + i % 10);
+    const float4* s_wth = reinterpret_cast<const float4*>(smem + p.smem_win) + l30;
     constexpr float WC[20] = {-0.5f, -0.47552825814757677f, -0.40450849718747373f, -0.29389262614623657f, -0.15450849718747373f,
                               0.f, 0.15450849718747367f, 0.29389262614623651f, 0.40450849718747367f, 0.47552825814757677f,
                               0.5f, 0.47552825814757688f, 0.40450849718747378f, 0.29389262614623662f, 0.15450849718747378f,
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                               0.5f, 0.47552825814757682f, 0.40450849718747373f, 0.29389262614623662f, 0.15450849718747375f,
                               0.f, -0.15450849718747345f, -0.29389262614623651f, -0.40450849718747367f, -0.47552825814757677f,
                               -0.5f, -0.47552825814757682f, -0.40450849718747378f, -0.29389262614623668f, -0.15450849718747381f};
-    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
+    const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + l30;
     // with 8 warps per SM there are registers to spare: keep the worker's 10 twiddle quads resident (saves 10 LDS.128/pass)
     constexpr bool TW_IN_REGS = (NWARPS <= 8);
     float4 twreg[10];
@@ -369,8 +374,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
         for (int i = 0; i < 10; ++i) twreg[i] = __ldg(p.twiddle + 10 * i + t);
     }
-    for (int i = threadIdx.x; i < 10; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i];
-    const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + t;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
+    for (int i = threadIdx.x; i < 30; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i % 10];
+    const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + l30;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
     __syncthreads();
 
     const int hop = HOP160 ? 160 : p.hop;
@@ -432,9 +437,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         f2 PR[20], PI[20];
         if (nvalid > 0) {
             const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
-            f2 w_cos = w_cos0, w_sin = w_sin0;
-            // opaque copy: keeps the 20 window pairs from being hoisted out of the tile loop into 40 live registers
-            asm volatile("" : "+f"(w_cos.x), "+f"(w_cos.y), "+f"(w_sin.x), "+f"(w_sin.y));
+            const float4 wth = *s_wth;
+            const f2 w_cos = make_float2(wth.x, wth.y), w_sin = make_float2(wth.z, wth.w);
             if (HOP160) {
                 // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
                 // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16).  Conflict-free: a half-warp's 16 float2
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const float4* z2 = s_z + ZROW * (10 + t) + 10 * g;   // (t + 2g mod 8 all different) never share a bank group
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
-                const float4 v = z1[i], u = z2[i], w = TW_IN_REGS ? twreg[i] : s_tw[10 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
+                const float4 v = z1[i], u = z2[i], w = TW_IN_REGS ? twreg[i] : s_tw[30 * i];   // v,u = (re n, re m, im n, im m); w = (wr n, wi n, wr m, wi m)
                 const int n = 2 * i, m = 2 * i + 1;
                 XR[n] = make_float2(v.x * w.x - v.z * w.y, fmaf(u.x, w.x, u.z * w.y));         // x * tw ,  y * conj(tw)
                 XI[n] = make_float2(fmaf(v.x, w.y, v.z * w.x), u.z * w.x - u.x * w.y);
