@@ -171,6 +171,40 @@ int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n
 int32_t melspec_stream_reset(melspec_stream* s);
 void melspec_stream_destroy(melspec_stream* s);
 
+/*
+ * ---- output formats: the step after the path (reference src/mel.rs:480-544, src/quant.rs:38-165) ----
+ *
+ * interleave_frames(frames, major_column_order = false, min_width): row-major (n_mels, W) f32 image of the Whisper mel
+ * frames, W = melspec_interleaved_width(F, min_width): an all-zero frame is appended when min_width > 0 and F is odd,
+ * then zero columns up to min_width (src/mel.rs:497-516).  The fused kernel writes this layout directly
+ * (d_out[clip][mel][W], clip r at d_out + r*out_clip_stride, 0 = dense); no separate transpose pass exists.
+ * Errors like the reference's asserts: odd min_width, no frame at all (MELSPEC_ERR_INVALID_ARG).
+ */
+int64_t melspec_interleaved_width(int64_t n_frames, int64_t min_width);   /* -1: invalid arguments */
+int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride,
+                                           int64_t n_samples, int64_t min_width, float* d_out, int64_t out_clip_stride,
+                                           void* stream);
+
+/*
+ * tga_8bit_data / quantize (src/quant.rs:38-64,140-152) and parse_tga_8bit / dequantize (src/quant.rs:66-88,155-165) on the
+ * device: 18-byte TGA header (type 3, 8 bpp, width/height little-endian u16) + 8-byte ID field holding f32 min and max of
+ * the image + n_mels*width bytes ((v - min) * (255 / (max - min))).round().clamp(0, 255).  Bytes are bit-exact with the
+ * reference for identical f32 input.  One image per clip: image r at d_img + r*img_stride floats (0 = dense), TGA r at
+ * d_tga + r*tga_stride bytes (0 = melspec_tga_size).  width >= 65535 is rejected like save_tga_8bit's assert.
+ */
+int64_t melspec_tga_size(int32_t n_mels, int64_t width);                 /* 26 + n_mels*width, -1 if it cannot be a TGA */
+int32_t melspec_quantize_tga_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
+                                    int64_t width, uint8_t* d_tga, int64_t tga_stride, void* stream);
+int32_t melspec_dequantize_tga_device(melspec_handle* h, const uint8_t* d_tga, int64_t n_imgs, int64_t tga_stride,
+                                      int32_t n_mels, int64_t width, float* d_img, int64_t img_stride, void* stream);
+/* host-buffer conveniences (blocking) */
+int32_t melspec_quantize_tga_host(melspec_handle* h, const float* h_img, int32_t n_mels, int64_t width, uint8_t* h_tga);
+int32_t melspec_dequantize_tga_host(melspec_handle* h, const uint8_t* h_tga, int64_t tga_bytes, float* h_img, int64_t capacity);
+/* PCM -> Whisper mel -> interleave -> TGA bytes in one call (examples/mel_tga/src/main.rs:23-76 as one device pipeline);
+ * h_img_opt (optional, n_mels*W floats) also returns the interleaved f32 image. */
+int32_t melspec_mel_tga_host(melspec_handle* h, const float* h_pcm, int64_t n_samples, int64_t min_width, uint8_t* h_tga,
+                             int64_t capacity, int64_t* width_out, float* h_img_opt);
+
 /* Number of kernel launches issued through this handle so far (bench.py's `gpu_launches`). */
 int64_t melspec_launch_count(const melspec_handle* h);
 

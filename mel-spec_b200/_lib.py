@@ -24,6 +24,8 @@ EXPORTS = [
     "melspec_max_frames_per_batch", "melspec_n_mels", "melspec_fft_size", "melspec_hop_size", "melspec_filterbank",
     "melspec_compute_device", "melspec_compute_host", "melspec_stream_create", "melspec_stream_push",
     "melspec_stream_reset", "melspec_stream_destroy", "melspec_launch_count",
+    "melspec_interleaved_width", "melspec_compute_interleaved_device", "melspec_tga_size", "melspec_quantize_tga_device",
+    "melspec_dequantize_tga_device", "melspec_quantize_tga_host", "melspec_dequantize_tga_host", "melspec_mel_tga_host",
 ]
 
 
@@ -106,6 +108,22 @@ def lib() -> C.CDLL:
     L.melspec_stream_destroy.argtypes = [vp]
     L.melspec_launch_count.restype = i64
     L.melspec_launch_count.argtypes = [vp]
+    L.melspec_interleaved_width.restype = i64
+    L.melspec_interleaved_width.argtypes = [i64, i64]
+    L.melspec_compute_interleaved_device.restype = i32
+    L.melspec_compute_interleaved_device.argtypes = [vp, vp, i64, i64, i64, i64, vp, i64, vp]
+    L.melspec_tga_size.restype = i64
+    L.melspec_tga_size.argtypes = [i32, i64]
+    L.melspec_quantize_tga_device.restype = i32
+    L.melspec_quantize_tga_device.argtypes = [vp, vp, i64, i64, i32, i64, vp, i64, vp]
+    L.melspec_dequantize_tga_device.restype = i32
+    L.melspec_dequantize_tga_device.argtypes = [vp, vp, i64, i64, i32, i64, vp, i64, vp]
+    L.melspec_quantize_tga_host.restype = i32
+    L.melspec_quantize_tga_host.argtypes = [vp, vp, i32, i64, vp]
+    L.melspec_dequantize_tga_host.restype = i32
+    L.melspec_dequantize_tga_host.argtypes = [vp, vp, i64, vp, i64]
+    L.melspec_mel_tga_host.restype = i32
+    L.melspec_mel_tga_host.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp]
     _LIB = L
     return L
 

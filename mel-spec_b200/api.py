@@ -9,6 +9,8 @@ Same names, argument meaning and error behaviour as the Rust prelude (reference 
     FbankConfig / Fbank            src/fbank.rs:25-82, 84-250
     mel()                          src/mel.rs:547-589  (filterbank; host-only, no GPU needed)
     RingBuffer                     src/rb.rs:12-122    add_frame / add / maybe_mel, frames come from the streaming C ABI
+    interleave_frames              src/mel.rs:480-544  (row-major (n_mels, W) image; produced by the kernel's mel-major store)
+    quantize / dequantize / tga_8bit_data / parse_tga_8bit / QuantizationRange      src/quant.rs:5-165
 
 Arrays are numpy instead of Vec<Vec<f32>> / ndarray; shapes and element order are the reference's.
 Everything numeric happens in `lib/libmelspec_b200.so`; nothing here computes features on the CPU.
@@ -49,6 +51,13 @@ def _check(rc: int, constructing: bool = False):
     if rc == ERR_INVALID_ARG:
         raise ValueError(msg)
     raise CudaError("Runtime", msg, rc)
+
+
+@dataclass
+class QuantizationRange:
+    """reference src/quant.rs:5-9."""
+    min: float
+    max: float
 
 
 @dataclass(frozen=True)
@@ -227,6 +236,63 @@ class _Handle:
         out = out.reshape(shape)
         return out[0] if single else out
 
+    # ---- output formats (reference src/mel.rs:480-544, src/quant.rs:38-165) ---------------------------------
+    def compute_interleaved_device(self, d_pcm, n_clips: int, clip_stride: int, n_samples: int, min_width: int, d_out, *,
+                                   out_clip_stride: int = 0, stream=None) -> None:
+        """`melspec_compute_interleaved_device`: d_out[clip][mel][W], W = interleaved_width(F, min_width)."""
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _check(self._L.melspec_compute_interleaved_device(self._h, _ptr(d_pcm), int(n_clips), int(clip_stride), int(n_samples),
+                                                          int(min_width), _ptr(d_out), int(out_clip_stride), s))
+
+    def quantize_tga_device(self, d_img, n_imgs: int, n_mels: int, width: int, d_tga, *, img_stride: int = 0,
+                            tga_stride: int = 0, stream=None) -> None:
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _check(self._L.melspec_quantize_tga_device(self._h, _ptr(d_img), int(n_imgs), int(img_stride), int(n_mels), int(width),
+                                                   _ptr(d_tga), int(tga_stride), s))
+
+    def dequantize_tga_device(self, d_tga, n_imgs: int, n_mels: int, width: int, d_img, *, img_stride: int = 0,
+                              tga_stride: int = 0, stream=None) -> None:
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _check(self._L.melspec_dequantize_tga_device(self._h, _ptr(d_tga), int(n_imgs), int(tga_stride), int(n_mels), int(width),
+                                                     _ptr(d_img), int(img_stride), s))
+
+    def tga_8bit_data(self, data, n_mels: int) -> bytes:
+        """src/quant.rs:38-64 on the device: row-major (n_mels, width) f32 image -> TGA bytes."""
+        x = np.ascontiguousarray(np.asarray(data, dtype=np.float32).reshape(-1))
+        if n_mels <= 0 or x.size == 0 or x.size % n_mels:
+            raise ValueError("data length must be a positive multiple of n_mels")
+        width = x.size // n_mels
+        size = int(self._L.melspec_tga_size(int(n_mels), int(width)))
+        if size < 0:
+            raise ValueError("width greater than TARGA max, use [`tga_8bit`]")      # src/quant.rs:18-21
+        out = np.empty(size, dtype=np.uint8)
+        _check(self._L.melspec_quantize_tga_host(self._h, x.ctypes.data, int(n_mels), int(width), out.ctypes.data))
+        return out.tobytes()
+
+    def quantize(self, frame):
+        """src/quant.rs:140-152: (u8 bytes, QuantizationRange)."""
+        x = np.asarray(frame, dtype=np.float32).reshape(-1)
+        tga = np.frombuffer(self.tga_8bit_data(x, 1) if x.size < 65535 else self._quantize_rows(x), dtype=np.uint8)
+        rng = QuantizationRange(*np.frombuffer(tga[18:26].tobytes(), dtype="<f4").tolist())
+        return tga[26:].copy(), rng
+
+    def _quantize_rows(self, x: np.ndarray) -> bytes:
+        # a flat vector longer than a TGA row: use the widest factorisation that fits the u16 fields
+        n = x.size
+        h = next((k for k in range(2, 65536) if n % k == 0 and n // k < 65535), None)
+        if h is None:
+            raise ValueError("vector cannot be laid out as a TGA image")
+        return self.tga_8bit_data(x, h)
+
+    def parse_tga_8bit(self, data: bytes) -> np.ndarray:
+        """src/quant.rs:66-88 on the device: TGA bytes -> dequantised f32 vector (row-major image)."""
+        b = np.frombuffer(bytes(data), dtype=np.uint8)
+        if b.size < 26:
+            raise IOError("failed to fill whole buffer")
+        out = np.empty(b.size - 26, dtype=np.float32)
+        _check(self._L.melspec_dequantize_tga_host(self._h, b.ctypes.data, int(b.size), out.ctypes.data, int(out.size)))
+        return out
+
     def compute_host_raw(self, h_pcm_ptr: int, n_clips: int, clip_stride: int, n_samples: int, h_out_ptr: int,
                          layout: int = LAYOUT_FRAME_MAJOR) -> int:
         """Pointer form of `melspec_compute_host` (pinned torch host tensors in bench.py)."""
@@ -251,6 +317,45 @@ class CudaMelSpectrogram(_Handle):
     def compute_mel_spectrogram(self, samples) -> np.ndarray:
         """&[f32] -> [frame][mel] f32 (src/cuda.rs:88-101).  Empty / too-short input => shape (0, n_mels)."""
         return self.compute_host(np.asarray(samples, dtype=np.float32).reshape(-1))
+
+    def interleaved_width(self, n_samples: int, min_width: int = 0) -> int:
+        return int(self._L.melspec_interleaved_width(self.num_frames(n_samples), int(min_width)))
+
+    def mel_tga(self, samples, min_width: int = 0, return_image: bool = False):
+        """PCM -> mel frames -> interleave_frames(.., false, min_width) -> tga_8bit_data, one device pipeline
+        (the reference's examples/mel_tga: src/stft.rs + src/mel.rs:480-544 + src/quant.rs:38-64)."""
+        x = np.ascontiguousarray(np.asarray(samples, dtype=np.float32).reshape(-1))
+        if min_width % 2:
+            raise ValueError("min_width must be even")                               # src/mel.rs:488
+        f = self.num_frames(x.size)
+        if f <= 0:
+            raise ValueError("frames is empty")                                      # src/mel.rs:487
+        w = int(self._L.melspec_interleaved_width(f, int(min_width)))
+        size = int(self._L.melspec_tga_size(self.n_mels, w))
+        if size < 0:
+            raise ValueError("width greater than TARGA max, use [`tga_8bit`]")
+        out = np.empty(size, dtype=np.uint8)
+        img = np.empty((self.n_mels, w), dtype=np.float32) if return_image else None
+        wout = C.c_int64(0)
+        _check(self._L.melspec_mel_tga_host(self._h, x.ctypes.data, int(x.size), int(min_width), out.ctypes.data, size,
+                                            C.byref(wout), img.ctypes.data if img is not None else 0))
+        return (out.tobytes(), img) if return_image else out.tobytes()
+
+    def interleave_frames(self, samples, major_column_order: bool = False, min_width: int = 0) -> np.ndarray:
+        """Mel frames of `samples` in the reference's interleave_frames layout (src/mel.rs:480-544), flat f32.
+        Row-major (default, what whisper.cpp expects) comes straight from the kernel's mel-major store."""
+        if major_column_order:
+            # frames one after the other, then the zero frame / padding block (src/mel.rs:520-530): frame-major + zeros
+            x = np.asarray(samples, dtype=np.float32).reshape(-1)
+            fm = self.compute_host(x)
+            if fm.shape[0] == 0:
+                raise ValueError("frames is empty")
+            if min_width % 2:
+                raise ValueError("min_width must be even")
+            w = int(self._L.melspec_interleaved_width(fm.shape[0], int(min_width)))
+            return np.concatenate([fm.reshape(-1), np.zeros((w - fm.shape[0]) * self.n_mels, np.float32)])
+        _, img = self.mel_tga(samples, min_width, return_image=True)
+        return img.reshape(-1)
 
 
 class Spectrogram:

@@ -190,6 +190,11 @@ struct melspec_handle {
     float* d_slot_pcm[3] = {nullptr, nullptr, nullptr};
     float* d_slot_out[3] = {nullptr, nullptr, nullptr};
     size_t slot_pcm_cap = 0, slot_out_cap = 0;
+    float2* d_partials = nullptr;   // min/max partials of the TGA quantiser
+    size_t partials_cap = 0;
+    float* d_fmt_img = nullptr;     // staging of the host-buffer format entry points
+    unsigned char* d_fmt_tga = nullptr;
+    size_t fmt_img_cap = 0, fmt_tga_cap = 0;
     int64_t launches = 0;
 };
 
@@ -543,7 +548,7 @@ int32_t launch_kernel(Kern kern, const melspec::KParams& p, int grid, int thread
 // Core launch: device pointers, explicit frame count (frames_per_clip may be smaller than num_frames(n_samples)).
 int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
                       int64_t frames_per_clip, const int32_t* d_lens, float* d_out, int64_t out_clip_stride, int32_t layout,
-                      cudaStream_t st) {
+                      cudaStream_t st, int64_t row_stride_override = 0) {
     using namespace melspec;
     const Resolved& c = h->cfg;
     if (n_clips == 0 || frames_per_clip == 0) return MELSPEC_OK;
@@ -554,7 +559,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (nemo && layout != MELSPEC_LAYOUT_MEL_MAJOR)
         return fail(MELSPEC_ERR_UNSUPPORTED, "the NeMo frontend produces (n_mels, frames) feature-major output only");
     if (nemo && d_lens) return fail(MELSPEC_ERR_UNSUPPORTED, "per-clip lengths are not supported by the NeMo frontend yet");
-    const int64_t row_stride = nemo ? padded_frames_for(c, n_samples) : frames_per_clip;
+    const int64_t row_stride = row_stride_override > 0 ? row_stride_override : nemo ? padded_frames_for(c, n_samples) : frames_per_clip;
     const int fpw = h->plan == 400 ? p400::FPW : p512::FPW;
     KParams p{};
     p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
@@ -793,6 +798,9 @@ void melspec_destroy(melspec_handle* h) {
     cudaFree(h->d_rot10);
     cudaFree(h->d_proj);
     cudaFree(h->d_meta);
+    cudaFree(h->d_partials);
+    cudaFree(h->d_fmt_img);
+    cudaFree(h->d_fmt_tga);
     for (int i = 0; i < 3; ++i) {
         if (h->d_slot_pcm[i]) cudaFree(h->d_slot_pcm[i]);
         if (h->d_slot_out[i]) cudaFree(h->d_slot_out[i]);
@@ -815,6 +823,187 @@ int32_t melspec_max_frames_per_batch(const melspec_handle* h) {
 int32_t melspec_n_mels(const melspec_handle* h) { return h ? h->cfg.n_mels : 0; }
 int32_t melspec_fft_size(const melspec_handle* h) { return h ? h->cfg.fft : 0; }
 int32_t melspec_hop_size(const melspec_handle* h) { return h ? h->cfg.hop : 0; }
+
+// ---- output formats: interleave_frames (src/mel.rs:480-544) and 8-bit TGA (src/quant.rs:38-165) -------------
+int64_t melspec_interleaved_width(int64_t n_frames, int64_t min_width) {
+    if (n_frames <= 0 || min_width < 0 || (min_width & 1)) return -1;   // asserts of src/mel.rs:487-488
+    const int64_t even = n_frames + ((min_width > 0 && (n_frames & 1)) ? 1 : 0);   // src/mel.rs:497-500
+    return std::max(even, min_width);                                               // src/mel.rs:506-516
+}
+
+int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride,
+                                           int64_t n_samples, int64_t min_width, float* d_out, int64_t out_clip_stride, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (h->cfg.frontend != MELSPEC_FRONTEND_WHISPER)
+        return fail(MELSPEC_ERR_UNSUPPORTED, "interleave_frames is defined on Whisper mel frames (src/mel.rs:480-544)");
+    if (n_clips < 0 || n_samples < 0 || clip_stride < 0 || out_clip_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (min_width < 0 || (min_width & 1)) return fail(MELSPEC_ERR_INVALID_ARG, "min_width must be even");           // src/mel.rs:488
+    const int64_t F = frames_for(h->cfg, n_samples);
+    if (F == 0) return fail(MELSPEC_ERR_INVALID_ARG, "frames is empty");                                            // src/mel.rs:487
+    if (n_clips == 0) return MELSPEC_OK;
+    if (!d_pcm || !d_out) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    if (n_clips > 1 && clip_stride < n_samples) return fail(MELSPEC_ERR_INVALID_ARG, "clip_stride < n_samples");
+    const int64_t W = melspec_interleaved_width(F, min_width);
+    const int64_t ocs = out_clip_stride ? out_clip_stride : W * h->cfg.n_mels;
+    if (ocs < W * h->cfg.n_mels) return fail(MELSPEC_ERR_INVALID_ARG, "out_clip_stride < n_mels * width");
+    MS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (W > F) {   // the zero frame / zero padding block of src/mel.rs:497-516
+        if (ocs == W * h->cfg.n_mels)
+            MS_CUDA(cudaMemset2DAsync(d_out + F, (size_t)W * 4, 0, (size_t)(W - F) * 4, (size_t)n_clips * h->cfg.n_mels, st));
+        else
+            for (int64_t c = 0; c < n_clips; ++c)
+                MS_CUDA(cudaMemset2DAsync(d_out + c * ocs + F, (size_t)W * 4, 0, (size_t)(W - F) * 4, (size_t)h->cfg.n_mels, st));
+    }
+    return launch_device(h, d_pcm, n_clips, clip_stride, n_samples, F, nullptr, d_out, ocs, MELSPEC_LAYOUT_MEL_MAJOR, st, W);
+}
+
+int64_t melspec_tga_size(int32_t n_mels, int64_t width) {
+    if (n_mels <= 0 || width <= 0 || n_mels > 65535 || width >= 65535) return -1;   // u16 fields; src/quant.rs:17-21
+    return (int64_t)melspec::kTgaHeader + (int64_t)n_mels * width;
+}
+
+int32_t melspec_quantize_tga_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
+                                    int64_t width, uint8_t* d_tga, int64_t tga_stride, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    const int64_t sz = melspec_tga_size(n_mels, width);
+    if (sz < 0) return fail(MELSPEC_ERR_INVALID_ARG, "width greater than TARGA max (or empty image)");   // src/quant.rs:18-21
+    if (n_imgs < 0 || img_stride < 0 || tga_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (n_imgs == 0) return MELSPEC_OK;
+    if (!d_img || !d_tga) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    const int64_t n = (int64_t)n_mels * width;
+    if (!img_stride) img_stride = n;
+    if (!tga_stride) tga_stride = sz;
+    if (n_imgs > 1 && (img_stride < n || tga_stride < sz)) return fail(MELSPEC_ERR_INVALID_ARG, "stride smaller than the image");
+    if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
+    MS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (int)std::min<int64_t>(256, (n + 4095) / 4096);
+    const size_t need = sizeof(float2) * (size_t)nblk * (size_t)n_imgs;
+    if (need > h->partials_cap) {
+        if (h->d_partials) { MS_CUDA(cudaStreamSynchronize(st)); cudaFree(h->d_partials); h->d_partials = nullptr; }
+        MS_CUDA(cudaMalloc(&h->d_partials, need));
+        h->partials_cap = need;
+    }
+    melspec::melspec_minmax_kernel<<<dim3(nblk, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, h->d_partials);
+    MS_CUDA(cudaGetLastError());
+    const int nblk2 = (int)std::min<int64_t>(1024, (n / 4 + 1023) / 1024 + 1);
+    melspec::melspec_quantize_kernel<<<dim3(nblk2, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, h->d_partials, nblk, d_tga,
+                                                                                  tga_stride, n_mels, (int)width);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return MELSPEC_OK;
+}
+
+int32_t melspec_dequantize_tga_device(melspec_handle* h, const uint8_t* d_tga, int64_t n_imgs, int64_t tga_stride, int32_t n_mels,
+                                      int64_t width, float* d_img, int64_t img_stride, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    const int64_t sz = melspec_tga_size(n_mels, width);
+    if (sz < 0) return fail(MELSPEC_ERR_INVALID_ARG, "width greater than TARGA max (or empty image)");
+    if (n_imgs < 0 || img_stride < 0 || tga_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (n_imgs == 0) return MELSPEC_OK;
+    if (!d_img || !d_tga) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    const int64_t n = (int64_t)n_mels * width;
+    if (!img_stride) img_stride = n;
+    if (!tga_stride) tga_stride = sz;
+    if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
+    MS_CUDA(cudaSetDevice(h->device));
+    const int nblk = (int)std::min<int64_t>(1024, (n + 1023) / 1024);
+    melspec::melspec_dequantize_kernel<<<dim3(nblk, (unsigned)n_imgs), 256, 0, (cudaStream_t)stream>>>(d_tga, tga_stride, n, d_img, img_stride);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MELSPEC_OK;
+}
+
+namespace {
+int32_t ensure_fmt(melspec_handle* h, size_t img_bytes, size_t tga_bytes) {
+    if (img_bytes > h->fmt_img_cap) {
+        if (h->d_fmt_img) cudaFree(h->d_fmt_img);
+        h->d_fmt_img = nullptr; h->fmt_img_cap = 0;
+        MS_CUDA(cudaMalloc(&h->d_fmt_img, img_bytes));
+        h->fmt_img_cap = img_bytes;
+    }
+    if (tga_bytes > h->fmt_tga_cap) {
+        if (h->d_fmt_tga) cudaFree(h->d_fmt_tga);
+        h->d_fmt_tga = nullptr; h->fmt_tga_cap = 0;
+        MS_CUDA(cudaMalloc(&h->d_fmt_tga, tga_bytes));
+        h->fmt_tga_cap = tga_bytes;
+    }
+    return MELSPEC_OK;
+}
+}  // namespace
+
+// Host-buffer conveniences (blocking).  h_img is row-major (n_mels, width) as produced by interleave_frames(.., false, w).
+int32_t melspec_quantize_tga_host(melspec_handle* h, const float* h_img, int32_t n_mels, int64_t width, uint8_t* h_tga) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    const int64_t sz = melspec_tga_size(n_mels, width);
+    if (sz < 0) return fail(MELSPEC_ERR_INVALID_ARG, "width greater than TARGA max (or empty image)");
+    if (!h_img || !h_tga) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    MS_CUDA(cudaSetDevice(h->device));
+    const size_t ib = (size_t)n_mels * (size_t)width * 4;
+    int32_t rc = ensure_fmt(h, ib, (size_t)sz + 8);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpy(h->d_fmt_img, h_img, ib, cudaMemcpyHostToDevice));
+    rc = melspec_quantize_tga_device(h, h->d_fmt_img, 1, 0, n_mels, width, h->d_fmt_tga, 0, nullptr);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpy(h_tga, h->d_fmt_tga, (size_t)sz, cudaMemcpyDeviceToHost));
+    return MELSPEC_OK;
+}
+
+// parse_tga_8bit (src/quant.rs:66-88): width and height come from the caller (the reference ignores the header's, too).
+int32_t melspec_dequantize_tga_host(melspec_handle* h, const uint8_t* h_tga, int64_t tga_bytes, float* h_img, int64_t capacity) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (!h_tga || !h_img) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    if (tga_bytes < melspec::kTgaHeader) return fail(MELSPEC_ERR_INVALID_ARG, "failed to fill whole buffer");   // read_exact error of the reference
+    const int64_t n = tga_bytes - melspec::kTgaHeader;
+    if (capacity < n) return fail(MELSPEC_ERR_INVALID_ARG, "capacity too small");
+    if (n == 0) return MELSPEC_OK;
+    MS_CUDA(cudaSetDevice(h->device));
+    int32_t rc = ensure_fmt(h, (size_t)n * 4, (size_t)tga_bytes + 8);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpy(h->d_fmt_tga, h_tga, (size_t)tga_bytes, cudaMemcpyHostToDevice));
+    const int nblk = (int)std::min<int64_t>(1024, (n + 1023) / 1024);
+    melspec::melspec_dequantize_kernel<<<dim3(nblk, 1), 256>>>(h->d_fmt_tga, tga_bytes, n, h->d_fmt_img, n);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    MS_CUDA(cudaMemcpy(h_img, h->d_fmt_img, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return MELSPEC_OK;
+}
+
+// PCM -> mel -> interleave -> 8-bit TGA in one call, everything between the two copies on the device
+// (the reference's examples/mel_tga pipeline: src/stft.rs + src/mel.rs:480-544 + src/quant.rs:38-64).
+int32_t melspec_mel_tga_host(melspec_handle* h, const float* h_pcm, int64_t n_samples, int64_t min_width, uint8_t* h_tga,
+                             int64_t capacity, int64_t* width_out, float* h_img_opt) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (h->cfg.frontend != MELSPEC_FRONTEND_WHISPER) return fail(MELSPEC_ERR_UNSUPPORTED, "Whisper frontend only");
+    if (n_samples < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (min_width < 0 || (min_width & 1)) return fail(MELSPEC_ERR_INVALID_ARG, "min_width must be even");
+    const int64_t F = frames_for(h->cfg, n_samples);
+    if (F == 0) return fail(MELSPEC_ERR_INVALID_ARG, "frames is empty");
+    const int64_t W = melspec_interleaved_width(F, min_width);
+    if (width_out) *width_out = W;
+    const int64_t sz = melspec_tga_size(h->cfg.n_mels, W);
+    if (sz < 0) return fail(MELSPEC_ERR_INVALID_ARG, "width greater than TARGA max, use chunks (src/quant.rs:17-21)");
+    if (!h_pcm || !h_tga) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    if (capacity < sz) return fail(MELSPEC_ERR_INVALID_ARG, "capacity too small");
+    MS_CUDA(cudaSetDevice(h->device));
+    const int64_t ns4 = (n_samples + 3) / 4 * 4;
+    int32_t rc = ensure_host_resources(h, (size_t)ns4 * 4, 16);
+    if (rc) return rc;
+    rc = ensure_fmt(h, (size_t)h->cfg.n_mels * (size_t)W * 4, (size_t)sz + 8);
+    if (rc) return rc;
+    cudaStream_t st = h->streams[0];
+    MS_CUDA(cudaMemcpyAsync(h->d_slot_pcm[0], h_pcm, (size_t)n_samples * 4, cudaMemcpyHostToDevice, st));
+    rc = melspec_compute_interleaved_device(h, h->d_slot_pcm[0], 1, ns4, n_samples, min_width, h->d_fmt_img, 0, st);
+    if (rc) return rc;
+    rc = melspec_quantize_tga_device(h, h->d_fmt_img, 1, 0, h->cfg.n_mels, W, h->d_fmt_tga, 0, st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(h_tga, h->d_fmt_tga, (size_t)sz, cudaMemcpyDeviceToHost, st));
+    if (h_img_opt) MS_CUDA(cudaMemcpyAsync(h_img_opt, h->d_fmt_img, (size_t)h->cfg.n_mels * (size_t)W * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MELSPEC_OK;
+}
+
 int64_t melspec_launch_count(const melspec_handle* h) { return h ? h->launches : 0; }
 
 int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacity) {

@@ -1126,4 +1126,104 @@ __global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long 
     for (int f = lane; f < frames; f += 32) r[f] = (r[f] - mean) * inv;
 }
 
+// ================================================================================================ output formats
+// 8-bit quantisation <-> TGA of a row-major (n_mels, width) image (reference src/quant.rs:38-88,140-165): the step after
+// the path for TGA interchange / whisper.cpp.  Byte and f32 arithmetic identical to the reference (no fused multiply-add:
+// every product and sum is rounded on its own), so the bytes are bit-exact for identical f32 input.
+constexpr int kTgaHeader = 26;   // 18-byte TGA header + 8-byte ID field carrying f32 min, max (src/quant.rs:44-57)
+
+// Pass 1: per-block (min, max) partials.  grid = (nblk, n_imgs).  f32::min / f32::max ignore NaN like fminf / fmaxf.
+__global__ void __launch_bounds__(256) melspec_minmax_kernel(const float* img, long long img_stride, long long n, float2* partials) {
+    const float* src = img + (long long)blockIdx.y * img_stride;
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = __ldg(src + i);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ float2 red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(mn, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, red[w].x); mx = fmaxf(mx, red[w].y); }
+        partials[(long long)blockIdx.y * gridDim.x + blockIdx.x] = make_float2(mn, mx);
+    }
+}
+
+__device__ __forceinline__ unsigned quantize_px(float v, float mn, float scale) {
+    // ((value - min) * scale).round().max(0.0).min(255.0) as u8     (src/quant.rs:146-149; round = half away from zero)
+    const float q = fminf(fmaxf(roundf(__fmul_rn(__fsub_rn(v, mn), scale)), 0.0f), 255.0f);
+    return (unsigned)q;   // NaN was turned into 0 by fmaxf, as f32::max does
+}
+
+// Pass 2: header + pixels.  grid = (nblk2, n_imgs); every block re-reduces the image's partials (<= 256 float2 from L2).
+__global__ void __launch_bounds__(256) melspec_quantize_kernel(const float* img, long long img_stride, long long n, const float2* partials,
+                                                               int nblk, unsigned char* tga, long long tga_stride, int height, int width) {
+    __shared__ float2 red[8];
+    __shared__ float s_mn, s_scale;
+    const float* src = img + (long long)blockIdx.y * img_stride;
+    unsigned char* dst = tga + (long long)blockIdx.y * tga_stride;
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    for (int i = threadIdx.x; i < nblk; i += 256) {
+        const float2 v = partials[(long long)blockIdx.y * nblk + i];
+        mn = fminf(mn, v.x); mx = fmaxf(mx, v.y);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(mn, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, red[w].x); mx = fmaxf(mx, red[w].y); }
+        s_mn = mn;
+        s_scale = __fdiv_rn(255.0f, __fsub_rn(mx, mn));   // src/quant.rs:144
+        if (blockIdx.x == 0) {   // src/quant.rs:44-57
+            const unsigned char hdr[18] = {8, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, (unsigned char)(width & 255), (unsigned char)(width >> 8),
+                                           (unsigned char)(height & 255), (unsigned char)(height >> 8), 8, 0};
+            for (int i = 0; i < 18; ++i) dst[i] = hdr[i];
+            const unsigned a = __float_as_uint(mn), b = __float_as_uint(mx);
+            for (int i = 0; i < 4; ++i) { dst[18 + i] = (unsigned char)(a >> (8 * i)); dst[22 + i] = (unsigned char)(b >> (8 * i)); }
+        }
+    }
+    __syncthreads();
+    mn = s_mn;
+    const float scale = s_scale;
+    unsigned char* px = dst + kTgaHeader;
+    // 32-bit stores on the aligned interior, single bytes on the (<= 3 byte) edges
+    const long long head = min((long long)((4 - (reinterpret_cast<uintptr_t>(px) & 3)) & 3), n);
+    const long long nwords = (n - head) / 4;
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const int i = threadIdx.x;
+        if (i < head) px[i] = (unsigned char)quantize_px(__ldg(src + i), mn, scale);
+        const long long tail0 = head + 4 * nwords;
+        if (i >= 4 && tail0 + (i - 4) < n) px[tail0 + (i - 4)] = (unsigned char)quantize_px(__ldg(src + tail0 + (i - 4)), mn, scale);
+    }
+    unsigned* wdst = reinterpret_cast<unsigned*>(px + head);
+    const float* wsrc = src + head;
+    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < nwords; k += (long long)gridDim.x * 256) {
+        const unsigned b0 = quantize_px(__ldg(wsrc + 4 * k), mn, scale), b1 = quantize_px(__ldg(wsrc + 4 * k + 1), mn, scale);
+        const unsigned b2 = quantize_px(__ldg(wsrc + 4 * k + 2), mn, scale), b3 = quantize_px(__ldg(wsrc + 4 * k + 3), mn, scale);
+        wdst[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+}
+
+// parse_tga_8bit + dequantize (src/quant.rs:66-88,155-165): value as f32 * ((max - min) / 255.0) + min, two roundings.
+__global__ void __launch_bounds__(256) melspec_dequantize_kernel(const unsigned char* tga, long long tga_stride, long long n, float* img,
+                                                                 long long img_stride) {
+    const unsigned char* src = tga + (long long)blockIdx.y * tga_stride;
+    float* dst = img + (long long)blockIdx.y * img_stride;
+    unsigned a = 0, b = 0;
+    for (int i = 0; i < 4; ++i) { a |= (unsigned)src[18 + i] << (8 * i); b |= (unsigned)src[22 + i] << (8 * i); }
+    const float mn = __uint_as_float(a), mx = __uint_as_float(b);
+    const float scale = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        dst[i] = __fadd_rn(__fmul_rn((float)src[kTgaHeader + i], scale), mn);
+}
+
 }  // namespace melspec

@@ -416,3 +416,73 @@ def batch_log_mel(samples, sample_rate=16000, n_fft=512, win_length=400, hop_len
         std = np.sqrt(var) + dtype(1e-5)
         feats[:, :valid] = ((v - mean) / std).astype(np.float32)
     return feats
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Output formats: interleave_frames (reference src/mel.rs:480-544) and 8-bit TGA (src/quant.rs:38-165)
+# ---------------------------------------------------------------------------------------------------------------
+TGA_HEADER_BYTES = 26   # 18-byte header + 8-byte ID field (f32 min, f32 max), src/quant.rs:44-57
+
+
+def interleave_frames(frames, major_column_order: bool = False, min_width: int = 0) -> np.ndarray:
+    """reference src/mel.rs:480-544.  `frames`: (T, n_mels) array ([frame][mel], one column each).  Returns flat f32:
+    row-major (n_mels, W) by default, W = T (+1 zero frame if min_width > 0 and T is odd), zero-padded to min_width."""
+    fr = np.asarray(frames)
+    assert fr.ndim == 2 and fr.shape[0] > 0, "frames is empty"            # src/mel.rs:487
+    assert min_width % 2 == 0, "min_width must be even"                   # src/mel.rs:488
+    t, m = fr.shape
+    if min_width > 0 and t % 2 != 0:                                      # src/mel.rs:497-500
+        fr = np.concatenate([fr, np.zeros((1, m), fr.dtype)])
+        t += 1
+    pad = max(min_width - t, 0)                                           # src/mel.rs:506
+    if pad > 0:                                                           # src/mel.rs:509-516
+        fr = np.concatenate([fr, np.zeros((pad, m), fr.dtype)])
+    if major_column_order:                                                # src/mel.rs:520-530 (frame after frame; the padding
+        return fr.astype(np.float32).reshape(-1)                          # block's rows come mel by mel, all zero either way)
+    return np.ascontiguousarray(fr.T).astype(np.float32).reshape(-1)      # src/mel.rs:531-541
+
+
+def _round_half_away(v: np.ndarray) -> np.ndarray:
+    """f32::round: half away from zero (numpy's round is half-to-even)."""
+    v = np.asarray(v, dtype=np.float32)
+    a = np.abs(v)
+    r = np.floor(a)
+    r = r + ((a - r) >= np.float32(0.5)).astype(np.float32)
+    return np.copysign(r, v).astype(np.float32)
+
+
+def quantize(frame):
+    """reference src/quant.rs:140-152, f32 arithmetic step by step.  Returns (u8 array, (min, max))."""
+    x = np.asarray(frame, dtype=np.float32).reshape(-1)
+    with np.errstate(all="ignore"):
+        mn = np.float32(np.fmin.reduce(x, initial=np.float32(np.inf)))
+        mx = np.float32(np.fmax.reduce(x, initial=np.float32(-np.inf)))
+        scale = np.float32(255.0) / np.float32(mx - mn)
+        v = _round_half_away((x - mn).astype(np.float32) * scale)
+        v = np.fmin(np.fmax(v, np.float32(0.0)), np.float32(255.0))       # f32::max / f32::min drop NaN
+    return v.astype(np.uint8), (float(mn), float(mx))
+
+
+def dequantize(data, rng) -> np.ndarray:
+    """reference src/quant.rs:155-165."""
+    mn, mx = np.float32(rng[0]), np.float32(rng[1])
+    scale = np.float32(np.float32(mx - mn) / np.float32(255.0))
+    return (np.asarray(data, dtype=np.uint8).astype(np.float32) * scale).astype(np.float32) + mn
+
+
+def tga_8bit_data(data, n_mels: int) -> bytes:
+    """reference src/quant.rs:38-64."""
+    x = np.asarray(data, dtype=np.float32).reshape(-1)
+    q, (mn, mx) = quantize(x)
+    width, height = (x.size // n_mels) & 0xFFFF, n_mels & 0xFFFF
+    hdr = bytes([8, 0, 3]) + bytes(5) + bytes(4) + int(width).to_bytes(2, "little") + int(height).to_bytes(2, "little") + bytes([8, 0])
+    return hdr + np.float32(mn).tobytes() + np.float32(mx).tobytes() + q.tobytes()
+
+
+def parse_tga_8bit(data: bytes) -> np.ndarray:
+    """reference src/quant.rs:66-88."""
+    b = bytes(data)
+    if len(b) < TGA_HEADER_BYTES:
+        raise IOError("failed to fill whole buffer")
+    mn, mx = np.frombuffer(b[18:26], dtype="<f4")
+    return dequantize(np.frombuffer(b[26:], dtype=np.uint8), (mn, mx))

@@ -16,6 +16,9 @@ vectors and the audio clip they were computed from.
   mel_filters_80x201.npy (80,201) f32 — testdata/mel_filters.npz['mel_80']  (src/mel.rs:837-850)
   nemo_filters_80x257.npy(80,257) f32 — testdata/nemo_mel_filters.npz['banks'][0] (src/mel.rs:852-871)
   kaldi_fbank_jfk.npy    (80,1098) f32 — testdata/kaldi_native_fbank_jfk.npz['features'] (src/fbank.rs:439-535)
+  quantized_mel_golden.tga  80 x 1100 8-bit TGA (src/quant.rs format) — testdata/quantized_mel_golden.tga, the fixture of the
+                         reference's VAD tests (src/vad.rs:712,742; tests/vad_regression.rs:157,215).  Columns 2..1099 are the
+                         quantised Whisper fft-400 / hop-160 stream mel of the JFK clip (verified bit-exact against the oracle).
 """
 import os
 import struct
@@ -56,6 +59,8 @@ def main():
     np.save(os.path.join(HERE, "mel_filters_80x201.npy"), np.load(os.path.join(td, "mel_filters.npz"))["mel_80"])
     np.save(os.path.join(HERE, "nemo_filters_80x257.npy"), np.load(os.path.join(td, "nemo_mel_filters.npz"))["banks"][0])
     np.save(os.path.join(HERE, "kaldi_fbank_jfk.npy"), np.load(os.path.join(td, "kaldi_native_fbank_jfk.npz"))["features"])
+    with open(os.path.join(td, "quantized_mel_golden.tga"), "rb") as src, open(os.path.join(HERE, "quantized_mel_golden.tga"), "wb") as dst:
+        dst.write(src.read())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npy"):
             a = np.load(os.path.join(HERE, f))
