@@ -205,6 +205,35 @@ int32_t melspec_dequantize_tga_host(melspec_handle* h, const uint8_t* h_tga, int
 int32_t melspec_mel_tga_host(melspec_handle* h, const float* h_pcm, int64_t n_samples, int64_t min_width, uint8_t* h_tga,
                              int64_t capacity, int64_t* width_out, float* h_img_opt);
 
+/*
+ * ---- VAD over the mel image: the consumer directly downstream (reference src/vad.rs) ----
+ *
+ * DetectionSettings (src/vad.rs:5-22).  melspec_vad_boundaries_device = vad_boundaries (src/vad.rs:251-338) for a batch of
+ * row-major (n_mels, width) f32 images (what melspec_compute_interleaved_device writes, or a dequantised TGA): per column
+ * the count of 3x3 Sobel gradients with gx^2+gy^2 >= min_energy^2 over mel rows [min_mel, n_mels-2) against min_y
+ * (classify_columns_in_frame, src/vad.rs:373-415; sobel_gradient_sq, 472-486; f64 like the reference), then the +-4 majority
+ * vote (smooth_mask, 343-360).  d_smoothed[img][x] = 1 <=> column x is in EdgeInfo::intersected(), x in [0, width-2);
+ * d_raw (optional) receives the unsmoothed decisions.  Images with n_mels < 3 or width < 3 produce nothing (empty EdgeInfo).
+ * melspec_vad_activity_device = VoiceActivityDetector::add_activity (src/vad.rs:163-207) for all frame indices at once from
+ * d_raw: d_activity[img][i] = (active, leading_active_columns, active_columns) over the window of the last min_x frames,
+ * (-1,-1,-1) for i < min_x-1 (the reference returns None); window_columns = max(min_x-2, 0) where defined.
+ */
+typedef struct melspec_vad_settings {
+    double min_energy; /* 0.98 */
+    int32_t min_y;     /* 11   */
+    int32_t min_x;     /* 5    */
+    int32_t min_mel;   /* 2    */
+} melspec_vad_settings;
+int32_t melspec_vad_default_settings(melspec_vad_settings* s);
+int32_t melspec_vad_boundaries_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
+                                      int64_t width, const melspec_vad_settings* vs, uint8_t* d_raw, uint8_t* d_smoothed,
+                                      int64_t mask_stride, void* stream);
+int32_t melspec_vad_activity_device(melspec_handle* h, const uint8_t* d_raw, int64_t n_imgs, int64_t mask_stride, int32_t n_mels,
+                                    int64_t width, const melspec_vad_settings* vs, int32_t* d_activity, int64_t activity_stride,
+                                    void* stream);
+int32_t melspec_vad_host(melspec_handle* h, const float* h_img, int32_t n_mels, int64_t width, const melspec_vad_settings* vs,
+                         uint8_t* h_smoothed, int32_t* h_activity_opt);
+
 /* Number of kernel launches issued through this handle so far (bench.py's `gpu_launches`). */
 int64_t melspec_launch_count(const melspec_handle* h);
 

@@ -6,13 +6,14 @@ binding of include/melspec_b200.h), api.py (host-side mirror of the reference in
 from ._lib import build, lib, last_error, LIB_PATH, EXPORTS  # noqa: F401
 from .api import (  # noqa: F401
     BatchLogMelConfig, BatchLogMelError, BatchLogMelOutput, BatchLogMelSpectrogram,
-    CudaError, CudaMelSpectrogram, Fbank, FbankConfig, MelConfig, QuantizationRange, RingBuffer, Spectrogram,
+    CudaError, CudaMelSpectrogram, DetectionSettings, EdgeInfo, Fbank, FbankConfig, MelConfig, QuantizationRange, RingBuffer,
+    Spectrogram, VadFrameTiming, VoiceActivity, VoiceActivityTimestamps, vad_on,
     kaldi_mel_filterbank, mel,
     FRONTEND_KALDI, FRONTEND_NEMO, FRONTEND_WHISPER, LAYOUT_FRAME_MAJOR, LAYOUT_MEL_MAJOR,
 )
 
 __all__ = [
     "BatchLogMelConfig", "BatchLogMelError", "BatchLogMelOutput", "BatchLogMelSpectrogram",
-    "CudaError", "CudaMelSpectrogram", "Fbank", "FbankConfig", "MelConfig", "QuantizationRange", "RingBuffer", "Spectrogram",
+    "CudaError", "CudaMelSpectrogram", "DetectionSettings", "EdgeInfo", "VadFrameTiming", "VoiceActivity", "vad_on", "Fbank", "FbankConfig", "MelConfig", "QuantizationRange", "RingBuffer", "Spectrogram",
     "kaldi_mel_filterbank", "mel", "build", "lib",
 ]

@@ -26,6 +26,7 @@ EXPORTS = [
     "melspec_stream_reset", "melspec_stream_destroy", "melspec_launch_count",
     "melspec_interleaved_width", "melspec_compute_interleaved_device", "melspec_tga_size", "melspec_quantize_tga_device",
     "melspec_dequantize_tga_device", "melspec_quantize_tga_host", "melspec_dequantize_tga_host", "melspec_mel_tga_host",
+    "melspec_vad_default_settings", "melspec_vad_boundaries_device", "melspec_vad_activity_device", "melspec_vad_host",
 ]
 
 
@@ -40,6 +41,11 @@ class MelspecConfig(C.Structure):
         ("htk", C.c_int32), ("slaney_norm", C.c_int32),
         ("log_zero_guard", C.c_double), ("f_min", C.c_double), ("f_max", C.c_double),
     ]
+
+
+class VadSettings(C.Structure):
+    """struct melspec_vad_settings (include/melspec_b200.h) == DetectionSettings (reference src/vad.rs:5-22)."""
+    _fields_ = [("min_energy", C.c_double), ("min_y", C.c_int32), ("min_x", C.c_int32), ("min_mel", C.c_int32)]
 
 
 def _stale() -> bool:
@@ -124,6 +130,15 @@ def lib() -> C.CDLL:
     L.melspec_dequantize_tga_host.argtypes = [vp, vp, i64, vp, i64]
     L.melspec_mel_tga_host.restype = i32
     L.melspec_mel_tga_host.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp]
+    vsp = C.POINTER(VadSettings)
+    L.melspec_vad_default_settings.restype = i32
+    L.melspec_vad_default_settings.argtypes = [vsp]
+    L.melspec_vad_boundaries_device.restype = i32
+    L.melspec_vad_boundaries_device.argtypes = [vp, vp, i64, i64, i32, i64, vsp, vp, vp, i64, vp]
+    L.melspec_vad_activity_device.restype = i32
+    L.melspec_vad_activity_device.argtypes = [vp, vp, i64, i64, i32, i64, vsp, vp, i64, vp]
+    L.melspec_vad_host.restype = i32
+    L.melspec_vad_host.argtypes = [vp, vp, i32, i64, vsp, vp, vp]
     _LIB = L
     return L
 

@@ -11,6 +11,7 @@ Same names, argument meaning and error behaviour as the Rust prelude (reference 
     RingBuffer                     src/rb.rs:12-122    add_frame / add / maybe_mel, frames come from the streaming C ABI
     interleave_frames              src/mel.rs:480-544  (row-major (n_mels, W) image; produced by the kernel's mel-major store)
     quantize / dequantize / tga_8bit_data / parse_tga_8bit / QuantizationRange      src/quant.rs:5-165
+    DetectionSettings / EdgeInfo / vad_boundaries / vad_on / VoiceActivity / VoiceActivityDetector   src/vad.rs:5-338
 
 Arrays are numpy instead of Vec<Vec<f32>> / ndarray; shapes and element order are the reference's.
 Everything numeric happens in `lib/libmelspec_b200.so`; nothing here computes features on the CPU.
@@ -51,6 +52,81 @@ def _check(rc: int, constructing: bool = False):
     if rc == ERR_INVALID_ARG:
         raise ValueError(msg)
     raise CudaError("Runtime", msg, rc)
+
+
+@dataclass
+class DetectionSettings:
+    """reference src/vad.rs:5-22 (Default) and 44-81."""
+    min_energy: float = 0.98
+    min_y: int = 11
+    min_x: int = 5
+    min_mel: int = 2
+
+    def _c(self) -> "_lib.VadSettings":
+        return _lib.VadSettings(float(self.min_energy), int(self.min_y), int(self.min_x), int(self.min_mel))
+
+
+@dataclass
+class EdgeInfo:
+    """reference src/vad.rs:488-520 (gradient_positions is left empty by the reference's current vad_boundaries)."""
+    non_intersected_columns: list
+    intersected_columns: list
+
+    def non_intersected(self) -> list:
+        return list(self.non_intersected_columns)
+
+    def intersected(self) -> list:
+        return list(self.intersected_columns)
+
+    def gradient_positions(self) -> set:
+        return set()
+
+
+def vad_on(edge_info: "EdgeInfo", n: int) -> bool:
+    """reference src/vad.rs:226-249 (host logic over the device mask), quirk included: the first column alone never fires."""
+    cols = edge_info.intersected_columns
+    if not cols:
+        return False
+    cnt, prev = 1, cols[0]
+    for ix in cols[1:]:
+        cnt = cnt + 1 if ix == prev + 1 else 1
+        if cnt >= n:
+            return True
+        prev = ix
+    return False
+
+
+@dataclass(frozen=True)
+class VoiceActivityTimestamps:
+    """reference src/vad.rs:117-122."""
+    start_ms: int
+    center_ms: int
+    end_ms: int
+
+
+@dataclass(frozen=True)
+class VadFrameTiming:
+    """reference src/vad.rs:90-115."""
+    fft_size: int
+    hop_size: int
+    sampling_rate: float
+
+    def timestamps_for_frame(self, frame_index: int) -> VoiceActivityTimestamps:
+        start = frame_index * self.hop_size
+        ms = lambda smp: int(np.floor(smp / self.sampling_rate * 1000.0 + 0.5))     # f64::round of a non-negative value
+        return VoiceActivityTimestamps(ms(start), ms(start + self.fft_size // 2), ms(start + self.fft_size))
+
+
+@dataclass(frozen=True)
+class VoiceActivity:
+    """reference src/vad.rs:124-133."""
+    active: bool
+    frame_index: int
+    leading_active_columns: int
+    active_columns: int
+    window_columns: int
+    confidence: float
+    timestamps: "VoiceActivityTimestamps | None" = None
 
 
 @dataclass
@@ -291,6 +367,56 @@ class _Handle:
             raise IOError("failed to fill whole buffer")
         out = np.empty(b.size - 26, dtype=np.float32)
         _check(self._L.melspec_dequantize_tga_host(self._h, b.ctypes.data, int(b.size), out.ctypes.data, int(out.size)))
+        return out
+
+    # ---- VAD over the mel image (reference src/vad.rs:251-486, 163-207) ---------------------------------------
+    def vad_boundaries_device(self, d_img, n_imgs: int, n_mels: int, width: int, settings: "DetectionSettings", d_smoothed, *,
+                              d_raw=None, img_stride: int = 0, mask_stride: int = 0, stream=None) -> None:
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        vs = settings._c()
+        _check(self._L.melspec_vad_boundaries_device(self._h, _ptr(d_img), int(n_imgs), int(img_stride), int(n_mels), int(width),
+                                                     C.byref(vs), _ptr(d_raw), _ptr(d_smoothed), int(mask_stride), s))
+
+    def vad_activity_device(self, d_raw, n_imgs: int, n_mels: int, width: int, settings: "DetectionSettings", d_activity, *,
+                            mask_stride: int = 0, activity_stride: int = 0, stream=None) -> None:
+        s = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        vs = settings._c()
+        _check(self._L.melspec_vad_activity_device(self._h, _ptr(d_raw), int(n_imgs), int(mask_stride), int(n_mels), int(width),
+                                                   C.byref(vs), _ptr(d_activity), int(activity_stride), s))
+
+    def vad_boundaries(self, frames, settings: "DetectionSettings | None" = None) -> "EdgeInfo":
+        """vad_boundaries (src/vad.rs:251-338) on a (n_mels, width) image (frames side by side, as to_array2 returns)."""
+        settings = settings or DetectionSettings()
+        a = np.ascontiguousarray(np.asarray(frames, dtype=np.float32))
+        if a.ndim != 2:
+            raise ValueError("frames must be a (n_mels, width) image")
+        h, w = a.shape
+        if h < 3 or w < 3:
+            return EdgeInfo([], [])
+        sm = np.zeros(w - 2, dtype=np.uint8)
+        vs = settings._c()
+        _check(self._L.melspec_vad_host(self._h, a.ctypes.data, int(h), int(w), C.byref(vs), sm.ctypes.data, 0))
+        idx = np.arange(w - 2)
+        return EdgeInfo(idx[sm == 0].tolist(), idx[sm != 0].tolist())
+
+    def vad_activities(self, frames, settings: "DetectionSettings | None" = None, timing: "VadFrameTiming | None" = None):
+        """VoiceActivityDetector::add_activity (src/vad.rs:163-207) for every column of the image: list of VoiceActivity."""
+        settings = settings or DetectionSettings()
+        a = np.ascontiguousarray(np.asarray(frames, dtype=np.float32))
+        h, w = a.shape
+        if w == 0:
+            return []
+        act = np.zeros((w, 3), dtype=np.int32)
+        sm = np.zeros(max(w - 2, 1), dtype=np.uint8)
+        vs = settings._c()
+        _check(self._L.melspec_vad_host(self._h, a.ctypes.data, int(h), int(w), C.byref(vs), sm.ctypes.data, act.ctypes.data))
+        win = max(settings.min_x - 2, 0) if (h >= 3 and settings.min_x >= 3) else 0
+        out = []
+        for i in range(w):
+            if act[i, 0] < 0:
+                continue
+            out.append(VoiceActivity(bool(act[i, 0]), i, int(act[i, 1]), int(act[i, 2]), win,
+                                     (act[i, 2] / win) if win else 0.0, timing.timestamps_for_frame(i) if timing else None))
         return out
 
     def compute_host_raw(self, h_pcm_ptr: int, n_clips: int, clip_stride: int, n_samples: int, h_out_ptr: int,

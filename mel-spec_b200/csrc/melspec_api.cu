@@ -1004,6 +1004,87 @@ int32_t melspec_mel_tga_host(melspec_handle* h, const float* h_pcm, int64_t n_sa
     return MELSPEC_OK;
 }
 
+
+// ---- VAD over the mel image (reference src/vad.rs:251-486, 163-207) -----------------------------------------
+int32_t melspec_vad_default_settings(melspec_vad_settings* s) {
+    if (!s) return fail(MELSPEC_ERR_INVALID_ARG, "settings is null");
+    s->min_energy = 0.98; s->min_y = 11; s->min_x = 5; s->min_mel = 2;   // src/vad.rs:13-22
+    return MELSPEC_OK;
+}
+
+int32_t melspec_vad_boundaries_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
+                                      int64_t width, const melspec_vad_settings* vs, uint8_t* d_raw, uint8_t* d_smoothed,
+                                      int64_t mask_stride, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (!vs) return fail(MELSPEC_ERR_INVALID_ARG, "settings is null");
+    if (n_imgs < 0 || img_stride < 0 || mask_stride < 0 || n_mels < 0 || width < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (vs->min_y < 0 || vs->min_x < 0 || vs->min_mel < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative setting");
+    if (width > 0x7fffffff || (int64_t)n_mels * width > 0x7fffffffll * 4) return fail(MELSPEC_ERR_INVALID_ARG, "image too large");
+    if (n_imgs == 0 || n_mels < 3 || width < 3) return MELSPEC_OK;        // empty EdgeInfo, src/vad.rs:264-266
+    if (!d_img || !d_smoothed) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
+    if (!img_stride) img_stride = (int64_t)n_mels * width;
+    if (!mask_stride) mask_stride = width - 2;
+    MS_CUDA(cudaSetDevice(h->device));
+    const int nb = (int)((width - 2 + melspec::kVadTile - 1) / melspec::kVadTile);
+    melspec::melspec_vad_kernel<<<dim3(nb, (unsigned)n_imgs), 256, 0, (cudaStream_t)stream>>>(
+        d_img, img_stride, n_mels, (int)width, vs->min_energy * vs->min_energy, vs->min_y, vs->min_mel, d_raw, d_smoothed, mask_stride);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MELSPEC_OK;
+}
+
+int32_t melspec_vad_activity_device(melspec_handle* h, const uint8_t* d_raw, int64_t n_imgs, int64_t mask_stride, int32_t n_mels,
+                                    int64_t width, const melspec_vad_settings* vs, int32_t* d_activity, int64_t activity_stride,
+                                    void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (!vs) return fail(MELSPEC_ERR_INVALID_ARG, "settings is null");
+    if (n_imgs < 0 || mask_stride < 0 || activity_stride < 0 || width < 0 || width > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "bad size");
+    if (vs->min_x < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative setting");
+    if (n_imgs == 0 || width == 0) return MELSPEC_OK;
+    if (!d_activity || (!d_raw && n_mels >= 3 && width >= 3)) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
+    if (!mask_stride) mask_stride = width - 2;
+    if (!activity_stride) activity_stride = 3 * width;
+    MS_CUDA(cudaSetDevice(h->device));
+    melspec::melspec_vad_activity_kernel<<<dim3((unsigned)((width + 255) / 256), (unsigned)n_imgs), 256, 0, (cudaStream_t)stream>>>(
+        d_raw, mask_stride, n_mels, (int)width, vs->min_x, d_activity, activity_stride);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MELSPEC_OK;
+}
+
+// Host-buffer convenience (blocking): one row-major (n_mels, width) f32 image -> smoothed mask (width-2 bytes, 1 = the column
+// intersects an edge) and, optionally, the per-frame activity triples (3*width int32).
+int32_t melspec_vad_host(melspec_handle* h, const float* h_img, int32_t n_mels, int64_t width, const melspec_vad_settings* vs,
+                         uint8_t* h_smoothed, int32_t* h_activity_opt) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (!vs) return fail(MELSPEC_ERR_INVALID_ARG, "settings is null");
+    if (n_mels < 0 || width < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (width == 0 || n_mels == 0) return MELSPEC_OK;
+    if (!h_img) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    MS_CUDA(cudaSetDevice(h->device));
+    const size_t ib = (size_t)n_mels * (size_t)width * 4;
+    const size_t nmask = width >= 3 ? (size_t)(width - 2) : 0;
+    const size_t act_off = (2 * nmask + 15) / 16 * 16;
+    int32_t rc = ensure_fmt(h, ib, act_off + 12 * (size_t)width + 16);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpy(h->d_fmt_img, h_img, ib, cudaMemcpyHostToDevice));
+    uint8_t* d_raw = h->d_fmt_tga;
+    uint8_t* d_sm = h->d_fmt_tga + nmask;
+    int32_t* d_act = reinterpret_cast<int32_t*>(h->d_fmt_tga + act_off);
+    if (nmask) MS_CUDA(cudaMemset(d_raw, 0, 2 * nmask));
+    rc = melspec_vad_boundaries_device(h, h->d_fmt_img, 1, 0, n_mels, width, vs, d_raw, d_sm, 0, nullptr);
+    if (rc) return rc;
+    if (h_smoothed && nmask && n_mels >= 3) MS_CUDA(cudaMemcpy(h_smoothed, d_sm, nmask, cudaMemcpyDeviceToHost));
+    if (h_activity_opt) {
+        rc = melspec_vad_activity_device(h, d_raw, 1, 0, n_mels, width, vs, d_act, 0, nullptr);
+        if (rc) return rc;
+        MS_CUDA(cudaMemcpy(h_activity_opt, d_act, 12 * (size_t)width, cudaMemcpyDeviceToHost));
+    }
+    return MELSPEC_OK;
+}
+
 int64_t melspec_launch_count(const melspec_handle* h) { return h ? h->launches : 0; }
 
 int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacity) {

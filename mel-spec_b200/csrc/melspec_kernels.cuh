@@ -1226,4 +1226,78 @@ __global__ void __launch_bounds__(256) melspec_dequantize_kernel(const unsigned 
         dst[i] = __fadd_rn(__fmul_rn((float)src[kTgaHeader + i], scale), mn);
 }
 
+// ================================================================================================ VAD over the mel image
+// vad_boundaries (reference src/vad.rs:251-338): per column x of the row-major (height, width) image, count the rows y in
+// [min(min_mel, height-2), height-2) whose 3x3 Sobel gradient (src/vad.rs:472-486) satisfies gx^2 + gy^2 >= min_energy^2;
+// the column is raw-active when the count reaches min_y; then a +-4 majority vote (smooth_mask, src/vad.rs:343-360).
+// f64 in the reference's operation order on the (f32-valued) pixels, so the masks are bit-exact with the CPU path.
+// grid = (ceil((width-2) / 248), n_imgs), block = 256: thread j owns raw column tile0 - 4 + j, threads 4..251 smooth.
+constexpr int kVadTile = 248;
+__global__ void __launch_bounds__(256) melspec_vad_kernel(const float* img, long long img_stride, int height, int width, double min_energy_sq,
+                                                          int min_y, int min_mel, unsigned char* raw_out, unsigned char* smooth_out,
+                                                          long long mask_stride) {
+    __shared__ unsigned char s_raw[256];
+    const float* a = img + (long long)blockIdx.y * img_stride;
+    const int n = width - 2;
+    const int x = blockIdx.x * kVadTile - 4 + (int)threadIdx.x;
+    unsigned char act = 0;
+    if (x >= 0 && x < n) {
+        if (min_y == 0) {
+            act = 1;
+        } else {
+            const int y0 = min(min_mel, height - 2);
+            int count = 0;
+            const float* p = a + (long long)y0 * width + x;
+            double r0l = p[0], r0c = p[1], r0r = p[2];
+            double r1l = p[width], r1c = p[width + 1], r1r = p[width + 2];
+            for (int y = y0; y < height - 2; ++y) {
+                const float* q = a + (long long)(y + 2) * width + x;
+                const double r2l = q[0], r2c = q[1], r2r = q[2];
+                const double gx = __dsub_rn(__dadd_rn(__dadd_rn(r0r, __dmul_rn(2.0, r1r)), r2r), __dadd_rn(__dadd_rn(r0l, __dmul_rn(2.0, r1l)), r2l));
+                const double gy = __dsub_rn(__dadd_rn(__dadd_rn(r2l, __dmul_rn(2.0, r2c)), r2r), __dadd_rn(__dadd_rn(r0l, __dmul_rn(2.0, r0c)), r0r));
+                if (__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)) >= min_energy_sq) ++count;
+                r0l = r1l; r0c = r1c; r0r = r1r;
+                r1l = r2l; r1c = r2c; r1r = r2r;
+            }
+            (void)r1c;
+            act = count >= min_y ? 1 : 0;
+        }
+    }
+    s_raw[threadIdx.x] = act;
+    __syncthreads();
+    if (threadIdx.x >= 4 && threadIdx.x < 4 + kVadTile && x < n) {
+        if (raw_out) raw_out[(long long)blockIdx.y * mask_stride + x] = act;
+        const int st = max(x - 4, 0), en = min(x + 5, n);
+        int cnt = 0;
+        for (int k = st; k < en; ++k) cnt += s_raw[(int)threadIdx.x + (k - x)];
+        smooth_out[(long long)blockIdx.y * mask_stride + x] = (cnt * 2 >= en - st) ? 1 : 0;
+    }
+}
+
+// VoiceActivityDetector::add_activity (src/vad.rs:163-207) for every frame index at once: frame i >= min_x - 1 looks at
+// the window of the last min_x columns, i.e. raw columns s .. s + min_x - 3 (s = i + 1 - min_x; the raw decision of a
+// column triple does not depend on the window), smooths them inside the window and reports
+// (active = first column intersected, leading_active_columns, active_columns).  Frames before that: (-1, -1, -1).
+__global__ void __launch_bounds__(256) melspec_vad_activity_kernel(const unsigned char* raw, long long mask_stride, int height, int width,
+                                                                   int min_x, int* out, long long out_stride) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= width) return;
+    int* o = out + (long long)blockIdx.y * out_stride + 3ll * i;
+    if (i + 1 < min_x) { o[0] = -1; o[1] = -1; o[2] = -1; return; }
+    if (height < 3 || min_x < 3) { o[0] = 0; o[1] = 0; o[2] = 0; return; }   // vad_boundaries' empty EdgeInfo (src/vad.rs:264-266)
+    const unsigned char* r = raw + (long long)blockIdx.y * mask_stride + (i + 1 - min_x);
+    const int n = min_x - 2;
+    int active = 0, leading = 0, total = 0;
+    bool lead_open = true;
+    for (int j = 0; j < n; ++j) {
+        const int st = max(j - 4, 0), en = min(j + 5, n);
+        int cnt = 0;
+        for (int k = st; k < en; ++k) cnt += r[k];
+        const bool sm = cnt * 2 >= en - st;
+        if (j == 0) active = sm;
+        if (sm) { ++total; if (lead_open) ++leading; } else lead_open = false;
+    }
+    o[0] = active; o[1] = leading; o[2] = total;
+}
+
 }  // namespace melspec

@@ -486,3 +486,86 @@ def parse_tga_8bit(data: bytes) -> np.ndarray:
         raise IOError("failed to fill whole buffer")
     mn, mx = np.frombuffer(b[18:26], dtype="<f4")
     return dequantize(np.frombuffer(b[26:], dtype=np.uint8), (mn, mx))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VAD over the mel image: Sobel edge count per column + majority smoothing (reference src/vad.rs:251-486)
+# ---------------------------------------------------------------------------------------------------------------
+DEFAULT_DETECTION = dict(min_energy=0.98, min_y=11, min_x=5, min_mel=2)      # src/vad.rs:13-22
+
+
+def vad_raw_classification(img, min_energy: float, min_y: int, min_mel: int) -> np.ndarray:
+    """classify_columns_in_frame (src/vad.rs:373-415): img is (height = n_mels, width) row-major; column x is active when
+    at least min_y rows y in [min(min_mel, height-2), height-2) have a squared Sobel gradient (src/vad.rs:472-486) of the
+    3x3 patch at (y, x) >= min_energy^2.  f64 arithmetic in the reference's operation order.  Returns bool (width-2,)."""
+    a = np.asarray(img, dtype=np.float64)
+    h, w = a.shape
+    if h < 3 or w < 3:                                                     # src/vad.rs:264-266
+        return np.zeros(0, dtype=bool)
+    if min_y == 0:                                                         # src/vad.rs:382-385
+        return np.ones(w - 2, dtype=bool)
+    y0 = min(min_mel, h - 2)
+    tl, tc, tr = a[y0:h - 2, 0:w - 2], a[y0:h - 2, 1:w - 1], a[y0:h - 2, 2:w]
+    ml, mr = a[y0 + 1:h - 1, 0:w - 2], a[y0 + 1:h - 1, 2:w]
+    bl, bc, br = a[y0 + 2:h, 0:w - 2], a[y0 + 2:h, 1:w - 1], a[y0 + 2:h, 2:w]
+    gx = ((tr + (2.0 * mr)) + br) - ((tl + (2.0 * ml)) + bl)
+    gy = ((bl + (2.0 * bc)) + br) - ((tl + (2.0 * tc)) + tr)
+    hit = ((gx * gx) + (gy * gy)) >= (min_energy * min_energy)
+    return hit.sum(axis=0) >= min_y
+
+
+def vad_smooth_mask(mask, window: int = 4) -> np.ndarray:
+    """smooth_mask (src/vad.rs:343-360): true when at least half of [i-window, i+window] (clipped) is true."""
+    m = np.asarray(mask, dtype=bool)
+    n = m.size
+    pre = np.concatenate([[0], np.cumsum(m)])
+    out = np.zeros(n, dtype=bool)
+    for i in range(n):
+        st, en = max(i - window, 0), min(i + window + 1, n)
+        out[i] = (pre[en] - pre[st]) * 2 >= (en - st)
+    return out
+
+
+def vad_boundaries(img, min_energy=0.98, min_y=11, min_x=5, min_mel=2):
+    """vad_boundaries (src/vad.rs:251-338) on one (n_mels, width) image.  Returns (non_intersected, intersected) column lists."""
+    sm = vad_smooth_mask(vad_raw_classification(img, min_energy, min_y, min_mel), 4)
+    idx = np.arange(sm.size)
+    return idx[~sm].tolist(), idx[sm].tolist()
+
+
+def vad_on(intersected, n: int) -> bool:
+    """vad_on (src/vad.rs:226-249), including its quirk: a lone first column never counts, so n == 1 needs two columns."""
+    if len(intersected) == 0:
+        return False
+    cnt, prev = 1, intersected[0]
+    for ix in intersected[1:]:
+        cnt = cnt + 1 if ix == prev + 1 else 1
+        if cnt >= n:
+            return True
+        prev = ix
+    return False
+
+
+def vad_leading_active_columns(intersected) -> int:
+    """src/vad.rs:213-224."""
+    exp = 0
+    for c in intersected:
+        if c == exp:
+            exp += 1
+        elif c > exp:
+            break
+    return exp
+
+
+def vad_activity_stream(img, min_energy=0.98, min_y=11, min_x=5, min_mel=2):
+    """VoiceActivityDetector::add_activity (src/vad.rs:163-207) fed the columns of img one by one: for every frame index
+    i >= min_x - 1 the decision over the window of the last min_x frames.  Returns a list of
+    (frame_index, active, leading_active_columns, active_columns, window_columns)."""
+    a = np.asarray(img, dtype=np.float64)
+    out = []
+    for i in range(a.shape[1]):
+        if i + 1 < min_x:
+            continue
+        non, inter = vad_boundaries(a[:, i + 1 - min_x:i + 1], min_energy, min_y, min_x, min_mel)
+        out.append((i, bool(inter and inter[0] == 0), vad_leading_active_columns(inter), len(inter), len(inter) + len(non)))
+    return out

@@ -19,6 +19,8 @@ vectors and the audio clip they were computed from.
   quantized_mel_golden.tga  80 x 1100 8-bit TGA (src/quant.rs format) — testdata/quantized_mel_golden.tga, the fixture of the
                          reference's VAD tests (src/vad.rs:712,742; tests/vad_regression.rs:157,215).  Columns 2..1099 are the
                          quantised Whisper fft-400 / hop-160 stream mel of the JFK clip (verified bit-exact against the oracle).
+  vad/blank/*.tga, vad/speech/*.tga   the 7 + 5 quantised mel images of the reference's VAD known-answer test
+                         (src/vad.rs:621-668: vad_on must be false on blank/, true on speech/)
 """
 import os
 import struct
@@ -61,6 +63,12 @@ def main():
     np.save(os.path.join(HERE, "kaldi_fbank_jfk.npy"), np.load(os.path.join(td, "kaldi_native_fbank_jfk.npz"))["features"])
     with open(os.path.join(td, "quantized_mel_golden.tga"), "rb") as src, open(os.path.join(HERE, "quantized_mel_golden.tga"), "wb") as dst:
         dst.write(src.read())
+    for kind in ("blank", "speech"):            # fixtures of src/vad.rs:621-668 (test_speech_detection)
+        os.makedirs(os.path.join(HERE, "vad", kind), exist_ok=True)
+        for f in sorted(os.listdir(os.path.join(td, kind))):
+            if f.endswith(".tga"):
+                with open(os.path.join(td, kind, f), "rb") as src, open(os.path.join(HERE, "vad", kind, f), "wb") as dst:
+                    dst.write(src.read())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npy"):
             a = np.load(os.path.join(HERE, f))
