@@ -110,6 +110,47 @@ impl CudaMelSpectrogram {
     }
 }
 
+impl CudaMelSpectrogram {
+    /// `interleave_frames(frames, false, min_width)` (reference src/mel.rs:480-544) + `tga_8bit_data` (src/quant.rs:38-64)
+    /// of the mel frames of `samples`, computed on the device in one pipeline.  Returns (tga bytes, width).
+    pub fn mel_tga(&mut self, samples: &[f32], min_width: usize) -> Result<(Vec<u8>, usize), CudaError> {
+        assert!(min_width % 2 == 0, "min_width must be even");
+        let frames = unsafe { ffi::melspec_num_frames(self.handle, samples.len() as i64) };
+        assert!(frames > 0, "frames is empty");
+        let width = unsafe { ffi::melspec_interleaved_width(frames, min_width as i64) };
+        let size = unsafe { ffi::melspec_tga_size(self.n_mels as i32, width) };
+        assert!(size > 0, "width greater than TARGA max, use [`tga_8bit`]");
+        let mut out = vec![0u8; size as usize];
+        let mut w = 0i64;
+        let rc = unsafe {
+            ffi::melspec_mel_tga_host(self.handle, samples.as_ptr(), samples.len() as i64, min_width as i64, out.as_mut_ptr(),
+                                      size, &mut w, ptr::null_mut())
+        };
+        if rc != 0 {
+            return Err(CudaError::Runtime(ffi::last_error()));
+        }
+        Ok((out, w as usize))
+    }
+
+    /// `vad_boundaries` (reference src/vad.rs:251-338) on a row-major (n_mels, width) image: the smoothed per-column mask
+    /// (`true` = column in `EdgeInfo::intersected()`), computed by the device kernel in f64 like the reference.
+    pub fn vad_mask(&mut self, image: &[f32], settings: (f64, usize, usize, usize)) -> Result<Vec<bool>, CudaError> {
+        let width = image.len() / self.n_mels;
+        if self.n_mels < 3 || width < 3 {
+            return Ok(Vec::new());
+        }
+        let vs = ffi::VadSettings { min_energy: settings.0, min_y: settings.1 as i32, min_x: settings.2 as i32, min_mel: settings.3 as i32 };
+        let mut mask = vec![0u8; width - 2];
+        let rc = unsafe {
+            ffi::melspec_vad_host(self.handle, image.as_ptr(), self.n_mels as i32, width as i64, &vs, mask.as_mut_ptr(), ptr::null_mut())
+        };
+        if rc != 0 {
+            return Err(CudaError::Runtime(ffi::last_error()));
+        }
+        Ok(mask.into_iter().map(|b| b != 0).collect())
+    }
+}
+
 impl Drop for CudaMelSpectrogram {
     fn drop(&mut self) {
         unsafe { ffi::melspec_destroy(self.handle) };
@@ -144,6 +185,31 @@ mod ffi {
         pub low_freq: f64,
         pub high_freq: f64,
         pub energy_floor: f64,
+        // NeMo block (BatchLogMelConfig, reference src/mel.rs:171-208)
+        pub win_length: i32,
+        pub center: i32,
+        pub pad_to: i32,
+        pub normalize_per_feature: i32,
+        pub htk: i32,
+        pub slaney_norm: i32,
+        pub log_zero_guard: f64,
+        pub f_min: f64,
+        pub f_max: f64,
+    }
+
+    #[repr(C)]
+    pub struct MelspecStream {
+        _private: [u8; 0],
+    }
+
+    /// `struct melspec_vad_settings` == DetectionSettings (reference src/vad.rs:5-22).
+    #[repr(C)]
+    #[derive(Clone, Copy)]
+    pub struct VadSettings {
+        pub min_energy: f64,
+        pub min_y: i32,
+        pub min_x: i32,
+        pub min_mel: i32,
     }
 
     #[link(name = "melspec_b200")]
@@ -176,6 +242,44 @@ mod ffi {
             frames_out: *mut i64,
         ) -> i32;
         pub fn melspec_last_error() -> *const c_char;
+        // streaming: RingBuffer::maybe_mel / Spectrogram::add semantics (reference src/rb.rs:86-121, src/stft.rs:48-86)
+        pub fn melspec_stream_create(h: *mut MelspecHandle, max_chunk_samples: i64, out: *mut *mut MelspecStream) -> i32;
+        pub fn melspec_stream_push(
+            s: *mut MelspecStream,
+            h_samples: *const f32,
+            n: i64,
+            h_out: *mut f32,
+            out_capacity_frames: i64,
+            frames_emitted: *mut i64,
+        ) -> i32;
+        pub fn melspec_stream_reset(s: *mut MelspecStream) -> i32;
+        pub fn melspec_stream_destroy(s: *mut MelspecStream);
+        // output formats: interleave_frames (src/mel.rs:480-544) and the 8-bit TGA quantiser (src/quant.rs:38-165)
+        pub fn melspec_interleaved_width(n_frames: i64, min_width: i64) -> i64;
+        pub fn melspec_tga_size(n_mels: i32, width: i64) -> i64;
+        pub fn melspec_mel_tga_host(
+            h: *mut MelspecHandle,
+            h_pcm: *const f32,
+            n_samples: i64,
+            min_width: i64,
+            h_tga: *mut u8,
+            capacity: i64,
+            width_out: *mut i64,
+            h_img_opt: *mut f32,
+        ) -> i32;
+        pub fn melspec_quantize_tga_host(h: *mut MelspecHandle, h_img: *const f32, n_mels: i32, width: i64, h_tga: *mut u8) -> i32;
+        pub fn melspec_dequantize_tga_host(h: *mut MelspecHandle, h_tga: *const u8, tga_bytes: i64, h_img: *mut f32, capacity: i64) -> i32;
+        // VAD over the mel image (src/vad.rs:251-338, 163-207)
+        pub fn melspec_vad_default_settings(s: *mut VadSettings) -> i32;
+        pub fn melspec_vad_host(
+            h: *mut MelspecHandle,
+            h_img: *const f32,
+            n_mels: i32,
+            width: i64,
+            vs: *const VadSettings,
+            h_smoothed: *mut u8,
+            h_activity_opt: *mut i32,
+        ) -> i32;
     }
 
     pub fn last_error() -> String {
