@@ -1126,7 +1126,12 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     // kernel of chunk i and the D2H copy of chunk i-1 overlap when the host buffers are pinned.
     const int64_t ns4 = (n_samples + 3) / 4 * 4;   // device rows are padded to 16 bytes so the TMA path applies
     const int64_t clip_out = padded_frames_for(h->cfg, n_samples) * h->cfg.n_mels;
-    const int64_t target = 32ll << 20;             // ~32 MiB of PCM per chunk
+    static const int64_t chunk_mb = [] {            // MELSPEC_HOST_CHUNK_MB: PCM bytes per pipeline chunk (tuning knob)
+        const char* e = std::getenv("MELSPEC_HOST_CHUNK_MB");
+        const int64_t v = e ? std::atoll(e) : 0;
+        return v > 0 ? v : (int64_t)32;
+    }();
+    const int64_t target = chunk_mb << 20;
     int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
     per_chunk = std::min(per_chunk, n_clips);
     if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
