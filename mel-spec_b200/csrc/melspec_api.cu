@@ -220,18 +220,6 @@ struct melspec_stream {
 
 namespace {
 
-// Power-slab row that holds bin b for a plan N = R x C (R/2 workers per FFT, row = (R/2)*j + t); see
-// melspec_kernels.cuh and tools/model_plan.py.  Plan 400: R = C = 20.  Plan 512: R = 32, C = 16.
-int row_of_bin(int b, int R, int C) {
-    const int rr = b % R, q = b / R;
-    int t, j;
-    if (rr == 0) { t = 0; j = C - q; }                 // worker 0, high half: bin R*(C-j)
-    else if (rr == R / 2) { t = 0; j = q; }            // worker 0, low half: bin R/2 + R*j
-    else if (rr < R / 2) { t = rr; j = q; }            // worker rr, low half: bin rr + R*j
-    else { t = R - rr; j = C - 1 - q; }                // worker R-rr, high half: bin (R-t) + R*(C-1-j)
-    return (R / 2) * j + t;
-}
-
 int32_t build_tables(melspec_handle* h) {
     const Resolved& c = h->cfg;
     using namespace melspec;
@@ -298,9 +286,11 @@ int32_t build_tables(melspec_handle* h) {
     std::vector<float2> proj;
     std::vector<int> meta(kMetaInts, -1);
     h->mpl = (c.n_mels + 31) / 32;
-    if (N == 400) {
-        // ---- plan 400: windowed projection program (melspec400_kernel).  A lane's slot-s entries are K_s consecutive bins
-        // [start, start + K_s) of the bin-ordered power planes; the table holds the weights only.
+    {
+        // ---- windowed projection program (both plans).  A lane's slot-s entries are K_s consecutive bins [start, start + K_s)
+        // of the bin-ordered power rows; the table holds the weights only.  Plan 400 reads 8-byte rows of three planes with
+        // LDS.64 (conflicts are per half-warp, rows mod 16), plan 512 reads 16-byte rows with LDS.128 (per quarter-warp, mod 8).
+        const int grp = N == 400 ? 16 : 8, ngrp = 32 / grp, last_row = N / 2;
         struct Piece { int mel, b0, len; };
         std::vector<Piece> pcs;
         for (int m = 0; m < c.n_mels; ++m) {
@@ -336,9 +326,9 @@ int32_t build_tables(melspec_handle* h) {
             const int nc = stage_cost();
             if (nc <= sc) sc = nc; else std::swap(pcs[a], pcs[b]);
         }
-        // (2) Window starts: piece i may start anywhere in [max(1, b0 + len - K), min(b0, 201 - K)] (rows 1..200 are the ones
-        // the kernel writes every pass).  The three LDS.64 of an entry are conflict-free when the 16 lanes of a half-warp
-        // start at 16 different rows mod 16: a perfect matching of the slot's 32 pieces onto (half-warp, residue) pairs
+        // (2) Window starts: piece i may start anywhere in [max(1, b0 + len - K), min(b0, N/2 + 1 - K)] (rows 1..N/2 are the ones
+        // the kernel writes every pass).  The power loads of an entry are conflict-free when the `grp` lanes of a lane group
+        // start at `grp` different rows mod `grp`: a perfect matching of the slot's 32 pieces onto (lane group, residue) pairs
         // (Kuhn's augmenting paths; whatever stays unmatched is placed anyway and merely costs a wavefront).
         const int ktot4 = std::max(4, (ktot + 3) / 4 * 4);
         std::vector<float> wtab((size_t)2 * ktot4 * 32, 0.f);
@@ -350,16 +340,16 @@ int32_t build_tables(melspec_handle* h) {
             for (int i = 0; i < 32; ++i) {
                 const Piece& pc = pcs[(size_t)32 * s + i];
                 lo[i] = std::max(1, pc.b0 + pc.len - Ks);
-                hi[i] = std::min(pc.b0, 201 - Ks);
-                if (pc.len == 0) { lo[i] = 1; hi[i] = std::max(1, 201 - Ks); }
+                hi[i] = std::min(pc.b0, last_row + 1 - Ks);
+                if (pc.len == 0) { lo[i] = 1; hi[i] = std::max(1, last_row + 1 - Ks); }
                 if (hi[i] < lo[i]) hi[i] = lo[i];
             }
             int owner[32];   // (half-warp, residue) -> piece
             std::fill(owner, owner + 32, -1);
             std::function<bool(int, std::vector<char>&)> augment = [&](int i, std::vector<char>& seen) {
-                for (int st = lo[i]; st <= hi[i] && st < lo[i] + 16; ++st)
-                    for (int hw = 0; hw < 2; ++hw) {
-                        const int node = 16 * hw + (st & 15);
+                for (int st = lo[i]; st <= hi[i] && st < lo[i] + grp; ++st)
+                    for (int hw = 0; hw < ngrp; ++hw) {
+                        const int node = grp * hw + (st & (grp - 1));
                         if (seen[node]) continue;
                         seen[node] = 1;
                         if (owner[node] < 0 || augment(owner[node], seen)) { owner[node] = i; return true; }
@@ -376,17 +366,19 @@ int32_t build_tables(melspec_handle* h) {
             }
             int lane_piece[32], lane_start[32];
             std::fill(lane_piece, lane_piece + 32, -1);
-            int fill[2] = {0, 0};
+            int fill[4] = {0, 0, 0, 0};
             for (int node = 0; node < 32; ++node) {
                 const int i = owner[node];
                 if (i < 0) continue;
-                const int hw = node / 16, l = 16 * hw + fill[hw]++;
+                const int hw = node / grp, l = grp * hw + fill[hw]++;
                 int st = lo[i];
-                while ((st & 15) != (node & 15)) ++st;
+                while ((st & (grp - 1)) != (node & (grp - 1))) ++st;
                 lane_piece[l] = i; lane_start[l] = st;
             }
             for (int i : unmatched) {
-                const int hw = fill[0] < 16 ? 0 : 1, l = 16 * hw + fill[hw]++;
+                int hw = 0;
+                while (hw < ngrp - 1 && fill[hw] >= grp) ++hw;
+                const int l = grp * hw + fill[hw]++;
                 lane_piece[l] = i; lane_start[l] = lo[i];
                 h->proj_wavefront_cost += 3 * Ks;
             }
@@ -410,105 +402,9 @@ int32_t build_tables(melspec_handle* h) {
         for (int s = h->mpl; s < kMaxMpl; ++s)
             for (int l = 0; l < 32; ++l) meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = 1;
         h->proj_ktot = ktot4;
-        h->kspec = (h->mpl == 3 && K[0] == 14 && K[1] == 4 && K[2] == 2) ? 1 : 0;
+        h->kspec = (N == 400 && h->mpl == 3 && K[0] == 14 && K[1] == 4 && K[2] == 2) ? 1 : 0;
         proj.resize(wtab.size() / 2);
         std::memcpy(proj.data(), wtab.data(), wtab.size() * sizeof(float));
-    } else {
-    std::vector<Band> sorted = bands;
-    std::stable_sort(sorted.begin(), sorted.end(), [](const Band& a, const Band& b) { return a.e.size() > b.e.size(); });
-    int ktot = 0;
-    for (int s = 0; s < kMaxMpl; ++s) {
-        int K = 0;
-        for (int l = 0; l < 32; ++l) {
-            const int r = s * 32 + l;
-            if (r < c.n_mels) K = std::max(K, (int)sorted[r].e.size());
-        }
-        meta[s] = K;
-        ktot += K;
-    }
-    // The kernel's projection loop reads, per entry, three consecutive float2 of one power-slab row per lane
-    // (LDS.64, processed per half-warp): it is bank-conflict free when the 16 lanes of a half-warp hit rows that
-    // differ mod 16.  Which lane of a slot owns which mel, the order of a mel's entries and the rows that padding
-    // entries point at are all free, so a small deterministic hill-climb minimises the number of wavefronts.
-    proj.assign((size_t)(std::max(ktot, 1) + 1) * 32, make_float2(0.f, 0.f));   // + one padding row (prefetch)
-    int eoff = 0;
-    uint64_t rng = 0x9E3779B97F4A7C15ull;
-    auto rnd = [&rng](int n) {
-        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
-        return (int)((rng >> 33) % (uint64_t)n);
-    };
-    for (int s = 0; s < kMaxMpl; ++s) {
-        const int K = meta[s];
-        if (K == 0) {   // mels without a single in-range bin still get their (floor-valued) output row
-            for (int l = 0; l < 32; ++l)
-                if (s * 32 + l < c.n_mels) meta[kMaxMpl + s * 32 + l] = sorted[s * 32 + l].mel;
-            continue;
-        }
-        struct Ent { int row; float w; };
-        std::vector<std::vector<Ent>> lanes(32);
-        std::vector<int> lane_mel(32, -1);
-        for (int l = 0; l < 32; ++l) {
-            const int r = s * 32 + l;
-            if (r >= c.n_mels) continue;
-            lane_mel[l] = sorted[r].mel;
-            for (auto& e : sorted[r].e) lanes[l].push_back({row_of_bin(e.first, R, C), (float)(e.second * 0.25)});
-        }
-        // plan 400 reads 24-byte rows with LDS.64 (conflicts per half-warp, rows mod 16); plan 512 reads 16-byte rows
-        // with LDS.128 (conflicts per quarter-warp, rows mod 8)
-        const int grp = N == 400 ? 16 : 8;
-        auto cost = [&]() {
-            int tot = 0;
-            for (int e = 0; e < K; ++e)
-                for (int hw = 0; hw < 32 / grp; ++hw) {
-                    int cnt[16] = {0}, mxc = 0;
-                    for (int l = grp * hw; l < grp * hw + grp; ++l)
-                        if (e < (int)lanes[l].size()) mxc = std::max(mxc, ++cnt[lanes[l][e].row & (grp - 1)]);
-                    tot += mxc;
-                }
-            return tot;
-        };
-        int best = cost();
-        for (int iter = 0; iter < 40000 && best > 2 * K; ++iter) {
-            const int kind = rnd(3), a = rnd(32), b = rnd(32);
-            if (kind == 0) {   // swap the mels of two lanes
-                if (a == b) continue;
-                std::swap(lanes[a], lanes[b]); std::swap(lane_mel[a], lane_mel[b]);
-                const int cst = cost();
-                if (cst <= best) best = cst; else { std::swap(lanes[a], lanes[b]); std::swap(lane_mel[a], lane_mel[b]); }
-            } else {           // swap two entries inside one lane (summation order is irrelevant at 1e-7)
-                if (lanes[a].size() < 2) continue;
-                const int i = rnd((int)lanes[a].size()), j = rnd((int)lanes[a].size());
-                if (i == j) continue;
-                std::swap(lanes[a][i], lanes[a][j]);
-                const int cst = cost();
-                if (cst <= best) best = cst; else std::swap(lanes[a][i], lanes[a][j]);
-            }
-        }
-        for (int l = 0; l < 32; ++l) {
-            meta[kMaxMpl + s * 32 + l] = lane_mel[l];
-            for (int e = 0; e < K; ++e) {
-                float2 ent;
-                int off;
-                const int rowmul = N == 400 ? 3 : 1;   // float2 index of a 3-FFT row / float4 index of a 2-FFT row
-                if (e < (int)lanes[l].size()) { ent.x = lanes[l][e].w; off = rowmul * lanes[l][e].row; }
-                else {   // padding: zero weight, pointed at a row whose bank group nobody in this lane group uses
-                    int cnt[16] = {0};
-                    for (int l2 = grp * (l / grp); l2 < grp * (l / grp) + grp; ++l2)
-                        if (e < (int)lanes[l2].size()) cnt[lanes[l2][e].row & (grp - 1)]++;
-                    int pick = 0;
-                    for (int r = 1; r < grp; ++r) if (cnt[r] < cnt[pick]) pick = r;
-                    lanes[l].push_back({pick, 0.f});
-                    ent.x = 0.f; off = rowmul * pick;
-                }
-                std::memcpy(&ent.y, &off, sizeof(int));
-                proj[(size_t)(eoff + e) * 32 + l] = ent;
-            }
-        }
-        h->proj_wavefront_cost += best;
-        eoff += K;
-    }
-    h->proj_ktot = std::max(ktot, 1);
-    h->kspec = 0;
     }
     MS_CUDA(cudaMalloc(&h->d_window, sizeof(float) * win.size()));
     MS_CUDA(cudaMalloc(&h->d_twiddle, sizeof(float4) * tw.size()));
@@ -581,6 +477,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.bulk_in = aligned_in ? 1 : 0;
     p.bulk_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) &&
                  (p.out_clip_stride % 4 == 0);
+    p.mm_aligned8 = (layout == MELSPEC_LAYOUT_MEL_MAJOR) && ((uintptr_t)d_out % 8 == 0) && (p.out_clip_stride % 2 == 0) && (row_stride % 2 == 0);
     p.window = reinterpret_cast<const float2*>(h->d_window); p.twiddle = h->d_twiddle; p.rot10 = h->d_rot10;
     p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
@@ -908,7 +805,7 @@ int32_t melspec_dequantize_tga_device(melspec_handle* h, const uint8_t* d_tga, i
     if (!tga_stride) tga_stride = sz;
     if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
     MS_CUDA(cudaSetDevice(h->device));
-    const int nblk = (int)std::min<int64_t>(1024, (n + 1023) / 1024);
+    const int nblk = (int)std::min<int64_t>(1024, (n + 8191) / 8192);   // 256 threads x 8 quads of 4 pixels
     melspec::melspec_dequantize_kernel<<<dim3(nblk, (unsigned)n_imgs), 256, 0, (cudaStream_t)stream>>>(d_tga, tga_stride, n, d_img, img_stride);
     MS_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -962,7 +859,7 @@ int32_t melspec_dequantize_tga_host(melspec_handle* h, const uint8_t* h_tga, int
     int32_t rc = ensure_fmt(h, (size_t)n * 4, (size_t)tga_bytes + 8);
     if (rc) return rc;
     MS_CUDA(cudaMemcpy(h->d_fmt_tga, h_tga, (size_t)tga_bytes, cudaMemcpyHostToDevice));
-    const int nblk = (int)std::min<int64_t>(1024, (n + 1023) / 1024);
+    const int nblk = (int)std::min<int64_t>(1024, (n + 8191) / 8192);   // 256 threads x 8 quads of 4 pixels
     melspec::melspec_dequantize_kernel<<<dim3(nblk, 1), 256>>>(h->d_fmt_tga, tga_bytes, n, h->d_fmt_img, n);
     MS_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -62,6 +62,7 @@ struct KParams {
     int frame_offset;        // NeMo: first sample of frame 0 relative to the clip (-200 when centred, +56 otherwise)
     float log_add;           // NeMo: log_zero_guard added to the energy before ln()
     int out_row_stride;      // mel-major output: floats between mel rows (NeMo: padded frame count)
+    int mm_aligned8;         // mel-major output: every mel row of every tile starts on an 8-byte boundary
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
@@ -622,7 +623,48 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
                 __syncwarp();
             }
-        } else {   // mel-major: out[clip][mel][frame]
+        } else if (nvalid == FPW) {
+            // mel-major / interleave_frames layout, full tile: a mel row receives 6 consecutive floats (24 bytes).  Stage the
+            // tile as [mel][3 x float2]; every lane then stores whole rows with the widest stores the row's address allows
+            // (3 x STG.64, or 4 + 8 + 8 + 4 bytes when the row starts on an odd word: odd frame counts / row strides), instead of
+            // 18 instructions that each scatter 4 bytes into 32 different rows.
+            float2* st2 = reinterpret_cast<float2*>(s_stage);
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const float v0 = p.normalize ? fmaf(fmaxf(lg[s][2 * u], mx[2 * u]), 0.25f, 1.0f) : lg[s][2 * u];
+                        const float v1 = p.normalize ? fmaf(fmaxf(lg[s][2 * u + 1], mx[2 * u + 1]), 0.25f, 1.0f) : lg[s][2 * u + 1];
+                        st2[3 * mel + u] = make_float2(v0, v1);
+                    }
+                }
+            }
+            __syncwarp();
+            float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
+            if (p.mm_aligned8) {   // all rows 8-byte aligned: walk the staged tile linearly, three lanes per row, one STG.64 each
+                int row = lane / 3, u = lane - 3 * row;
+                for (int i = lane; i < 3 * p.n_mels; i += 32) {
+                    *reinterpret_cast<float2*>(dst + (long long)row * p.out_row_stride + 2 * u) = st2[i];
+                    row += 10; u += 2;
+                    if (u >= 3) { u -= 3; ++row; }
+                }
+            } else
+            for (int row = lane; row < p.n_mels; row += 32) {
+                const float2 a = st2[3 * row], b = st2[3 * row + 1], c = st2[3 * row + 2];
+                float* r = dst + (long long)row * p.out_row_stride;
+                if ((reinterpret_cast<uintptr_t>(r) & 7) == 0) {
+                    reinterpret_cast<float2*>(r)[0] = a; reinterpret_cast<float2*>(r)[1] = b; reinterpret_cast<float2*>(r)[2] = c;
+                } else {
+                    r[0] = a.x;
+                    *reinterpret_cast<float2*>(r + 1) = make_float2(a.y, b.x);
+                    *reinterpret_cast<float2*>(r + 3) = make_float2(b.y, c.x);
+                    r[5] = c.y;
+                }
+            }
+            __syncwarp();
+        } else {   // mel-major: out[clip][mel][frame], ragged tile or unaligned rows
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
@@ -714,7 +756,7 @@ constexpr int FPW = 4;
 constexpr int ZROWB = 144;                   // bytes per Z row: 16 complex + 16 B pad  (9 units: odd => conflict-free LDS.128)
 constexpr int ZSLABB = 32 * ZROWB + 64;      // 4672 B per FFT (292 units = 4 mod 8: the two FFTs of a quarter-warp never collide)
 constexpr int ZBYTES = 2 * ZSLABB;           // 9344 per warp
-constexpr int PBYTES = 256 * 16;             // power rows 16*j + t, one float4 (A0, B0, A1, B1) per row
+constexpr int PBYTES = 258 * 16;             // power rows in natural bin order 0..256, one float4 (A0, B0, A1, B1) per row
 constexpr int STAGE_MAX = ZBYTES - PBYTES;
 constexpr int CHUNK = 320;
 constexpr int PAD = 16;
@@ -738,7 +780,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     const int c = lane & 15, g1 = lane >> 4;   // step-1 role
     const int t = lane >> 1, g3 = lane & 1;    // step-3 role
 
-    const float2* s_proj = reinterpret_cast<const float2*>(smem + p.smem_proj);
+    const float* s_projw = reinterpret_cast<const float*>(smem + p.smem_proj);
     const int* s_meta = reinterpret_cast<const int*>(smem + p.smem_meta);
     unsigned char* s_warp = smem + p.smem_warp0 + warp * p.smem_warp_stride;
     float4* s_p4 = reinterpret_cast<float4*>(s_warp);
@@ -750,8 +792,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
     for (int i = threadIdx.x; i < 512; i += NWARPS * 32) reinterpret_cast<float*>(smem + p.smem_win)[i] = reinterpret_cast<const float*>(p.window)[i];
     for (int i = threadIdx.x; i < 128; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
-    for (int i = threadIdx.x; i < (p.proj_ktot + 1) * 32; i += NWARPS * 32) reinterpret_cast<float2*>(smem + p.smem_proj)[i] = p.proj[i];
-    for (int i = threadIdx.x; i < kMaxMpl + kMaxMpl * 32; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
+    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32)   // weights, [entry][lane]
+        reinterpret_cast<float*>(smem + p.smem_proj)[i] = reinterpret_cast<const float*>(p.proj)[i];
+    for (int i = threadIdx.x; i < kMetaInts; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -943,14 +986,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         __syncwarp();
         dft16x2(XR, XI);   // .x = X; .y = D with the row's spectrum Y[m] = D[(m + 1) % 16]
         {
+            // Powers go to natural bin order: slot j < 8 is bin 32j + t (worker 0: 32j + 16), slot j >= 8 is the mirror bin
+            // 32(16-j) - t; row = float4 (A0, B0, A1, B1), this lane fills the float2 of its FFT g3.  The 32 lanes of a
+            // store cover 32 consecutive float2 (conflict-free).
             const bool t0 = (t == 0);
+            float2* const p_lo = s_p2 + 2 * (t0 ? 16 : t) + g3;
+            float2* const p_hi = s_p2 - 2 * t + g3;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float ur = XR[j].x, ui = XI[j].x, vr = XR[(16 - j) % 16].y, vi = XI[(16 - j) % 16].y;
                 if (j < 8) { ur = t0 ? XR[j + 1].y : ur; ui = t0 ? XI[j + 1].y : ui; }
                 else       { vr = t0 ? XR[16 - j].x : vr; vi = t0 ? XI[16 - j].x : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
-                s_p2[32 * j + lane] = make_float2(fmaf(sr, sr, di * di), fmaf(si, si, dr * dr));   // row 16j+t, FFT g3
+                const float2 pw = make_float2(fmaf(sr, sr, di * di), fmaf(si, si, dr * dr));
+                if (j < 8) p_lo[64 * j] = pw;
+                else       p_hi[64 * (16 - j)] = pw;
             }
         }
         __syncwarp();
@@ -961,21 +1011,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
         {
-            int eoff = 0;
+            // windowed projection (see melspec400_kernel): the lane's K_s entries are consecutive power rows from its window
+            // start, so the loads do not depend on the table and pipeline freely; weights come from [entry][lane]
+            const float* wt = s_projw + lane;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int K = s_meta[s];
-                float acc[FPW];
-#pragma unroll
-                for (int q = 0; q < FPW; ++q) acc[q] = 0.f;
-#pragma unroll 2
+                const float4* pr = s_p4 + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
+                f2 acc01 = make_float2(0.f, 0.f), acc23 = acc01;
+#pragma unroll 4
                 for (int e = 0; e < K; ++e) {
-                    const float2 ent = s_proj[(eoff + e) * 32 + lane];
-                    const float4 pw = s_p4[__float_as_int(ent.y)];
-                    acc[0] = fmaf(ent.x, pw.x, acc[0]); acc[1] = fmaf(ent.x, pw.y, acc[1]);
-                    acc[2] = fmaf(ent.x, pw.z, acc[2]); acc[3] = fmaf(ent.x, pw.w, acc[3]);
+                    const float w = wt[e * 32];
+                    const float4 pw = pr[e];
+                    const f2 ww = make_float2(w, w);
+                    acc01 = fma2(ww, make_float2(pw.x, pw.y), acc01);
+                    acc23 = fma2(ww, make_float2(pw.z, pw.w), acc23);
                 }
-                eoff += K;
+                wt += K * 32;
+                const float acc[FPW] = {acc01.x, acc01.y, acc23.x, acc23.y};
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
                     const float e = fmaxf(acc[q], p.floor_val) + p.log_add;
@@ -1012,6 +1065,39 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
                 __syncwarp();
             }
+        } else if (nvalid == FPW) {
+            // mel-major / feature-major layout, full tile: a mel row receives 4 consecutive floats (16 bytes): stage the
+            // tile as [mel] x float4 and store whole rows with the widest stores the row's address allows (odd frame counts
+            // make the rows start on odd words: 4 + 8 + 4 bytes)
+            float4* st4 = reinterpret_cast<float4*>(s_stage);
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) {
+                    float v[FPW];
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q) v[q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                    st4[mel] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+            __syncwarp();
+            float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
+            for (int mel = lane; mel < p.n_mels; mel += 32) {
+                const float4 v = st4[mel];
+                float* r = dst + (long long)mel * p.out_row_stride;
+                const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(r) & 15);
+                if (al == 0) {
+                    *reinterpret_cast<float4*>(r) = v;
+                } else if ((al & 7) == 0) {
+                    *reinterpret_cast<float2*>(r) = make_float2(v.x, v.y);
+                    *reinterpret_cast<float2*>(r + 2) = make_float2(v.z, v.w);
+                } else {
+                    r[0] = v.x;
+                    *reinterpret_cast<float2*>(r + 1) = make_float2(v.y, v.z);
+                    r[3] = v.w;
+                }
+            }
+            __syncwarp();
         } else {
             float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
 #pragma unroll
@@ -1214,16 +1300,40 @@ __global__ void __launch_bounds__(256) melspec_quantize_kernel(const float* img,
 }
 
 // parse_tga_8bit + dequantize (src/quant.rs:66-88,155-165): value as f32 * ((max - min) / 255.0) + min, two roundings.
+// One thread = four consecutive output floats (one float4 store when the image row is 16-byte aligned); their four bytes
+// come from two aligned 32-bit loads joined by a funnel shift (the pixel data start at byte 26 of the TGA).
 __global__ void __launch_bounds__(256) melspec_dequantize_kernel(const unsigned char* tga, long long tga_stride, long long n, float* img,
                                                                  long long img_stride) {
     const unsigned char* src = tga + (long long)blockIdx.y * tga_stride;
     float* dst = img + (long long)blockIdx.y * img_stride;
-    unsigned a = 0, b = 0;
-    for (int i = 0; i < 4; ++i) { a |= (unsigned)src[18 + i] << (8 * i); b |= (unsigned)src[22 + i] << (8 * i); }
-    const float mn = __uint_as_float(a), mx = __uint_as_float(b);
+    __shared__ float s_rng[2];
+    if (threadIdx.x < 2) {   // f32 min (bytes 18..21) and max (22..25) of the ID field, little-endian, any alignment
+        unsigned v = 0;
+        for (int i = 0; i < 4; ++i) v |= (unsigned)src[18 + 4 * threadIdx.x + i] << (8 * i);
+        s_rng[threadIdx.x] = __uint_as_float(v);
+    }
+    __syncthreads();
+    const float mn = s_rng[0], mx = s_rng[1];
     const float scale = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
-        dst[i] = __fadd_rn(__fmul_rn((float)src[kTgaHeader + i], scale), mn);
+    const unsigned char* px = src + kTgaHeader;
+    const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const long long nquads = vec ? n / 4 : 0;
+    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < nquads; k += (long long)gridDim.x * 256) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(px + 4 * k);
+        const unsigned* w = reinterpret_cast<const unsigned*>(addr & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(addr & 3) * 8;
+        // the second word is only dereferenced when the quad really straddles it (never reads past the last pixel's word)
+        const unsigned lo = __ldg(w), hi = sh ? __ldg(w + 1) : 0u;
+        const unsigned q = __funnelshift_r(lo, hi, sh);
+        float4 v;
+        v.x = __fadd_rn(__fmul_rn((float)(q & 255u), scale), mn);
+        v.y = __fadd_rn(__fmul_rn((float)((q >> 8) & 255u), scale), mn);
+        v.z = __fadd_rn(__fmul_rn((float)((q >> 16) & 255u), scale), mn);
+        v.w = __fadd_rn(__fmul_rn((float)(q >> 24), scale), mn);
+        reinterpret_cast<float4*>(dst)[k] = v;
+    }
+    for (long long i = 4 * nquads + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        dst[i] = __fadd_rn(__fmul_rn((float)px[i], scale), mn);
 }
 
 // ================================================================================================ VAD over the mel image
