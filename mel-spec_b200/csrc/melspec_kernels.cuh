@@ -821,9 +821,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const long long endl = (long long)p.n_samples - t0;
             const int hi = endl < need ? (endl < lo ? lo : (int)endl) : need;
             const float* tsrc = p.pcm + (long long)clip * p.clip_stride + t0;
-            if (lo > 0 || hi < need)
+            if (lo > 0 || hi < need) {   // warp-uniform
                 for (int i = lane; i < need; i += 32)
                     if (i < lo || i >= hi) s_pcm[i + PAD * (i / CHUNK)] = 0.f;
+                __syncwarp();   // the zeros are read by other lanes; the mbarrier below only orders the TMA bytes
+            }
             if (p.bulk_in && hi > lo) {
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)(hi - lo) * 4u);
@@ -1322,9 +1324,15 @@ __global__ void __launch_bounds__(256) melspec_dequantize_kernel(const unsigned 
         const uintptr_t addr = reinterpret_cast<uintptr_t>(px + 4 * k);
         const unsigned* w = reinterpret_cast<const unsigned*>(addr & ~(uintptr_t)3);
         const unsigned sh = (unsigned)(addr & 3) * 8;
-        // the second word is only dereferenced when the quad really straddles it (never reads past the last pixel's word)
-        const unsigned lo = __ldg(w), hi = sh ? __ldg(w + 1) : 0u;
-        const unsigned q = __funnelshift_r(lo, hi, sh);
+        // the second word is only dereferenced when the quad really straddles it
+        unsigned q;
+        if (sh && k == nquads - 1) {   // last quad: its second word may end past the image, read the four bytes one by one
+            const unsigned char* b = px + 4 * k;
+            q = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+        } else {
+            const unsigned lo = __ldg(w), hi = sh ? __ldg(w + 1) : 0u;
+            q = __funnelshift_r(lo, hi, sh);
+        }
         float4 v;
         v.x = __fadd_rn(__fmul_rn((float)(q & 255u), scale), mn);
         v.y = __fadd_rn(__fmul_rn((float)((q >> 8) & 255u), scale), mn);
