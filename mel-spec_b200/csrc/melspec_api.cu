@@ -493,6 +493,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.smem_rot = (int)off; off = up(off + 512, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * kMetaInts, 128);
+    p.smem_cmn = (int)off;
+    if (h->plan == 512) off = up(off + sizeof(float) * 128 * (12 + 1), 128);   // fused CMN: column sums per warp + means
     p.smem_warp0 = (int)off;
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
     static_assert(p512::FPW * 32 * kMaxMpl * 4 <= p512::STAGE_MAX, "output rows must fit behind the power rows");
@@ -508,10 +510,19 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     }
     p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
     const int nw = warps_per_cta(h->plan);
+    // Kaldi CMN inside the fused kernel: one CTA works through whole clips (see melspec512_kernel).  Needs enough clips to
+    // fill the GPU, enough tiles per clip for every warp, and float4-addressable rows; otherwise CMN stays a second kernel.
+    static const bool cmn_fuse_enabled = [] { const char* e = std::getenv("MELSPEC_CMN_FUSED"); return !(e && e[0] == '0'); }();
+    p.n_clips = (int)n_clips;
+    p.vec_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) && (p.out_clip_stride % 4 == 0);
+    const bool fused_cmn = cmn_fuse_enabled && kaldi && c.cmn && h->plan == 512 && layout == MELSPEC_LAYOUT_FRAME_MAJOR && p.vec_out &&
+                           n_clips >= h->num_sms && p.wtiles_per_clip >= 2 * nw && c.n_mels <= 128;
+    p.cmn_fused = fused_cmn ? 1 : 0;
+    if (fused_cmn) p.bulk_out = 0;   // plain stores: the CTA re-reads its own rows after a block barrier
     off += (size_t)p.smem_warp_stride * nw;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;
-    const int grid = (int)std::min<int64_t>(n_tiles, h->num_sms);
+    const int grid = fused_cmn ? h->num_sms : (int)std::min<int64_t>(n_tiles, h->num_sms);
     int32_t rc;
     const bool m3 = h->mpl <= 3;
     if (h->plan == 400) {
@@ -549,7 +560,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         MS_CUDA(cudaGetLastError());
         h->launches += 1;
     }
-    if (kaldi && c.cmn) {   // CMN couples all frames of a clip: second, small kernel over rows that are still in L2
+    if (kaldi && c.cmn && !fused_cmn) {   // CMN couples all frames of a clip: second kernel (short clips / small batches)
         melspec_cmn_kernel<<<(unsigned)n_clips, 512, 0, st>>>(d_out, p.out_clip_stride, p.frames_per_clip, c.n_mels, d_lens,
                                                              p.n_samples, c.frame_len, c.hop);
         MS_CUDA(cudaGetLastError());

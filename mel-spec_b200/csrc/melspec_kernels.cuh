@@ -63,6 +63,10 @@ struct KParams {
     float log_add;           // NeMo: log_zero_guard added to the energy before ln()
     int out_row_stride;      // mel-major output: floats between mel rows (NeMo: padded frame count)
     int mm_aligned8;         // mel-major output: every mel row of every tile starts on an 8-byte boundary
+    int cmn_fused;           // Kaldi: CMN inside the fused kernel (one CTA per clip at a time), see melspec512_kernel
+    int vec_out;             // frame-major output rows are 16-byte aligned (float4 stores when TMA stores are not used)
+    int n_clips;
+    int smem_cmn;            // [NWARPS][128] column sums + [128] means (floats)
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
 };
@@ -855,11 +859,28 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         }
     };
 
+    // Tile order.  Default: warp-strided over all tiles of the launch.  Fused CMN (Kaldi, cmn_fused): the CTA works on one
+    // clip at a time (clips blockIdx.x, + gridDim.x, ...; tiles warp, + NWARPS, ... inside the clip), so that when the clip
+    // is finished its rows are still in L2: the CTA then subtracts the per-mel mean in place (src/fbank.rs:226-233) instead
+    // of a second kernel making two more trips to HBM.  Column sums: per lane in registers (fixed order), per warp in
+    // shared memory, across warps in a fixed order -> deterministic.
+    const bool fused = KALDI && p.cmn_fused;
     const int wstride = gridDim.x * NWARPS;
-    int wt = blockIdx.x * NWARPS + warp;
+    int wt = fused ? blockIdx.x * p.wtiles_per_clip + warp : blockIdx.x * NWARPS + warp;
+    int tile_in_clip = warp;                                  // fused mode only
+    auto next_tile = [&](int cur, int& tin) -> int {          // fused: advance (clip, tile); returns the next global tile id
+        if (!fused) return cur + wstride;
+        if (tin + NWARPS < p.wtiles_per_clip) { tin += NWARPS; return cur + NWARPS; }
+        const int clip_now = cur / p.wtiles_per_clip;
+        tin = warp;
+        return (clip_now + (int)gridDim.x) * p.wtiles_per_clip + warp;
+    };
+    float csum[MPL];
+#pragma unroll
+    for (int s = 0; s < MPL; ++s) csum[s] = 0.f;
     if (wt < p.n_wtiles) issue_load(wt);
 
-    for (int it = 0; wt < p.n_wtiles; wt += wstride, ++it) {
+    for (int it = 0; wt < p.n_wtiles; ++it) {
         const int clip = wt / p.wtiles_per_clip;
         const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
         int nfr = p.frames_per_clip;
@@ -951,8 +972,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             }
         }
         __syncwarp();
-        if (wt + wstride < p.n_wtiles) issue_load(wt + wstride);
-        if (nvalid == 0) continue;
+        int tin_next = tile_in_clip;
+        const int wt_next = next_tile(wt, tin_next);
+        if (wt_next < p.n_wtiles) issue_load(wt_next);
+        if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
 
         float ar[32], ai[32];
         dft32_packed(er, ei, ar, ai);
@@ -1062,10 +1085,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
                     bulk_commit();
                 }
+            } else if (p.vec_out) {
+                __syncwarp();
+                for (int i = lane; i < nout / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_stage)[i];
+                __syncwarp();
             } else {
                 __syncwarp();
                 for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
                 __syncwarp();
+            }
+            if (fused) {
+#pragma unroll
+                for (int s = 0; s < MPL; ++s)
+#pragma unroll
+                    for (int q = 0; q < FPW; ++q)
+                        if (q < nvalid) csum[s] += lg[s][q];
             }
         } else if (nvalid == FPW) {
             // mel-major / feature-major layout, full tile: a mel row receives 4 consecutive floats (16 bytes): stage the
@@ -1114,6 +1148,50 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             }
             __syncwarp();
         }
+        }   // nvalid != 0
+
+        // ------------------------------------------------------------------ fused CMN: end of this warp's share of the clip
+        if (fused && (wt_next >= p.n_wtiles || wt_next / p.wtiles_per_clip != clip)) {
+            float* s_cs = reinterpret_cast<float*>(smem + p.smem_cmn);       // [NWARPS][128]
+            float* s_mean = s_cs + NWARPS * 128;                             // [128]
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) s_cs[warp * 128 + mel] = csum[s];
+                csum[s] = 0.f;
+            }
+            __syncthreads();   // every warp of the CTA finishes the same clip here (wtiles_per_clip >= NWARPS, host-checked)
+            if ((int)threadIdx.x < p.n_mels) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < NWARPS; ++w) sum += s_cs[w * 128 + threadIdx.x];
+                s_mean[threadIdx.x] = nfr > 0 ? sum / (float)nfr : 0.f;
+            }
+            __syncthreads();
+            // the clip's nfr x n_mels floats were written by this CTA's own (plain) stores a few microseconds ago: L2 hits
+            float* base = p.out + (long long)clip * p.out_clip_stride;
+            const int quads = p.n_mels / 4, total = nfr * quads;
+            const float4* mean4 = reinterpret_cast<const float4*>(s_mean);
+            // four independent L2 loads in flight per thread: the pass is latency-bound otherwise (one CTA per SM)
+            constexpr int NT = NWARPS * 32, UN = 4;
+            for (int i0 = threadIdx.x; i0 < total; i0 += NT * UN) {
+                float4 v[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+                    if (i0 + u * NT < total) v[u] = __ldcg(reinterpret_cast<const float4*>(base) + i0 + u * NT);
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + u * NT;
+                    if (i < total) {
+                        const float4 m = mean4[i % quads];
+                        v[u].x -= m.x; v[u].y -= m.y; v[u].z -= m.z; v[u].w -= m.w;
+                        reinterpret_cast<float4*>(base)[i] = v[u];
+                    }
+                }
+            }
+        }
+        wt = wt_next;
+        tile_in_clip = tin_next;
     }
     if (lane == 0) bulk_wait0();
 }

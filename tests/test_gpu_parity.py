@@ -326,6 +326,36 @@ def test_kaldi_batch_vs_oracle(m, torch):
     fb.close()
 
 
+def test_kaldi_fused_cmn_large_batch(m, torch):
+    """Batches with >= one clip per SM and >= 24 warp tiles per clip take the fused-CMN path of the plan-512 kernel (one CTA
+    per clip at a time, mean subtracted in place while the clip is in L2).  Checked against the oracle on a few clips, against
+    the un-normalised features minus their column means for every clip, for ragged per-clip lengths, and for determinism."""
+    n_clips, n = 300, 24000                                       # 148 frames = 37 tiles of 4 per clip
+    base = np.stack([o.synth_clip(i, n) for i in range(6)]).astype(np.float32)
+    rng = np.random.default_rng(3)
+    pcm = np.ascontiguousarray(base[rng.integers(0, 6, n_clips)] * rng.uniform(0.2, 1.0, (n_clips, 1)).astype(np.float32))
+    lens = rng.integers(300, n + 1, n_clips).astype(np.int32)
+    lens[:4] = n
+    lens[4] = 399                                                 # a clip with no frame at all
+    fb = m.Fbank(m.FbankConfig())
+    raw = m.Fbank(m.FbankConfig(apply_cmn=False))
+    got = _device_run(torch, fb, pcm, lens=lens.tolist())
+    again = _device_run(torch, fb, pcm, lens=lens.tolist())
+    plain = _device_run(torch, raw, pcm, lens=lens.tolist())
+    for i in range(n_clips):
+        f = 0 if lens[i] < 400 else (int(lens[i]) - 400) // 160 + 1
+        if f == 0:
+            assert np.isnan(got[i]).all()                         # untouched (the test buffer is NaN-filled)
+            continue
+        want = plain[i, :f] - plain[i, :f].mean(axis=0, dtype=np.float32)
+        assert np.abs(got[i, :f] - want).max() <= 2e-5, i
+        assert np.isnan(got[i, f:]).all()
+        assert np.array_equal(got[i, :f], again[i, :f])
+    for i in range(4):
+        _kaldi_check(got[i], o.kaldi_fbank(pcm[i]))
+    fb.close(); raw.close()
+
+
 # ------------------------------------------------------------------------------------------ long stream (BASELINE config 5 shape)
 def test_long_stream_chunked_equals_batch(m, torch):
     """10 minutes of audio through the streaming C ABI in 1 s pushes and in one large push: frame count follows the
