@@ -1,4 +1,6 @@
-"""Numpy model of the plan-400 kernel's index algebra (PFA DFT-20, 20x20 Cooley-Tukey, Z slot map,
+"""(The kernel now stores the powers in natural bin order, `b` below, not at `row = 10*j + t`; the (t, j) -> bin map and the
+rest of the algebra are unchanged.)
+Numpy model of the plan-400 kernel's index algebra (PFA DFT-20, 20x20 Cooley-Tukey, Z slot map,
 two-frames-per-complex-FFT untangle, P row map).  Development aid: validates the tables/permutations the
 CUDA kernel hard-codes.  Not used by the product or the tests' oracle."""
 import numpy as np
