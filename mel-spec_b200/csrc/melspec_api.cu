@@ -1077,7 +1077,13 @@ int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, mels
     s->max_chunk = max_chunk_samples;
     const Resolved& c = h->cfg;
     // a push is cut into pieces of <= 4 s of 16 kHz audio; piece k+1's H2D copy overlaps piece k's kernel and D2H copy
-    s->piece = std::min<int64_t>(max_chunk_samples, 1 << 16);
+    // (pieces of up to 2^22 samples = 4.4 min of 16 kHz audio: far below that a piece's kernel + copies are launch-latency bound, ~25 us each)
+    static const int64_t piece_cap = [] {
+        const char* e = std::getenv("MELSPEC_STREAM_PIECE");
+        const int64_t v = e ? std::atoll(e) : 0;
+        return v >= 1024 ? v : (int64_t)(1 << 22);
+    }();
+    s->piece = std::min<int64_t>(max_chunk_samples, piece_cap);
     s->cap = (s->piece + c.frame_len + c.hop + 8 + 3) / 4 * 4;
     s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;   // c = ceil(N/H)*H - N
     s->out_cap_frames = s->cap / c.hop + 2;
