@@ -317,7 +317,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))
     if world > 1:
