@@ -11,13 +11,16 @@
 // Thread organisation ("plan 400"): a warp owns 3 complex FFTs = 6 frames per pass; 10 lanes cooperate on one FFT
 // (lane = 10*g + t: t = worker 0..9, g = FFT 0..2; lanes 30,31 shadow lane 29).  N = 400 = 20 x 20:
 //   step 1  worker t transforms columns n2 = 2t, 2t+1 (elements x[20*n1 + n2]) with a 20-point DFT -> Y[n2][k1]
-//   exchange through the warp's private shared-memory slab Z[slot(k1)][n2][g]   (only __syncwarp, no CTA barrier)
+//   exchange through the warp's private shared-memory slab Z[slot(k1)][g][n2 pair]   (only __syncwarp, no CTA barrier)
 //   step 3  worker t owns rows k1 = t and 20-t (t = 0: rows 0 and 10): twiddle, 20-point DFT over n2 -> X[k1 + 20*k2].
-//           The twiddles W_400^(t*n2) live in registers; row 20-t uses their conjugates and a rotation of the DFT
+//           The twiddles W_400^(t*n2) come from a shared table (registers in the 8-warp build); row 20-t uses their
+//           conjugates and a rotation of the DFT
 //           outputs by one (W_400^((20-t)n2) = W_20^n2 * conj W_400^(t*n2)); row 10 is pre-rotated by W_40^(-n2) when
 //           it is written, which makes worker 0 (twiddle 1) follow exactly the same code.
 //   untangle: frame A = Re, frame B = Im of the packed input, |A[k]|^2 = |Z[k] + conj Z[N-k]|^2 / 4 (the 1/4 lives
 //   in the mel weights); both Z[k] and Z[N-k] sit in the same worker by construction (rows k1 and 20-k1).
+//   projection: powers are stored in natural bin order (one plane per FFT), a mel band is a run of consecutive rows, so a
+//   lane's entries are K consecutive rows from a host-chosen, conflict-free window start; weights-only table.
 // Bins 1..200 are produced (DC never is: every supported filterbank has a zero DC column; the host checks).
 #pragma once
 
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                               0.f, -0.15450849718747345f, -0.29389262614623651f, -0.40450849718747367f, -0.47552825814757677f,
                               -0.5f, -0.47552825814757682f, -0.40450849718747378f, -0.29389262614623668f, -0.15450849718747381f};
     const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + l30;
-    // with 8 warps per SM there are registers to spare: keep the worker's 10 twiddle quads resident (saves 10 LDS.128/pass)
+    // the 8-warp build (MELSPEC_WARPS=8; the default is 12) has registers to spare: it keeps the worker's 10 twiddle quads resident
     constexpr bool TW_IN_REGS = (NWARPS <= 8);
     float4 twreg[10];
     if (TW_IN_REGS) {
