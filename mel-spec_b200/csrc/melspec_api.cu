@@ -291,25 +291,89 @@ int32_t build_tables(melspec_handle* h) {
         // of the bin-ordered power rows; the table holds the weights only.  Plan 400 reads 8-byte rows of three planes with
         // LDS.64 (conflicts are per half-warp, rows mod 16), plan 512 reads 16-byte rows with LDS.128 (per quarter-warp, mod 8).
         const int grp = N == 400 ? 16 : 8, ngrp = 32 / grp, last_row = N / 2;
-        struct Piece { int mel, b0, len; };
+        // A piece is a run of consecutive bins of one mel band.  Long bands may be split into two pieces that sit in the same
+        // slot on two lanes and are added up with one warp shuffle per frame (plan 400): the slot lengths K_s are set by the
+        // longest piece, so halving the long bands shortens every lane's loop (Whisper-80: 14+4+2 -> 8+5+2 entries).
+        struct Piece { int mel, b0, len, emit, pair; };   // mel: weight row; emit: this lane stores the mel; pair: id or -1
+        // Measured on B200 (profiles/README.md): 23 fewer shared-memory wavefronts per pass, but the 12 shuffles and their
+        // latency cost more than that (0.4245 -> 0.4330 ms), so splitting is opt-in (MELSPEC_SPLIT=1) and off by default.
+        static const bool split_enabled = [] { const char* e = std::getenv("MELSPEC_SPLIT"); return e && e[0] == '1'; }();
+        const int capacity = 32 * h->mpl;
         std::vector<Piece> pcs;
-        for (int m = 0; m < c.n_mels; ++m) {
-            Piece pc{m, 1, 0};
-            if (!bands[m].e.empty()) { pc.b0 = bands[m].e.front().first; pc.len = bands[m].e.back().first - pc.b0 + 1; }
-            pcs.push_back(pc);
+        int K[kMaxMpl] = {0, 0, 0, 0}, EX[kMaxMpl] = {0, 0, 0, 0}, ktot = 0;
+        auto build = [&](int L, std::vector<Piece>& out, int (&Kc)[kMaxMpl], int (&Ex)[kMaxMpl]) -> int {
+            struct Unit { Piece a, b; int n, key; };
+            std::vector<Unit> units;
+            int npieces = 0, pid = 0;
+            for (int m = 0; m < c.n_mels; ++m) {
+                Piece pc{m, 1, 0, 1, -1};
+                if (!bands[m].e.empty()) { pc.b0 = bands[m].e.front().first; pc.len = bands[m].e.back().first - pc.b0 + 1; }
+                if (L > 0 && pc.len > L) {
+                    const int hlen = (pc.len + 1) / 2;
+                    Piece a{m, pc.b0, hlen, 1, pid}, b2{m, pc.b0 + hlen, pc.len - hlen, 0, pid};
+                    ++pid;
+                    units.push_back(Unit{a, b2, 2, hlen});
+                    npieces += 2;
+                } else {
+                    units.push_back(Unit{pc, pc, 1, pc.len});
+                    npieces += 1;
+                }
+            }
+            if (npieces > capacity) return -1;
+            std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.key > y.key; });
+            std::vector<std::vector<Piece>> slots(h->mpl);
+            for (const Unit& u : units) {
+                bool placed = false;
+                for (int sl = 0; sl < h->mpl && !placed; ++sl)
+                    if ((int)slots[sl].size() + u.n <= 32) {
+                        slots[sl].push_back(u.a);
+                        if (u.n == 2) slots[sl].push_back(u.b);
+                        placed = true;
+                    }
+                if (!placed) return -1;
+            }
+            out.clear();
+            int tot = 0;
+            for (int sl = 0; sl < kMaxMpl; ++sl) { Kc[sl] = 0; Ex[sl] = 0; }
+            for (int sl = 0; sl < h->mpl; ++sl) {
+                for (const Piece& pc : slots[sl]) { Kc[sl] = std::max(Kc[sl], pc.len); Ex[sl] |= pc.pair >= 0; }
+                while ((int)slots[sl].size() < 32) slots[sl].push_back(Piece{-1, 1, 0, 0, -1});   // idle lanes
+                out.insert(out.end(), slots[sl].begin(), slots[sl].end());
+                tot += Kc[sl];
+            }
+            return tot;
+        };
+        {
+            int best = build(0, pcs, K, EX), bestL = 0;
+            if (N == 400 && split_enabled) {
+                int maxlen = 0;
+                for (int m = 0; m < c.n_mels; ++m)
+                    if (!bands[m].e.empty()) maxlen = std::max(maxlen, bands[m].e.back().first - bands[m].e.front().first + 1);
+                for (int L = maxlen - 1; L >= 3; --L) {
+                    std::vector<Piece> t;
+                    int Kt[kMaxMpl], Et[kMaxMpl];
+                    const int tot = build(L, t, Kt, Et);
+                    if (tot < 0) continue;
+                    int nex = 0;
+                    for (int sl = 0; sl < kMaxMpl; ++sl) nex += Et[sl];
+                    if (tot + nex < best) { best = tot + nex; bestL = L; }   // an exchange costs about one entry
+                }
+                if (bestL) build(bestL, pcs, K, EX);
+            }
+            ktot = 0;
+            for (int sl = 0; sl < h->mpl; ++sl) { ktot += K[sl]; meta[sl] = K[sl] | (EX[sl] << 16); }
+            for (int sl = h->mpl; sl < kMaxMpl; ++sl) meta[sl] = 0;
         }
-        std::stable_sort(pcs.begin(), pcs.end(), [](const Piece& a, const Piece& b) { return a.len > b.len; });
-        while ((int)pcs.size() < 32 * h->mpl) pcs.push_back(Piece{-1, 1, 0});   // idle lanes of the last slot
-        int K[kMaxMpl] = {0, 0, 0, 0}, ktot = 0;
-        for (int s = 0; s < h->mpl; ++s) { K[s] = pcs[(size_t)32 * s].len; ktot += K[s]; meta[s] = K[s]; }
-        for (int s = h->mpl; s < kMaxMpl; ++s) meta[s] = 0;
         // (1) The output rows are staged with one 32-bit store per (slot, frame): conflict-free when the 32 mels of a slot
-        // differ mod 32.  Pieces may change slots as long as they still fit (len <= K of the new slot).
+        // differ mod 32.  Unsplit pieces may change slots as long as they still fit (len <= K of the new slot).
         auto stage_cost = [&]() {
             int tot = 0;
             for (int s = 0; s < h->mpl; ++s) {
                 int cnt[32] = {0};
-                for (int l = 0; l < 32; ++l) if (pcs[(size_t)32 * s + l].mel >= 0) tot += cnt[pcs[(size_t)32 * s + l].mel & 31]++;
+                for (int l = 0; l < 32; ++l) {
+                    const Piece& pc = pcs[(size_t)32 * s + l];
+                    if (pc.mel >= 0 && pc.emit) tot += cnt[pc.mel & 31]++;
+                }
             }
             return tot;
         };
@@ -321,7 +385,7 @@ int32_t build_tables(melspec_handle* h) {
         int sc = stage_cost();
         for (int iter = 0; iter < 20000 && sc > 0; ++iter) {
             const int a = rnd(32 * h->mpl), b = rnd(32 * h->mpl);
-            if (a / 32 == b / 32 || pcs[a].len > K[b / 32] || pcs[b].len > K[a / 32]) continue;
+            if (a / 32 == b / 32 || pcs[a].len > K[b / 32] || pcs[b].len > K[a / 32] || pcs[a].pair >= 0 || pcs[b].pair >= 0) continue;
             std::swap(pcs[a], pcs[b]);
             const int nc = stage_cost();
             if (nc <= sc) sc = nc; else std::swap(pcs[a], pcs[b]);
@@ -382,9 +446,17 @@ int32_t build_tables(melspec_handle* h) {
                 lane_piece[l] = i; lane_start[l] = lo[i];
                 h->proj_wavefront_cost += 3 * Ks;
             }
+            for (int l = 0; l < 32; ++l) {   // partner lane of a split band's piece (own lane otherwise)
+                const Piece& pc = pcs[(size_t)32 * s + lane_piece[l]];
+                int partner = l;
+                if (pc.pair >= 0)
+                    for (int l2 = 0; l2 < 32; ++l2)
+                        if (l2 != l && pcs[(size_t)32 * s + lane_piece[l2]].pair == pc.pair) partner = l2;
+                meta[kMaxMpl + 2 * kMaxMpl * 32 + s * 32 + l] = partner;
+            }
             for (int l = 0; l < 32; ++l) {
                 const Piece& pc = pcs[(size_t)32 * s + lane_piece[l]];
-                meta[kMaxMpl + s * 32 + l] = pc.mel;
+                meta[kMaxMpl + s * 32 + l] = pc.emit ? pc.mel : -1;
                 const int plane_unit = lane_start[l];
                 meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = plane_unit;
                 for (int e = 0; e < Ks; ++e) {
@@ -400,9 +472,13 @@ int32_t build_tables(melspec_handle* h) {
             eoff += Ks;
         }
         for (int s = h->mpl; s < kMaxMpl; ++s)
-            for (int l = 0; l < 32; ++l) meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = 1;
+            for (int l = 0; l < 32; ++l) { meta[kMaxMpl + kMaxMpl * 32 + s * 32 + l] = 1; meta[kMaxMpl + 2 * kMaxMpl * 32 + s * 32 + l] = l; }
         h->proj_ktot = ktot4;
-        h->kspec = (N == 400 && h->mpl == 3 && K[0] == 14 && K[1] == 4 && K[2] == 2) ? 1 : 0;
+        h->kspec = 0;
+        if (N == 400 && h->mpl == 3) {
+            if (K[0] == 14 && K[1] == 4 && K[2] == 2 && !EX[0] && !EX[1] && !EX[2]) h->kspec = 1;
+            if (K[0] == 8 && K[1] == 5 && K[2] == 2 && EX[0] && EX[1] && !EX[2]) h->kspec = 2;
+        }
         proj.resize(wtab.size() / 2);
         std::memcpy(proj.data(), wtab.data(), wtab.size() * sizeof(float));
     }
@@ -527,7 +603,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const bool m3 = h->mpl <= 3;
     if (h->plan == 400) {
 #define MS_DISPATCH(NW)                                                                                             \
-    (h->kspec == 1 && hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 1>, p, grid, NW * 32, off, st)           \
+    (h->kspec == 2 && hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 2>, p, grid, NW * 32, off, st)           \
+     : h->kspec == 1 && hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 1>, p, grid, NW * 32, off, st)         \
      : m3 ? (hop160 ? launch_kernel(melspec400_kernel<NW, 3, true, 0>, p, grid, NW * 32, off, st)                    \
                     : launch_kernel(melspec400_kernel<NW, 3, false, 0>, p, grid, NW * 32, off, st))                   \
           : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true, 0>, p, grid, NW * 32, off, st)                    \

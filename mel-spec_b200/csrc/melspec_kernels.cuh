@@ -54,8 +54,9 @@ struct KParams {
     const float2* rot10;     // [20]  W_40^(-c): row 10 is pre-rotated on the write side so worker 0 fits the same scheme
     const float2* proj;      // plan 512: [proj_ktot][32] (weight, __int_as_float(row))
                              // plan 400: floats, [proj_ktot4][32] weights (entry-major) then [proj_ktot4/4][32][4] (lane-major quads)
-    const int* proj_meta;    // [kMaxMpl] K_s, then [kMaxMpl][32] mel index or -1, then (plan 400) [kMaxMpl][32] first bin of the
-                             // lane's window (the K_s consecutive power rows its entries multiply)
+    const int* proj_meta;    // [kMaxMpl] K_s | exchange flag << 16, then [kMaxMpl][32] mel index or -1, then [kMaxMpl][32] first bin
+                             // of the lane's window (the K_s consecutive power rows its entries multiply), then [kMaxMpl][32] the
+                             // lane holding the other half of a split band (own lane if none)
     int proj_ktot;           // plan 400: entries rounded up to a multiple of 4
     float floor_val;         // 1e-10 (Whisper) — floor applied to the *unscaled* energy
     float log_mul;           // log10(2) (Whisper)
@@ -75,7 +76,7 @@ struct KParams {
 };
 
 constexpr int kMaxMpl = 4;
-constexpr int kMetaInts = kMaxMpl + 2 * kMaxMpl * 32;
+constexpr int kMetaInts = kMaxMpl + 3 * kMaxMpl * 32;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -325,7 +326,9 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 10 ? r : 30 -
 // of the warp's next tile is issued right after that and lands during the rest of the pass.
 // KSPEC selects a compile-time projection schedule: 0 = entry counts per slot read from the table (any filterbank),
 // 1 = the Whisper 80-mel / fft-400 bank, whose slots hold 14, 4 and 2 entries (loops fully unrolled: no loop control,
-// no register rotation, all table and power loads of a slot in flight together).  The host picks it by comparing counts.
+// no register rotation, all table and power loads of a slot in flight together), 2 = the same bank with its 13 longest
+// bands split over two lanes (8, 5 and 2 entries, halves added with a warp shuffle in slots 0 and 1).  The host picks it by
+// comparing counts.
 template <int NWARPS, int MPL, bool HOP160, int KSPEC>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParams p) {
     using namespace p400;
@@ -555,7 +558,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
         {
-            constexpr int KS[4] = {14, 4, 2, 0};   // KSPEC == 1: the Whisper 80-mel / fft-400 bank
+            constexpr int KS[4] = {KSPEC == 2 ? 8 : 14, KSPEC == 2 ? 5 : 4, 2, 0};   // KSPEC != 0: the Whisper 80-mel / fft-400 bank
+            constexpr bool EXS[4] = {KSPEC == 2, KSPEC == 2, false, false};         // slots whose split bands are summed by shuffle
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             const float* wt = s_projw + lane;                                                          // [entry][lane]
             int eoff = 0;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             for (int s = 0; s < MPL; ++s) {
                 const float2* pr = s_p + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
                 f2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0;
-                if (KSPEC == 1) {
+                if (KSPEC != 0) {
                     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int e = 0; e < KS[s]; ++e) {
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     }
                     eoff += KS[s];
                 } else {
-                    const int K = s_meta[s];
+                    const int K = s_meta[s] & 0xffff;
 #pragma unroll 2
                     for (int e = 0; e < K; ++e) {
                         const float w = wt[(eoff + e) * 32];
@@ -587,6 +591,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                         acc2 = fma2(ww, pr[PPLANE2 + e], acc2);
                     }
                     eoff += K;
+                }
+                if (KSPEC != 0 ? EXS[s] : (s_meta[s] >> 16) != 0) {   // warp-uniform: add the other half of split bands
+                    const int pl = s_meta[kMaxMpl + 2 * kMaxMpl * 32 + s * 32 + lane];
+                    const float sel = pl != lane ? 1.0f : 0.0f;
+                    const f2 o0 = make_float2(__shfl_sync(0xffffffffu, acc0.x, pl), __shfl_sync(0xffffffffu, acc0.y, pl));
+                    const f2 o1 = make_float2(__shfl_sync(0xffffffffu, acc1.x, pl), __shfl_sync(0xffffffffu, acc1.y, pl));
+                    const f2 o2 = make_float2(__shfl_sync(0xffffffffu, acc2.x, pl), __shfl_sync(0xffffffffu, acc2.y, pl));
+                    const f2 ss = make_float2(sel, sel);
+                    acc0 = fma2(ss, o0, acc0); acc1 = fma2(ss, o1, acc1); acc2 = fma2(ss, o2, acc2);
                 }
                 const float a[FPW] = {acc0.x, acc0.y, acc1.x, acc1.y, acc2.x, acc2.y};
 #pragma unroll
@@ -1044,7 +1057,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const float* wt = s_projw + lane;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int K = s_meta[s];
+                const int K = s_meta[s] & 0xffff;
                 const float4* pr = s_p4 + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
                 f2 acc01 = make_float2(0.f, 0.f), acc23 = acc01;
 #pragma unroll 4
