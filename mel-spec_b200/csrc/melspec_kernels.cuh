@@ -826,9 +826,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 
     const int need = (FPW - 1) * 160 + p.frame_len;
 
-    auto issue_load = [&](int wt) {
-        const int clip = wt / p.wtiles_per_clip;
-        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+    auto issue_load = [&](int clip, int tin) {
+        const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * 160;
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
@@ -883,22 +882,29 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     const bool fused = KALDI && p.cmn_fused;
     const int wstride = gridDim.x * NWARPS;
     int wt = fused ? blockIdx.x * p.wtiles_per_clip + warp : blockIdx.x * NWARPS + warp;
-    int tile_in_clip = warp;                                  // fused mode only
-    auto next_tile = [&](int cur, int& tin) -> int {          // fused: advance (clip, tile); returns the next global tile id
-        if (!fused) return cur + wstride;
+    // (clip, tile in clip) of the current tile, advanced without divisions in the loop
+    const int wq = wstride / p.wtiles_per_clip, wr = wstride - wq * p.wtiles_per_clip;
+    int clip_f = fused ? (int)blockIdx.x : wt / p.wtiles_per_clip;
+    int tile_in_clip = fused ? warp : wt - clip_f * p.wtiles_per_clip;
+    auto next_tile = [&](int cur, int& tin, int& cl) -> int { // advance; returns the next global tile id
+        if (!fused) {
+            cl += wq; tin += wr;
+            if (tin >= p.wtiles_per_clip) { tin -= p.wtiles_per_clip; ++cl; }
+            return cur + wstride;
+        }
         if (tin + NWARPS < p.wtiles_per_clip) { tin += NWARPS; return cur + NWARPS; }
-        const int clip_now = cur / p.wtiles_per_clip;
         tin = warp;
-        return (clip_now + (int)gridDim.x) * p.wtiles_per_clip + warp;
+        cl += (int)gridDim.x;
+        return cl * p.wtiles_per_clip + warp;
     };
     float csum[MPL];
 #pragma unroll
     for (int s = 0; s < MPL; ++s) csum[s] = 0.f;
-    if (wt < p.n_wtiles) issue_load(wt);
+    if (wt < p.n_wtiles) issue_load(clip_f, tile_in_clip);
 
     for (int it = 0; wt < p.n_wtiles; ++it) {
-        const int clip = wt / p.wtiles_per_clip;
-        const int fw0 = (wt - clip * p.wtiles_per_clip) * FPW;
+        const int clip = clip_f;
+        const int fw0 = tile_in_clip * FPW;
         int nfr = p.frames_per_clip;
         if (!NEMO && p.lens) {
             const int len = min(p.lens[clip], p.n_samples);
@@ -988,9 +994,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             }
         }
         __syncwarp();
-        int tin_next = tile_in_clip;
-        const int wt_next = next_tile(wt, tin_next);
-        if (wt_next < p.n_wtiles) issue_load(wt_next);
+        int tin_next = tile_in_clip, clip_next = clip_f;
+        const int wt_next = next_tile(wt, tin_next, clip_next);
+        if (wt_next < p.n_wtiles) issue_load(clip_next, tin_next);
         if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
 
         float ar[32], ai[32];
@@ -1167,7 +1173,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         }   // nvalid != 0
 
         // ------------------------------------------------------------------ fused CMN: end of this warp's share of the clip
-        if (fused && (wt_next >= p.n_wtiles || wt_next / p.wtiles_per_clip != clip)) {
+        if (fused && clip_next != clip) {
             float* s_cs = reinterpret_cast<float*>(smem + p.smem_cmn);       // [NWARPS][128]
             float* s_mean = s_cs + NWARPS * 128;                             // [128]
 #pragma unroll
@@ -1190,24 +1196,32 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const float4* mean4 = reinterpret_cast<const float4*>(s_mean);
             // four independent L2 loads in flight per thread: the pass is latency-bound otherwise (one CTA per SM)
             constexpr int NT = NWARPS * 32, UN = 4;
+            const int step1 = NT % quads, stepu = (NT * UN) % quads;   // column of element i + NT / i + NT*UN without a division
+            int mq = (int)threadIdx.x % quads;
             for (int i0 = threadIdx.x; i0 < total; i0 += NT * UN) {
                 float4 v[UN];
 #pragma unroll
                 for (int u = 0; u < UN; ++u)
                     if (i0 + u * NT < total) v[u] = __ldcg(reinterpret_cast<const float4*>(base) + i0 + u * NT);
+                int mc = mq;
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     const int i = i0 + u * NT;
                     if (i < total) {
-                        const float4 m = mean4[i % quads];
+                        const float4 m = mean4[mc];
                         v[u].x -= m.x; v[u].y -= m.y; v[u].z -= m.z; v[u].w -= m.w;
                         reinterpret_cast<float4*>(base)[i] = v[u];
                     }
+                    mc += step1;
+                    if (mc >= quads) mc -= quads;
                 }
+                mq += stepu;
+                if (mq >= quads) mq -= quads;
             }
         }
         wt = wt_next;
         tile_in_clip = tin_next;
+        clip_f = clip_next;
     }
     if (lane == 0) bulk_wait0();
 }
