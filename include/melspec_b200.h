@@ -61,15 +61,15 @@ enum {
  */
 typedef struct melspec_config {
     int32_t frontend;      /* MELSPEC_FRONTEND_*                                                               */
-    int32_t fft_size;      /* Whisper: N (400 or 512).  Kaldi: ignored on input (next pow2 of frame_length).   */
+    int32_t fft_size;      /* Whisper / NeMo: N (any size).  Kaldi: ignored on input (next pow2 of frame_length). */
     int32_t hop_size;      /* samples between frames (Whisper hop / Kaldi frame shift)                         */
     int32_t n_mels;        /* 1..128                                                                           */
     double sampling_rate;  /* Hz                                                                               */
     /* Kaldi-only fields (FbankConfig).  Ignored for the Whisper frontend. */
-    int32_t frame_length;  /* samples per frame before zero padding (400)                                      */
+    int32_t frame_length;  /* samples per frame before zero padding (400 at 25 ms / 16 kHz; any length >= 2)   */
     int32_t apply_cmn;     /* subtract per-mel mean over time (src/fbank.rs:226-233)                           */
     int32_t use_log_fbank; /* ln() of the floored energies                                                     */
-    int32_t use_power;     /* 1: |X|^2 (only value supported), 0: |X|                                          */
+    int32_t use_power;     /* 1: |X|^2, 0: |X| (src/fbank.rs:197-203)                                          */
     double preemphasis;    /* 0.97                                                                             */
     double low_freq;       /* 20 Hz                                                                            */
     double high_freq;      /* 0 => Nyquist                                                                     */
@@ -95,7 +95,12 @@ typedef struct melspec_stream melspec_stream;
 int32_t melspec_default_config(int32_t frontend, melspec_config* cfg);
 
 /* Builds the constant tables (window, twiddles, sparse banded filterbank) on `device` and returns a handle.
- * Replaces CudaMelSpectrogram::new (src/cuda.rs:39-82) / Fbank::new (src/fbank.rs:94-132). */
+ * Replaces CudaMelSpectrogram::new (src/cuda.rs:39-82) / Fbank::new (src/fbank.rs:94-132).
+ * Every size the reference accepts is served: the configurations of the reference's tests, goldens and benchmarks
+ * (Whisper fft_size 400 at hop <= 256, Whisper fft_size 512 / hop 160, Kaldi 400-sample frames / hop 160 / power spectrum,
+ * NeMo n_fft 512 / win_length 400 / hop 160) run on two specialised kernels, every other fft_size (<= 14080; odd sizes
+ * <= 9386) / hop / frame length / sample rate on a general mixed-radix kernel with the same fusion and the same results
+ * contract.  n_mels <= 128. */
 int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle** out);
 
 /* Replaces Drop (src/cuda.rs:142-148, 366-375).  NULL is a no-op. */

@@ -13,7 +13,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libmelspec_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "melspec_api.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_ROOT, "include", "melspec_b200.h")]
+HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_PKG, "csrc", "melspec_generic.cuh"),
+           os.path.join(_ROOT, "include", "melspec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "melspec_kernels.cuh"
+#include "melspec_generic.cuh"
 
 namespace {
 
@@ -173,8 +174,14 @@ struct melspec_handle {
     Resolved cfg;
     int device = 0;
     int num_sms = 0;
-    int plan = 0;   // 400 or 512
+    int plan = 0;   // 400 or 512 (specialised kernels), 1 = the general plan (melspec_generic.cuh)
     std::vector<double> dense;   // (n_mels, fft/2+1)
+    // general plan: twiddles W_N^k, window, CSR band table, radix schedule
+    float2* d_gtw = nullptr;
+    float* d_gwin = nullptr;
+    int* d_gbands = nullptr;
+    float* d_gweights = nullptr;
+    std::vector<int> radices;
     // device tables
     float* d_window = nullptr;
     float4* d_twiddle = nullptr;
@@ -220,7 +227,61 @@ struct melspec_stream {
 
 namespace {
 
+// Tables of the general plan (melspec_generic.cuh): twiddles, window, CSR bands, radix schedule.
+int32_t build_tables_generic(melspec_handle* h) {
+    const Resolved& c = h->cfg;
+    const int N = c.fft, nb = N / 2 + 1, L = c.frame_len;
+    std::vector<float2> tw((size_t)N);
+    for (int k = 0; k < N; ++k) {
+        const double a = 2.0 * M_PI * (double)k / (double)N;
+        tw[k] = make_float2((float)std::cos(a), (float)-std::sin(a));
+    }
+    std::vector<float> win((size_t)L, 0.f);
+    for (int i = 0; i < L; ++i) {
+        if (c.frontend == MELSPEC_FRONTEND_WHISPER)        // periodic Hann, src/stft.rs:141-145
+            win[i] = (float)(0.5 * (1.0 - std::cos(2.0 * M_PI * (double)i / (double)N)));
+        else if (c.frontend == MELSPEC_FRONTEND_NEMO)      // symmetric Hann of win_length (zeros if <= 1), src/mel.rs:708-719
+            win[i] = L <= 1 ? 0.f : (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(L - 1)));
+        else                                               // Povey, src/fbank.rs:100-105
+            win[i] = (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(L - 1)), 0.85);
+    }
+    // radix schedule: 4s, then a 2, then the odd prime factors in ascending order
+    h->radices.clear();
+    int n = (N % 2 == 0) ? N / 2 : N;   // even N: one complex N/2-point transform of the even/odd samples
+    while (n % 4 == 0) { h->radices.push_back(4); n /= 4; }
+    if (n % 2 == 0) { h->radices.push_back(2); n /= 2; }
+    for (int f = 3; (long long)f * f <= n; f += 2)
+        while (n % f == 0) { h->radices.push_back(f); n /= f; }
+    if (n > 1) h->radices.push_back(n);
+    if ((int)h->radices.size() > melspec::kMaxStages) return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size has too many prime factors");
+    // CSR bands: per mel row the run [first non-zero bin, last non-zero bin]; Whisper drops bins >= N/2 (src/mel.rs:158-162)
+    const int last = c.frontend == MELSPEC_FRONTEND_WHISPER ? N / 2 - 1 : N / 2;
+    std::vector<int> bands((size_t)3 * c.n_mels, 0);
+    std::vector<float> wts;
+    for (int m = 0; m < c.n_mels; ++m) {
+        int b0 = -1, b1 = -1;
+        for (int b = 0; b <= last; ++b)
+            if (h->dense[(size_t)m * nb + b] != 0.0) { if (b0 < 0) b0 = b; b1 = b; }
+        bands[3 * m] = b0 < 0 ? 0 : b0;
+        bands[3 * m + 1] = b0 < 0 ? 0 : b1 - b0 + 1;
+        bands[3 * m + 2] = (int)wts.size();
+        for (int b = b0; b0 >= 0 && b <= b1; ++b) wts.push_back((float)h->dense[(size_t)m * nb + b]);
+    }
+    if (wts.empty()) wts.push_back(0.f);
+    MS_CUDA(cudaMalloc(&h->d_gtw, sizeof(float2) * tw.size()));
+    MS_CUDA(cudaMalloc(&h->d_gwin, sizeof(float) * std::max<size_t>(win.size(), 1)));
+    MS_CUDA(cudaMalloc(&h->d_gbands, sizeof(int) * bands.size()));
+    MS_CUDA(cudaMalloc(&h->d_gweights, sizeof(float) * wts.size()));
+    MS_CUDA(cudaMemcpy(h->d_gtw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+    if (!win.empty()) MS_CUDA(cudaMemcpy(h->d_gwin, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_gbands, bands.data(), sizeof(int) * bands.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(h->d_gweights, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice));
+    h->mpl = (c.n_mels + 31) / 32;
+    return MELSPEC_OK;
+}
+
 int32_t build_tables(melspec_handle* h) {
+    if (h->plan == 1) return build_tables_generic(h);
     const Resolved& c = h->cfg;
     using namespace melspec;
     const int N = h->plan, nb = N / 2 + 1;
@@ -517,6 +578,62 @@ int32_t launch_kernel(Kern kern, const melspec::KParams& p, int grid, int thread
     return MELSPEC_OK;
 }
 
+// Kernels that couple all frames of a clip and therefore follow the fused kernel: NeMo per-feature mean/std
+// (src/mel.rs:721-749) and Kaldi CMN (src/fbank.rs:226-233) when it is not fused.
+int32_t launch_post_kernels(melspec_handle* h, const melspec::KParams& p, int64_t n_clips, const int32_t* d_lens, float* d_out,
+                            bool cmn_done, cudaStream_t st) {
+    using namespace melspec;
+    const Resolved& c = h->cfg;
+    if (c.frontend == MELSPEC_FRONTEND_NEMO && c.norm_feat) {
+        const long long rows = (long long)n_clips * c.n_mels;
+        melspec_featnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_out, p.out_clip_stride, p.out_row_stride,
+                                                                          p.frames_per_clip, c.n_mels, (int)rows);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    if (c.frontend == MELSPEC_FRONTEND_KALDI && c.cmn && !cmn_done) {
+        melspec_cmn_kernel<<<(unsigned)n_clips, 512, 0, st>>>(d_out, p.out_clip_stride, p.frames_per_clip, c.n_mels, d_lens,
+                                                             p.n_samples, c.frame_len, c.hop);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    return MELSPEC_OK;
+}
+
+// The general plan: one warp per pair of frames, mixed-radix shared-memory FFT (melspec_generic.cuh).
+int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, const int32_t* d_lens, float* d_out,
+                       int64_t row_stride, cudaStream_t st) {
+    using namespace melspec;
+    const Resolved& c = h->cfg;
+    GParams g{};
+    g.tw = h->d_gtw; g.window = h->d_gwin; g.bands = h->d_gbands; g.weights = h->d_gweights;
+    g.N = c.fft;
+    g.Nf = (c.fft % 2 == 0) ? c.fft / 2 : c.fft;
+    g.n_stages = (int)h->radices.size();
+    for (int i = 0; i < g.n_stages; ++i) g.radix[i] = h->radices[i];
+    g.mode = c.frontend == MELSPEC_FRONTEND_KALDI ? 1 : c.frontend == MELSPEC_FRONTEND_NEMO ? 2 : 0;
+    g.use_power = c.use_power; g.use_log = c.use_log;
+    g.n_units = (long long)p.frames_per_clip * n_clips;
+    // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
+    const size_t budget = 220 * 1024, per_warp = (size_t)16 * g.Nf, tw_bytes = (size_t)8 * c.fft;
+    int nw = (int)std::min<size_t>(8, (budget - tw_bytes) / per_warp);
+    if (nw < 1) nw = 1;
+    const size_t smem = tw_bytes + per_warp * nw;
+    MS_CUDA(cudaFuncSetAttribute(melspec_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int per_sm = 1;
+    MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, melspec_generic_kernel, nw * 32, smem));
+    if (per_sm < 1) return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size too large for the shared-memory FFT of this build");
+    const long long want = (g.n_units + nw - 1) / nw;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->num_sms * per_sm));
+    if (c.frontend == MELSPEC_FRONTEND_NEMO && row_stride > p.frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
+        MS_CUDA(cudaMemset2DAsync(d_out + p.frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - p.frames_per_clip) * 4,
+                                  (size_t)n_clips * c.n_mels, st));   // pad_to columns are zeros (src/mel.rs:336)
+    melspec_generic_kernel<<<grid, nw * 32, smem, st>>>(p, g);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return launch_post_kernels(h, p, n_clips, d_lens, d_out, false, st);
+}
+
 // Core launch: device pointers, explicit frame count (frames_per_clip may be smaller than num_frames(n_samples)).
 int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
                       int64_t frames_per_clip, const int32_t* d_lens, float* d_out, int64_t out_clip_stride, int32_t layout,
@@ -532,7 +649,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         return fail(MELSPEC_ERR_UNSUPPORTED, "the NeMo frontend produces (n_mels, frames) feature-major output only");
     if (nemo && d_lens) return fail(MELSPEC_ERR_UNSUPPORTED, "per-clip lengths are not supported by the NeMo frontend yet");
     const int64_t row_stride = row_stride_override > 0 ? row_stride_override : nemo ? padded_frames_for(c, n_samples) : frames_per_clip;
-    const int fpw = h->plan == 400 ? p400::FPW : p512::FPW;
+    const int fpw = h->plan == 400 ? p400::FPW : h->plan == 512 ? p512::FPW : 2;
     KParams p{};
     p.pcm = d_pcm; p.out = d_out; p.lens = d_lens;
     p.clip_stride = clip_stride;
@@ -561,6 +678,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
+    if (h->plan == 1) return launch_generic(h, p, n_clips, d_lens, d_out, row_stride, st);
     // shared-memory carve-up: [mbarriers | window | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
@@ -630,20 +748,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     }
     if (rc != MELSPEC_OK) return rc;
     h->launches += 1;
-    if (nemo && c.norm_feat) {   // per-feature mean/std couples all frames of a clip: second kernel (src/mel.rs:721-749)
-        const long long rows = (long long)n_clips * c.n_mels;
-        melspec_featnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_out, p.out_clip_stride, p.out_row_stride,
-                                                                          p.frames_per_clip, c.n_mels, (int)rows);
-        MS_CUDA(cudaGetLastError());
-        h->launches += 1;
-    }
-    if (kaldi && c.cmn && !fused_cmn) {   // CMN couples all frames of a clip: second kernel (short clips / small batches)
-        melspec_cmn_kernel<<<(unsigned)n_clips, 512, 0, st>>>(d_out, p.out_clip_stride, p.frames_per_clip, c.n_mels, d_lens,
-                                                             p.n_samples, c.frame_len, c.hop);
-        MS_CUDA(cudaGetLastError());
-        h->launches += 1;
-    }
-    return MELSPEC_OK;
+    return launch_post_kernels(h, p, n_clips, d_lens, d_out, fused_cmn, st);
 }
 
 int32_t ensure_host_resources(melspec_handle* h, size_t pcm_bytes, size_t out_bytes) {
@@ -749,15 +854,20 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
     MS_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return fail(MELSPEC_ERR_NO_DEVICE, "CUDA unavailable: kernels are built for sm_100a (Blackwell) only");
-    int plan = 0;
-    if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400) plan = 400;
+    // Specialised kernels for the configurations the reference's tests / goldens / BASELINE.json name; the general plan
+    // (melspec_generic.cuh) for every other size.  MELSPEC_FORCE_GENERIC=1 routes everything through the general plan (tests).
+    static const bool force_generic = [] { const char* e = std::getenv("MELSPEC_FORCE_GENERIC"); return e && e[0] == '1'; }();
+    int plan = 1;
+    if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400 && r.hop <= 256) plan = 400;
     else if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 512 && r.hop == 160) plan = 512;
     else if (r.frontend == MELSPEC_FRONTEND_KALDI && r.fft == 512 && r.frame_len == 400 && r.hop == 160 && r.use_power) plan = 512;
     else if (r.frontend == MELSPEC_FRONTEND_NEMO && r.fft == 512 && r.frame_len == 400 && r.hop == 160) plan = 512;
-    if (!plan)
-        return fail(MELSPEC_ERR_UNSUPPORTED,
-                    "supported plans: Whisper fft_size 400 (any hop), Whisper fft_size 512 / hop 160, Kaldi 400-sample frames / "
-                    "hop 160 / power spectrum, NeMo n_fft 512 / win_length 400 / hop 160");
+    if (force_generic) plan = 1;
+    if (plan == 1) {
+        // the CTA's twiddle table (8 N bytes) and one warp's two ping-pong buffers (16 N bytes, 8 N for even N) must fit
+        if ((size_t)r.fft * (r.fft % 2 ? 24 : 16) > 220 * 1024)
+            return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size too large for the shared-memory FFT of this build (max 14080, odd sizes 9386)");
+    }
     MS_CUDA(cudaSetDevice(device));
     melspec_handle* h = new (std::nothrow) melspec_handle();
     if (!h) return fail(MELSPEC_ERR_CUDA, "out of host memory");
@@ -783,6 +893,10 @@ void melspec_destroy(melspec_handle* h) {
     cudaFree(h->d_rot10);
     cudaFree(h->d_proj);
     cudaFree(h->d_meta);
+    cudaFree(h->d_gtw);
+    cudaFree(h->d_gwin);
+    cudaFree(h->d_gbands);
+    cudaFree(h->d_gweights);
     cudaFree(h->d_partials);
     cudaFree(h->d_fmt_img);
     cudaFree(h->d_fmt_tga);
