@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the optional NCCL all-gather of the output shards (reported separately, never in `value`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -272,6 +274,27 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- optional: NCCL all-gather of the output shards (north_star: not on the hot path; reported on its own)
+    gather = None
+    if args.gather and world > 1:
+        from mel_spec_b200.shard import gather_output
+        full = gather_output(out, world * clips, dist)   # warm-up (NCCL channel setup)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            full = gather_output(out, world * clips, dist)
+        g1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(full[rank * clips:(rank + 1) * clips], out))
+        recv = (world - 1) * out.numel() * 4
+        gather = {"ms": float(tg.item()), "bytes_received_per_gpu": recv, "GB/s_per_gpu": recv / (float(tg.item()) * 1e-3) / 1e9,
+                  "own_shard_intact": ok, "collective": "ncclAllGather via torch.distributed.all_gather_into_tensor"}
+        del full
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H inside the region)
     e2e_steps = max(1, args.e2e_steps)
     hx = torch.empty((clips, n_samples), dtype=torch.float32, pin_memory=True)
@@ -317,6 +340,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if gather is not None:
+            line["gather"] = gather
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))

@@ -273,7 +273,8 @@ public:
         cfg.frame_length = (int32_t)c.frame_length_samples(); cfg.hop_size = (int32_t)c.frame_shift_samples();
         cfg.apply_cmn = c.apply_cmn; cfg.use_log_fbank = c.use_log_fbank; cfg.use_power = c.use_power;
         cfg.preemphasis = c.preemphasis; cfg.low_freq = c.low_freq; cfg.high_freq = c.high_freq; cfg.energy_floor = c.energy_floor;
-        if (c.use_energy || c.dither != 0.0) throw CudaError(CudaError::Kind::Unavailable, "use_energy / dither are not supported");
+        // `dither` and `use_energy` are carried by the reference's FbankConfig but never read by Fbank::compute
+        // (src/fbank.rs:141-236): accepted and ignored here as well.
         h_ = detail::Handle(cfg, device);
     }
     // returns the flat (T, n_mels) matrix; `frames` receives T

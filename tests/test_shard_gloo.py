@@ -26,7 +26,17 @@ def _worker(rank, world, port, q):
     lo, hi = shard_range(1025, rank, world)
     dist.barrier()
     rate = whole_job_rate((hi - lo) * 998, 0.5 + rank, dist)      # rank 1 is the slow one: 1.5 s
-    q.put((rank, lo, hi, rate))
+    # optional output gather (north_star: "only an optional NCCL gather of the output mel tensor"): uneven and even batches
+    import torch
+    from mel_spec_b200.shard import gather_output
+    ok = True
+    for n in (1025, 1024, 3, 1):
+        a, b = shard_range(n, rank, world)
+        local = (torch.arange(a, b, dtype=torch.float32)[:, None, None] * 10 + torch.arange(6, dtype=torch.float32).reshape(1, 2, 3))
+        full = gather_output(local, n, dist)
+        want = torch.arange(n, dtype=torch.float32)[:, None, None] * 10 + torch.arange(6, dtype=torch.float32).reshape(1, 2, 3)
+        ok = ok and full.shape == want.shape and bool(torch.equal(full, want))
+    q.put((rank, lo, hi, rate, ok))
     dist.destroy_process_group()
 
 
@@ -42,6 +52,8 @@ def test_two_rank_sharding_and_rate():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert all(r[4] for r in res), "gather_output must return the whole batch in clip order on every rank"
+    res = [r[:4] for r in res]
     (r0, lo0, hi0, rate0), (r1, lo1, hi1, rate1) = res
     assert (lo0, hi0, lo1, hi1) == (0, 513, 513, 1025)           # contiguous, disjoint, complete
     assert rate0 == rate1 == pytest.approx(1025 * 998 / 1.5)     # sum of units / max of times

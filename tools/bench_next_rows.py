@@ -5,6 +5,7 @@ CUDA events on the launch stream, inputs larger than L2.  One JSON object per ro
   f-3a fused kernel writing the interleave_frames image directly (mel-major, min_width padding)
   f-3b TGA quantiser (min/max pass + quantise pass) and dequantiser on 1024 images of 80 x 998
   f-4  VAD Sobel/majority kernel + per-frame activity kernel on the same images
+  general plan: Whisper at fft 1024 / 2048 / 480 and Kaldi at 8 kHz (sizes outside the specialised kernels)
 `achieved` = algorithmic bytes / time against MEASURED_PEAKS.json hbm_gbs (these are HBM-bound byte/stencil kernels).
 Run: python tools/bench_next_rows.py [--steps 20]"""
 import argparse
@@ -92,6 +93,23 @@ def main():
     t = timeit(vad, args.steps, st)
     row("f-4 VAD boundaries + per-frame activity (f64 Sobel), 1024 images 80 x 1000", t, clips * W, "frames/s",
         px * 4 + clips * (W - 2) * 2 + clips * W * 12)
+    # ---- general plan (melspec_generic.cuh): sizes outside the two specialised kernels
+    del img, tga, back, sm, rw, act
+    for fft, hop, nm in ((1024, 256, 128), (2048, 512, 80), (480, 160, 80)):
+        g = ms.CudaMelSpectrogram(fft, hop, 16000.0, nm)
+        Fg = g.num_frames(n)
+        og = torch.empty((clips, Fg, nm), dtype=torch.float32, device=dev)
+        t = timeit(lambda: g.compute_device(x, clips, n, n, og, stream=st), args.steps, st)
+        row(f"general plan: Whisper fft {fft} hop {hop} {nm} mel, 1024 x 10 s", t, clips * Fg, "frames/s",
+            clips * (4 * n + 4 * nm * Fg), {"frames_per_clip": Fg})
+        g.close()
+        del og
+    fb8 = ms.Fbank(ms.FbankConfig(sample_rate=8000.0, num_mel_bins=40))
+    Fk = fb8.num_frames(n)
+    ok = torch.empty((clips, Fk, 40), dtype=torch.float32, device=dev)
+    t = timeit(lambda: fb8.compute_device(x, clips, n, n, ok, stream=st), args.steps, st)
+    row("general plan: Kaldi fbank 8 kHz (200-sample frames, fft 256, shift 80) 40 bins + CMN, 1024 x 20 s", t, clips * Fk, "frames/s",
+        clips * (4 * n + 4 * 40 * Fk), {"frames_per_clip": Fk})
     return rows
 
 
