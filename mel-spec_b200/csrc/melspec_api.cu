@@ -610,7 +610,13 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     g.N = c.fft;
     g.Nf = (c.fft % 2 == 0) ? c.fft / 2 : c.fft;
     g.n_stages = (int)h->radices.size();
-    for (int i = 0; i < g.n_stages; ++i) g.radix[i] = h->radices[i];
+    for (int i = 0, st = 1; i < g.n_stages; ++i) {
+        g.radix[i] = h->radices[i];
+        int sh = -1;
+        if ((st & (st - 1)) == 0) { sh = 0; while ((1 << sh) < st) ++sh; }
+        g.sshift[i] = sh;
+        st *= h->radices[i];
+    }
     g.mode = c.frontend == MELSPEC_FRONTEND_KALDI ? 1 : c.frontend == MELSPEC_FRONTEND_NEMO ? 2 : 0;
     g.use_power = c.use_power; g.use_log = c.use_log;
     g.n_units = (long long)p.frames_per_clip * n_clips;

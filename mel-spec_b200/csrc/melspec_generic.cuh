@@ -45,6 +45,7 @@ struct GParams {
     int use_power, use_log;
     long long n_units;      // frames_per_clip * n_clips
     int radix[kMaxStages];
+    int sshift[kMaxStages]; // log2 of the stage's stride s when it is a power of two (shift instead of an integer division), else -1
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, fmaf(a.x, b.y, a.y * b.x)); }
@@ -109,10 +110,10 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
         float2* dst = buf1;
         int ncur = Nf, s = 1;
         for (int st = 0; st < g.n_stages; ++st) {
-            const int r = g.radix[st], m = ncur / r;
+            const int r = g.radix[st], m = ncur / r, sh = g.sshift[st];
             if (r == 4) {
                 for (int bfly = lane; bfly < Nf / 4; bfly += 32) {
-                    const int pp = bfly / s, q = bfly - pp * s;
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
                     const float2* xi = src + q + s * pp;
                     const float2 a0 = xi[0], a1 = xi[(size_t)s * m], a2 = xi[(size_t)2 * s * m], a3 = xi[(size_t)3 * s * m];
                     const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
                 }
             } else if (r == 2) {
                 for (int bfly = lane; bfly < Nf / 2; bfly += 32) {
-                    const int pp = bfly / s, q = bfly - pp * s;
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
                     const float2 a0 = src[q + s * pp], a1 = src[q + s * (pp + m)];
                     float2* yo = dst + q + (size_t)s * 2 * pp;
                     yo[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
                 const int wr = N / r;   // W_r^e = W_N^(e N/r)
                 for (int e = lane; e < Nf; e += 32) {
                     const int bfly = e / r, j = e - bfly * r;
-                    const int pp = bfly / s, q = bfly - pp * s;
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
                     const float2* xi = src + q + s * pp;
                     float2 acc = xi[0];
                     int idx = 0;
