@@ -173,3 +173,22 @@ def test_nemo_any_config_vs_oracle(m, jfk, kw):
         want = o.batch_log_mel(x, log_zero_guard=guard, **kw)
         _ln_check(got, want)
     fe.close()
+
+
+def test_generic_interleaved_image_and_tga(m, jfk):
+    # the formats after the path (src/mel.rs:480-544, src/quant.rs:38-64) on a size that runs on the general plan
+    fft, hop, n_mels = 1024, 256, 80
+    h = m.CudaMelSpectrogram(fft, hop, 16000.0, n_mels)
+    x = jfk[:70000]
+    frames = h.compute_mel_spectrogram(x)
+    want = o.whisper_mel_batch(x, fft, hop, n_mels, 16000.0)
+    assert np.abs(frames - want).max() <= WHISPER_TOL
+    f = frames.shape[0]                                        # 270 frames -> even width 270; min_width 300 pads with zeros
+    for min_width in (0, 300):
+        tga, img = h.mel_tga(x, min_width=min_width, return_image=True)
+        w = img.shape[1]
+        assert w == o.interleave_frames(want, False, min_width).size // n_mels
+        assert np.array_equal(img[:, :f], frames.T), "interleaved image == frames transposed"
+        assert np.all(img[:, f:] == 0.0)
+        assert tga == o.tga_8bit_data(img.reshape(-1), n_mels), "device quantiser bytes == quant.rs arithmetic on the same f32 image"
+    h.close()
