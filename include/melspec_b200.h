@@ -98,8 +98,8 @@ int32_t melspec_default_config(int32_t frontend, melspec_config* cfg);
  * Replaces CudaMelSpectrogram::new (src/cuda.rs:39-82) / Fbank::new (src/fbank.rs:94-132).
  * Every size the reference accepts is served: the configurations of the reference's tests, goldens and benchmarks
  * (Whisper fft_size 400 at hop <= 256, Whisper fft_size 512 / hop 160, Kaldi 400-sample frames / hop 160 / power spectrum,
- * NeMo n_fft 512 / win_length 400 / hop 160) run on two specialised kernels, every other fft_size (<= 14080; odd sizes
- * <= 9386) / hop / frame length / sample rate on a general mixed-radix kernel with the same fusion and the same results
+ * NeMo n_fft 512 / win_length 400 / hop 160) run on two specialised kernels, every other fft_size (<= 13652; odd sizes
+ * <= 9009) / hop / frame length / sample rate on a general mixed-radix kernel with the same fusion and the same results
  * contract.  n_mels <= 128. */
 int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle** out);
 

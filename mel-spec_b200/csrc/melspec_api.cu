@@ -245,9 +245,10 @@ int32_t build_tables_generic(melspec_handle* h) {
         else                                               // Povey, src/fbank.rs:100-105
             win[i] = (float)std::pow(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)(L - 1)), 0.85);
     }
-    // radix schedule: 4s, then a 2, then the odd prime factors in ascending order
+    // radix schedule: 8s, 4s, then a 2, then the odd prime factors in ascending order
     h->radices.clear();
     int n = (N % 2 == 0) ? N / 2 : N;   // even N: one complex N/2-point transform of the even/odd samples
+    while (n % 8 == 0) { h->radices.push_back(8); n /= 8; }
     while (n % 4 == 0) { h->radices.push_back(4); n /= 4; }
     if (n % 2 == 0) { h->radices.push_back(2); n /= 2; }
     for (int f = 3; (long long)f * f <= n; f += 2)
@@ -621,7 +622,8 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     g.use_power = c.use_power; g.use_log = c.use_log;
     g.n_units = (long long)p.frames_per_clip * n_clips;
     // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
-    const size_t budget = 220 * 1024, per_warp = (size_t)16 * g.Nf, tw_bytes = (size_t)8 * c.fft;
+    g.vec2 = ((uintptr_t)p.pcm % 8 == 0) && (p.clip_stride % 2 == 0) && (c.hop % 2 == 0) && (p.frame_offset % 2 == 0) && (c.fft % 2 == 0);
+    const size_t budget = 220 * 1024, per_warp = (size_t)16 * generic_buf_elems(g.Nf), tw_bytes = (size_t)8 * c.fft;
     int nw = (int)std::min<size_t>(8, (budget - tw_bytes) / per_warp);
     if (nw < 1) nw = 1;
     const size_t smem = tw_bytes + per_warp * nw;
@@ -871,8 +873,9 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
     if (force_generic) plan = 1;
     if (plan == 1) {
         // the CTA's twiddle table (8 N bytes) and one warp's two ping-pong buffers (16 N bytes, 8 N for even N) must fit
-        if ((size_t)r.fft * (r.fft % 2 ? 24 : 16) > 220 * 1024)
-            return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size too large for the shared-memory FFT of this build (max 14080, odd sizes 9386)");
+        const int nf = r.fft % 2 ? r.fft : r.fft / 2;
+        if ((size_t)r.fft * 8 + (size_t)16 * melspec::generic_buf_elems(nf) > 220 * 1024)
+            return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size too large for the shared-memory FFT of this build (max 13652, odd sizes 9009)");
     }
     MS_CUDA(cudaSetDevice(device));
     melspec_handle* h = new (std::nothrow) melspec_handle();

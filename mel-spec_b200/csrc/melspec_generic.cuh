@@ -17,9 +17,12 @@
 //     src/stft.rs:141-169), DC removal + pre-emphasis with look-back + Povey window + zero padding (Kaldi,
 //     src/fbank.rs:166-190), whole-waveform pre-emphasis + centre padding + centred symmetric Hann (NeMo,
 //     src/mel.rs:685-719);
-//   * a mixed-radix Stockham autosort FFT in the warp's private shared-memory ping-pong buffers (radix 4 and 2 in
-//     registers, any other prime factor r as an r-term sum per output, balanced over (butterfly, output) pairs so that a
-//     large prime factor — even a prime N — is slow but correct); twiddles W_N^k come from one f64-built table per CTA;
+//   * a mixed-radix Stockham autosort FFT in the warp's private shared-memory ping-pong buffers: radix 8, 4, 2, 3 and 5
+//     butterflies in registers, any other prime factor r as an r-term sum per output, balanced over (butterfly, output)
+//     pairs so that a large prime factor — even a prime N — is slow but correct.  Element i lives at i + (i >> 4): with
+//     that one-in-sixteen padding the strided 64-bit stores of the early stages spread over all 16 bank pairs of a
+//     half-warp (modelled: 224 instead of 512 wavefronts per 512-point transform together with radix 8).  Twiddles
+//     W_N^k come from one f64-built table per CTA;
 //   * power (or magnitude) of bins 0..N/2, banded projection in ascending bin order from a CSR table (one lane per mel
 //     row, the reference's own summation order, src/mel.rs:106-168), log / floor / guard and the Whisper per-frame clamp
 //     (src/mel.rs:645-654) with a warp max, stores in the caller's layout.
@@ -46,9 +49,66 @@ struct GParams {
     long long n_units;      // frames_per_clip * n_clips
     int radix[kMaxStages];
     int sshift[kMaxStages]; // log2 of the stage's stride s when it is a power of two (shift instead of an integer division), else -1
+    int vec2;               // Whisper prologue may use 64-bit loads (8-byte aligned rows, even hop and frame offset)
 };
 
+// physical position of element i in a ping-pong buffer (one pad slot per 16 elements)
+__device__ __forceinline__ int gph(int i) { return i + (i >> 4); }
+__host__ __device__ inline int generic_buf_elems(int nf) { return ((nf + (nf >> 4) + 2) + 1) & ~1; }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, fmaf(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// forward 4-point DFT, natural order out
+__device__ __forceinline__ void gdft4(float2 b0, float2 b1, float2 b2, float2 b3, float2& y0, float2& y1, float2& y2, float2& y3) {
+    const float2 s02 = cadd(b0, b2), d02 = csub(b0, b2), s13 = cadd(b1, b3), d13 = csub(b1, b3);
+    y0 = cadd(s02, s13);
+    y1 = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+    y2 = csub(s02, s13);
+    y3 = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+}
+
+// forward 8-point DFT in place, natural order (one radix-2 layer with W_8^k, then two 4-point DFTs)
+__device__ __forceinline__ void gdft8(float2 (&a)[8]) {
+    constexpr float c = 0.70710678118654752f;
+    const float2 t0 = cadd(a[0], a[4]), t4 = csub(a[0], a[4]);
+    const float2 t1 = cadd(a[1], a[5]), d1 = csub(a[1], a[5]);
+    const float2 t2 = cadd(a[2], a[6]), d2 = csub(a[2], a[6]);
+    const float2 t3 = cadd(a[3], a[7]), d3 = csub(a[3], a[7]);
+    const float2 t5 = make_float2(c * (d1.x + d1.y), c * (d1.y - d1.x));    // d1 W_8
+    const float2 t6 = make_float2(d2.y, -d2.x);                             // d2 W_8^2 = -i d2
+    const float2 t7 = make_float2(c * (d3.y - d3.x), -c * (d3.x + d3.y));   // d3 W_8^3
+    gdft4(t0, t1, t2, t3, a[0], a[2], a[4], a[6]);
+    gdft4(t4, t5, t6, t7, a[1], a[3], a[5], a[7]);
+}
+
+// forward R-point DFT for R = 3, 5 from compile-time roots of unity (r-term sums in registers)
+// (cos, sin)(2 pi e / R) as compile-time constants (the loops below are fully unrolled, so `e` is a constant)
+template <int R> __host__ __device__ constexpr float groot_cos(int e) {
+    return R == 3 ? (e == 0 ? 1.f : -0.5f)
+                  : (e == 0 ? 1.f : (e == 1 || e == 4) ? 0.30901699437494742f : -0.80901699437494742f);
+}
+template <int R> __host__ __device__ constexpr float groot_sin(int e) {
+    return R == 3 ? (e == 0 ? 0.f : e == 1 ? 0.86602540378443865f : -0.86602540378443865f)
+                  : (e == 0 ? 0.f : e == 1 ? 0.95105651629515357f : e == 2 ? 0.58778525229247313f
+                                   : e == 3 ? -0.58778525229247313f : -0.95105651629515357f);
+}
+template <int R>
+__device__ __forceinline__ void gdft_small(const float2 (&a)[R], float2 (&y)[R]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        float2 acc = a[0];
+#pragma unroll
+        for (int i = 1; i < R; ++i) {
+            const int e = (i * j) % R;                       // W_R^e = (cos, -sin)(2 pi e / R)
+            const float wc = groot_cos<R>(e), ws = -groot_sin<R>(e);
+            acc.x = fmaf(a[i].x, wc, fmaf(-a[i].y, ws, acc.x));
+            acc.y = fmaf(a[i].x, ws, fmaf(a[i].y, wc, acc.y));
+        }
+        y[j] = acc;
+    }
+}
 
 __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, const GParams g) {
     extern __shared__ __align__(16) unsigned char gsm[];
@@ -56,8 +116,9 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
     const bool packed = Nf != N;
     const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* s_tw = reinterpret_cast<float2*>(gsm);
-    float2* buf0 = s_tw + N + (size_t)warp * 2 * Nf;
-    float2* buf1 = buf0 + Nf;
+    const int nfp = generic_buf_elems(Nf);
+    float2* buf0 = s_tw + N + (size_t)warp * 2 * nfp;
+    float2* buf1 = buf0 + nfp;
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_tw[i] = g.tw[i];
     __syncthreads();
 
@@ -99,8 +160,18 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
             const long long ia = sa + n;   // src/mel.rs:696-706: wave[i] = x[i] - c x[i-1] (i >= 1), zero outside the clip
             return (ia >= 0 && ia < len) ? fmaf(-p.preemph, at(ia - 1), at(ia)) * w : 0.f;
         };
-        if (packed) for (int n = lane; n < Nf; n += 32) buf0[n] = make_float2(sample(2 * n), sample(2 * n + 1));
-        else        for (int n = lane; n < Nf; n += 32) buf0[n] = make_float2(sample(n), 0.f);
+        if (packed && g.mode == 0 && g.vec2 && sa + N <= len) {   // whole frame inside the clip, 8-byte aligned pairs
+            const float2* x2 = reinterpret_cast<const float2*>(x + sa);
+            const float2* w2 = reinterpret_cast<const float2*>(g.window);
+            for (int n = lane; n < Nf; n += 32) {
+                const float2 v = __ldg(x2 + n), w = __ldg(w2 + n);
+                buf0[gph(n)] = make_float2(v.x * w.x, v.y * w.y);
+            }
+        } else if (packed) {
+            for (int n = lane; n < Nf; n += 32) buf0[gph(n)] = make_float2(sample(2 * n), sample(2 * n + 1));
+        } else {
+            for (int n = lane; n < Nf; n += 32) buf0[gph(n)] = make_float2(sample(n), 0.f);
+        }
         __syncwarp();
 
         // ------------------------------------------------------------------ Stockham autosort FFT (decimation in frequency)
@@ -111,44 +182,85 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
         int ncur = Nf, s = 1;
         for (int st = 0; st < g.n_stages; ++st) {
             const int r = g.radix[st], m = ncur / r, sh = g.sshift[st];
-            if (r == 4) {
+            const int sm = s * m;   // input stride between the r legs of a butterfly
+            if (r == 8) {
+                for (int bfly = lane; bfly < Nf / 8; bfly += 32) {
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
+                    const int bi = q + s * pp, bo = q + s * 8 * pp;
+                    float2 a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = src[gph(bi + sm * i)];
+                    gdft8(a);
+                    if (m > 1) {   // W^(j p s), j = 1..7, from three table reads
+                        const int tws = pp * s * tmul;
+                        const float2 w1 = s_tw[tws], w2 = s_tw[2 * tws], w4 = s_tw[4 * tws];
+                        const float2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+                        a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], w3); a[4] = cmul(a[4], w4);
+                        a[5] = cmul(a[5], w5); a[6] = cmul(a[6], w6); a[7] = cmul(a[7], cmul(w4, w3));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[gph(bo + s * j)] = a[j];
+                }
+            } else if (r == 4) {
                 for (int bfly = lane; bfly < Nf / 4; bfly += 32) {
                     const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
-                    const float2* xi = src + q + s * pp;
-                    const float2 a0 = xi[0], a1 = xi[(size_t)s * m], a2 = xi[(size_t)2 * s * m], a3 = xi[(size_t)3 * s * m];
-                    const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
-                    const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y), t3 = make_float2(a1.x - a3.x, a1.y - a3.y);
-                    float2* yo = dst + q + (size_t)s * 4 * pp;
-                    const int tws = pp * s * tmul;
-                    yo[0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-                    yo[s] = cmul(make_float2(t1.x + t3.y, t1.y - t3.x), s_tw[tws]);          // a0 - i a1 - a2 + i a3
-                    yo[2 * s] = cmul(make_float2(t0.x - t2.x, t0.y - t2.y), s_tw[2 * tws]);
-                    yo[3 * s] = cmul(make_float2(t1.x - t3.y, t1.y + t3.x), s_tw[3 * tws]);  // a0 + i a1 - a2 - i a3
+                    const int bi = q + s * pp, bo = q + s * 4 * pp;
+                    float2 y0, y1, y2, y3;
+                    gdft4(src[gph(bi)], src[gph(bi + sm)], src[gph(bi + 2 * sm)], src[gph(bi + 3 * sm)], y0, y1, y2, y3);
+                    if (m > 1) {
+                        const int tws = pp * s * tmul;
+                        y1 = cmul(y1, s_tw[tws]); y2 = cmul(y2, s_tw[2 * tws]); y3 = cmul(y3, s_tw[3 * tws]);
+                    }
+                    dst[gph(bo)] = y0; dst[gph(bo + s)] = y1; dst[gph(bo + 2 * s)] = y2; dst[gph(bo + 3 * s)] = y3;
                 }
             } else if (r == 2) {
                 for (int bfly = lane; bfly < Nf / 2; bfly += 32) {
                     const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
-                    const float2 a0 = src[q + s * pp], a1 = src[q + s * (pp + m)];
-                    float2* yo = dst + q + (size_t)s * 2 * pp;
-                    yo[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
-                    yo[s] = cmul(make_float2(a0.x - a1.x, a0.y - a1.y), s_tw[pp * s * tmul]);
+                    const float2 a0 = src[gph(q + s * pp)], a1 = src[gph(q + s * (pp + m))];
+                    const int bo = q + s * 2 * pp;
+                    dst[gph(bo)] = cadd(a0, a1);
+                    dst[gph(bo + s)] = cmul(csub(a0, a1), s_tw[pp * s * tmul]);
+                }
+            } else if (r == 3) {
+                for (int bfly = lane; bfly < Nf / 3; bfly += 32) {
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
+                    const int bi = q + s * pp, bo = q + s * 3 * pp, tws = pp * s * tmul;
+                    float2 a[3], y[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a[i] = src[gph(bi + sm * i)];
+                    gdft_small<3>(a, y);
+                    dst[gph(bo)] = y[0];
+#pragma unroll
+                    for (int j = 1; j < 3; ++j) dst[gph(bo + s * j)] = cmul(y[j], s_tw[j * tws]);
+                }
+            } else if (r == 5) {
+                for (int bfly = lane; bfly < Nf / 5; bfly += 32) {
+                    const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
+                    const int bi = q + s * pp, bo = q + s * 5 * pp, tws = pp * s * tmul;
+                    float2 a[5], y[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) a[i] = src[gph(bi + sm * i)];
+                    gdft_small<5>(a, y);
+                    dst[gph(bo)] = y[0];
+#pragma unroll
+                    for (int j = 1; j < 5; ++j) dst[gph(bo + s * j)] = cmul(y[j], s_tw[j * tws]);
                 }
             } else {   // any other prime factor: one (butterfly, output) pair per work item
                 const int wr = N / r;   // W_r^e = W_N^(e N/r)
                 for (int e = lane; e < Nf; e += 32) {
                     const int bfly = e / r, j = e - bfly * r;
                     const int pp = sh >= 0 ? bfly >> sh : bfly / s, q = bfly - pp * s;
-                    const float2* xi = src + q + s * pp;
-                    float2 acc = xi[0];
+                    const int bi = q + s * pp;
+                    float2 acc = src[gph(bi)];
                     int idx = 0;
                     for (int i = 1; i < r; ++i) {
                         idx += j;
                         if (idx >= r) idx -= r;
-                        const float2 v = xi[(size_t)s * m * i], w = s_tw[idx * wr];
+                        const float2 v = src[gph(bi + sm * i)], w = s_tw[idx * wr];
                         acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
                         acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
                     }
-                    dst[q + (size_t)s * ((size_t)r * pp + j)] = cmul(acc, s_tw[pp * j * s * tmul]);
+                    dst[gph(q + s * (r * pp + j))] = cmul(acc, s_tw[pp * j * s * tmul]);
                 }
             }
             __syncwarp();
@@ -161,14 +273,14 @@ __global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, c
         for (int k = lane; k <= nb; k += 32) {
             float xr, xi;
             if (packed) {   // X[k] = E[k] + W_N^k O[k]
-                const float2 zk = src[k == Nf ? 0 : k], zm = src[(k == 0 || k == Nf) ? 0 : Nf - k];
+                const float2 zk = src[gph(k == Nf ? 0 : k)], zm = src[gph((k == 0 || k == Nf) ? 0 : Nf - k)];
                 const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
                 const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
                 const float2 w = k == Nf ? make_float2(-1.f, 0.f) : s_tw[k];
                 xr = er + (orr * w.x - oi * w.y);
                 xi = ei + fmaf(orr, w.y, oi * w.x);
             } else {
-                xr = src[k].x; xi = src[k].y;
+                xr = src[gph(k)].x; xi = src[gph(k)].y;
             }
             float e = fmaf(xr, xr, xi * xi);
             if (!g.use_power) e = sqrtf(e);   // src/fbank.rs:197-203
