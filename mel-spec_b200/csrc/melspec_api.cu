@@ -624,8 +624,24 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
     g.vec2 = ((uintptr_t)p.pcm % 8 == 0) && (p.clip_stride % 2 == 0) && (c.hop % 2 == 0) && (p.frame_offset % 2 == 0) && (c.fft % 2 == 0);
     const size_t budget = 220 * 1024, per_warp = (size_t)16 * generic_buf_elems(g.Nf), tw_bytes = (size_t)8 * c.fft;
-    int nw = (int)std::min<size_t>(8, (budget - tw_bytes) / per_warp);
-    if (nw < 1) nw = 1;
+    // warps per CTA: the count that puts the most warps on an SM (the kernel is latency bound: every FFT stage is a
+    // round trip through shared memory), given one twiddle table per CTA, 227 KB of shared memory and 64 K registers per SM
+    cudaFuncAttributes fa;
+    MS_CUDA(cudaFuncGetAttributes(&fa, melspec_generic_kernel));
+    const int reg_warps = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 32));
+    int warps_at[17] = {0};
+    for (int cand = 1; cand <= 16; ++cand) {
+        const size_t need = tw_bytes + per_warp * cand + 1024;   // + the per-CTA reservation
+        if (need > budget + 1024) break;
+        const int ctas = (int)std::min<size_t>(32, (228 * 1024) / need);
+        warps_at[cand] = std::min(std::min(cand * ctas, 64), reg_warps / cand * cand);
+    }
+    // 8-warp CTAs by default (neighbouring frames of a CTA share their PCM in L1; measured: smaller CTAs lose more than their
+    // extra warps gain); another size only where it puts clearly more warps on the SM (large transforms)
+    int nw = 8;
+    while (nw > 1 && warps_at[nw] == 0) --nw;
+    for (int cand = 1; cand <= 16; ++cand)
+        if (warps_at[cand] * 100 > warps_at[nw] * (cand < nw ? 140 : 115)) nw = cand;
     const size_t smem = tw_bytes + per_warp * nw;
     MS_CUDA(cudaFuncSetAttribute(melspec_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int per_sm = 1;

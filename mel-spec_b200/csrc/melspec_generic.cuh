@@ -110,7 +110,7 @@ __device__ __forceinline__ void gdft_small(const float2 (&a)[R], float2 (&y)[R])
     }
 }
 
-__global__ void __launch_bounds__(256) melspec_generic_kernel(const KParams p, const GParams g) {
+__global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, const GParams g) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int N = g.N, Nf = g.Nf, tmul = N / Nf;   // W_Nf^k = W_N^(tmul k)
     const bool packed = Nf != N;

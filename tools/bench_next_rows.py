@@ -104,6 +104,17 @@ def main():
             clips * (4 * n + 4 * nm * Fg), {"frames_per_clip": Fg})
         g.close()
         del og
+    # ---- plan 512 in its three modes at the cfg2 / cfg3 size (where the Kaldi prologue and CMN cost show)
+    for name, mk, nm in (("plan 512: Whisper fft 512 hop 160 80 mel (golden-file configuration)", lambda: ms.CudaMelSpectrogram(512, 160, 16000.0, 80), 80),
+                         ("plan 512: Kaldi fbank 80 bins, CMN off", lambda: ms.Fbank(ms.FbankConfig(apply_cmn=False)), 80),
+                         ("plan 512: Kaldi fbank 80 bins + CMN (cfg3)", lambda: ms.Fbank(ms.FbankConfig()), 80)):
+        hh = mk()
+        Fh = hh.num_frames(n)
+        oh = torch.empty((clips, Fh, nm), dtype=torch.float32, device=dev)
+        t = timeit(lambda: hh.compute_device(x, clips, n, n, oh, stream=st), args.steps, st)
+        row(name + ", 1024 x 10 s", t, clips * Fh, "frames/s", clips * (4 * n + 4 * nm * Fh), {"frames_per_clip": Fh})
+        hh.close()
+        del oh
     fb8 = ms.Fbank(ms.FbankConfig(sample_rate=8000.0, num_mel_bins=40))
     Fk = fb8.num_frames(n)
     ok = torch.empty((clips, Fk, 40), dtype=torch.float32, device=dev)
