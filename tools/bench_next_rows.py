@@ -105,7 +105,8 @@ def main():
         g.close()
         del og
     # ---- plan 512 in its three modes at the cfg2 / cfg3 size (where the Kaldi prologue and CMN cost show)
-    for name, mk, nm in (("plan 512: Whisper fft 512 hop 160 80 mel (golden-file configuration)", lambda: ms.CudaMelSpectrogram(512, 160, 16000.0, 80), 80),
+    for name, mk, nm in (("plan 400: Whisper large-v3 style, fft 400 hop 160 128 mel", lambda: ms.CudaMelSpectrogram(400, 160, 16000.0, 128), 128),
+                         ("plan 512: Whisper fft 512 hop 160 80 mel (golden-file configuration)", lambda: ms.CudaMelSpectrogram(512, 160, 16000.0, 80), 80),
                          ("plan 512: Kaldi fbank 80 bins, CMN off", lambda: ms.Fbank(ms.FbankConfig(apply_cmn=False)), 80),
                          ("plan 512: Kaldi fbank 80 bins + CMN (cfg3)", lambda: ms.Fbank(ms.FbankConfig()), 80)):
         hh = mk()
