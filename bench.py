@@ -154,6 +154,27 @@ def run_reference(args, rank):
     }))
 
 
+def bind_to_gpu_cpus(index: int):
+    """N > 1: pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is allocated, so that
+    the end-to-end leg's staging buffers are first-touched on the GPU's own NUMA node (every rank otherwise lands wherever
+    the scheduler puts it and the H2D / D2H copies of several ranks share one socket's memory and inter-socket links).
+    Not used at N = 1, where the CPU baseline needs all host cores.  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline(workload):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -211,6 +232,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     ms.build()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -342,6 +364,8 @@ def main():
         }
         if gather is not None:
             line["gather"] = gather
+        if numa is not None:
+            line["config"]["host_affinity"] = f"each rank bound to the {numa} CPUs local to its GPU (NVML) before pinned allocation"
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))
