@@ -77,3 +77,34 @@ def test_no_cpu_fallback(m):
     with pytest.raises(m.CudaError) as ei:
         m.CudaMelSpectrogram(400, 160, 16000.0, 80)
     assert ei.value.kind == "Unavailable" and "no CPU fallback" in str(ei.value)
+
+
+def test_general_sizes_host_logic(m):
+    """Device-free host logic for configurations that run on the general plan: filterbanks and frame counts for arbitrary
+    fft_size / hop / sample rate / mel scale match the oracle (src/mel.rs:547-643, src/fbank.rs:253-313, src/stft.rs:153-157)."""
+    from mel_spec_b200._lib import MelspecConfig
+    from mel_spec_b200 import api
+    L = m.lib()
+    for sr, fft, n_mels in ((16000, 1024, 128), (8000, 256, 40), (22050, 441, 64), (48000, 8192, 80), (16000, 16, 4), (16000, 251, 40)):
+        assert np.abs(m.mel(sr, fft, n_mels) - o.slaney_mel_filterbank(sr, fft, n_mels)).max() <= 1e-12
+    for kw in (dict(sample_rate=8000.0, num_mel_bins=40), dict(sample_rate=44100.0, num_mel_bins=64),
+               dict(low_freq=100.0, high_freq=7000.0, num_mel_bins=23, sample_rate=22050.0)):
+        fc = m.FbankConfig(**kw)
+        want = o.kaldi_mel_filterbank(fc.sample_rate, fc.fft_size(), fc.num_mel_bins, fc.low_freq,
+                                      fc.high_freq if fc.high_freq else fc.sample_rate / 2)
+        assert np.abs(m.kaldi_mel_filterbank(fc) - want).max() <= 1e-12
+    # NeMo bank with HTK scale, no area normalisation, band limits
+    bc = m.BatchLogMelConfig(n_fft=1024, win_length=800, hop_length=200, n_mels=128, htk=True, norm=False, f_min=50.0, f_max=7600.0)
+    cfg = api._nemo_cfg(bc)
+    out = np.zeros((128, 513), dtype=np.float64)
+    assert L.melspec_build_filterbank(C.byref(cfg), out.ctypes.data_as(C.POINTER(C.c_double)), out.size) == 0
+    assert np.abs(out - o.general_mel_filterbank(16000.0, 1024, 128, 50.0, 7600.0, True, False)).max() <= 1e-12
+    # frame counts: Whisper (len - N)/hop + 1, NeMo centred len/hop + 1 or (len - n_fft)/hop + 1
+    w = api._whisper_cfg(1024, 256, 128, 16000.0)
+    for n in (0, 1023, 1024, 1279, 1280, 100000):
+        assert L.melspec_num_frames_cfg(C.byref(w), n) == o.num_frames(n, 1024, 256)
+    for center in (True, False):
+        c2 = api._nemo_cfg(m.BatchLogMelConfig(n_fft=768, win_length=601, hop_length=123, center=center))
+        for n in (0, 1, 767, 768, 50000):
+            want = 0 if n == 0 else o.batch_num_frames(n, 768, 123, center)
+            assert L.melspec_num_frames_cfg(C.byref(c2), n) == want
