@@ -1256,6 +1256,36 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
         return v > 0 ? v : (int64_t)32;
     }();
     const int64_t target = chunk_mb << 20;
+    // One long clip (the reference's own call shape, `compute_mel_spectrogram(&[f32])`, on minutes to hours of audio): cut it
+    // along time into pieces of whole warp tiles, so that the H2D copy of piece i+1, the kernel of piece i and the D2H copy
+    // of piece i-1 overlap like the chunks of a batch do.  Whisper frames depend on their own samples only, so a piece is
+    // just a shorter clip starting at frame f0 (its samples [f0 hop, (f1-1) hop + N) are re-read with their 240-sample
+    // halo); pieces are multiples of 12 frames, which keeps every frame in the same slot of its transform as in the
+    // unsplit launch: the result is bit-identical.  Kaldi (CMN, look-back) and NeMo (centre padding) are not cut.
+    const int64_t piece_bytes = std::min<int64_t>(target, 8 << 20);   // 8 MB pieces: short ramp-up and tail, still DMA-efficient
+    if (h->cfg.frontend == MELSPEC_FRONTEND_WHISPER && n_clips == 1 && n_samples * 4 >= 2 * piece_bytes) {
+        const Resolved& c = h->cfg;
+        int64_t pf = std::max<int64_t>(12, piece_bytes / 4 / c.hop / 12 * 12);   // frames per piece
+        const int64_t psamples = ((pf - 1) * c.hop + c.fft + 3) / 4 * 4;
+        int32_t rc = ensure_host_resources(h, (size_t)psamples * 4, (size_t)pf * c.n_mels * 4);
+        if (rc) return rc;
+        int slot = 0;
+        for (int64_t f0 = 0; f0 < F; f0 += pf, slot = (slot + 1) % 3) {
+            const int64_t nf = std::min(pf, F - f0);
+            const int64_t s0 = f0 * c.hop, ns = (nf - 1) * c.hop + c.fft;
+            cudaStream_t st = h->streams[slot];
+            MS_CUDA(cudaMemcpyAsync(h->d_slot_pcm[slot], h_pcm + s0, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+            rc = launch_device(h, h->d_slot_pcm[slot], 1, psamples, ns, nf, nullptr, h->d_slot_out[slot], 0, layout, st);
+            if (rc) return rc;
+            if (layout == MELSPEC_LAYOUT_FRAME_MAJOR)
+                MS_CUDA(cudaMemcpyAsync(h_out + f0 * c.n_mels, h->d_slot_out[slot], (size_t)nf * c.n_mels * 4, cudaMemcpyDeviceToHost, st));
+            else   // mel-major: the piece's [n_mels][nf] block goes into columns [f0, f0 + nf) of the [n_mels][F] image
+                MS_CUDA(cudaMemcpy2DAsync(h_out + f0, (size_t)F * 4, h->d_slot_out[slot], (size_t)nf * 4, (size_t)nf * 4,
+                                          (size_t)c.n_mels, cudaMemcpyDeviceToHost, st));
+        }
+        for (int i = 0; i < 3; ++i) MS_CUDA(cudaStreamSynchronize(h->streams[i]));
+        return MELSPEC_OK;
+    }
     int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
     per_chunk = std::min(per_chunk, n_clips);
     if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);

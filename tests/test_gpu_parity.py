@@ -441,3 +441,27 @@ def test_nemo_per_feature_normalisation(m, jfk):
     v = got[:, :1101]
     assert np.abs(v.mean(axis=1)).max() < 1e-4 and np.abs(v.std(axis=1, ddof=1) - 1.0).max() < 1e-3
     fe.close()
+
+
+def test_long_single_clip_host_call_is_pipelined_and_identical(m, torch):
+    """`compute_mel_spectrogram(&[f32])` on several minutes of audio (src/cuda.rs:88-101): the host call cuts one long clip
+    along time into pieces of whole warp tiles and pipelines H2D / kernel / D2H; the frames must equal the unsplit device
+    launch bit for bit, in both layouts, for a length that is not a multiple of anything."""
+    n = 16000 * 60 * 6 + 1234                                   # 6 minutes: 23 MB of PCM -> three 8 MB pieces
+    x = np.concatenate([o.synth_clip(i, 160000) for i in range(37)])[:n]
+    for fft, hop in ((400, 160), (512, 160), (1024, 256)):
+        h = m.CudaMelSpectrogram(fft, hop, 16000.0, 80)
+        xd = torch.from_numpy(x).cuda()
+        f = h.num_frames(n)
+        for layout in (0, 1):
+            shape = (f, 80) if layout == 0 else (80, f)
+            dev = torch.empty(shape, dtype=torch.float32, device="cuda")
+            h.compute_device(xd, 1, n, n, dev, layout=layout)
+            torch.cuda.synchronize()
+            host = h.compute_host(x, layout=layout)
+            assert host.shape == shape
+            assert np.array_equal(host, dev.cpu().numpy()), (fft, hop, layout)
+        want = o.whisper_mel_batch(x[:160 * 3000 + fft], fft, hop, 80, 16000.0)
+        got = h.compute_host(x)[:want.shape[0]]
+        assert np.abs(got - want).max() <= WHISPER_TOL
+        h.close()

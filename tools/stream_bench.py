@@ -37,5 +37,13 @@ for chunk in (16000, 160000, 960000, n):
     assert got == frames, (got, frames)
     res[f"push_{chunk}_samples"] = {"frames_per_s": got / dt, "seconds": dt, "x_realtime": 3600.0 / dt}
     L.melspec_stream_destroy(s)
+# the reference's own call shape on the whole hour: one blocking host call (time-split pipeline inside the library)
+fb = h.num_frames(n)
+outb = torch.empty((fb, 80), dtype=torch.float32).pin_memory()
+for rep in range(3):
+    t0 = time.perf_counter()
+    h.compute_host_raw(x.data_ptr(), 1, n, n, outb.data_ptr())
+    dt = time.perf_counter() - t0
+res["one_compute_host_call"] = {"frames_per_s": fb / dt, "seconds": dt, "x_realtime": 3600.0 / dt}
 print(json.dumps({"workload": "BASELINE configs[4]: 1 h @16 kHz stream, Whisper 80-mel fft400 hop160, pinned host buffers",
                   "frames": frames, "results": res}))
