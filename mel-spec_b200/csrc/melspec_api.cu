@@ -1289,6 +1289,12 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
     per_chunk = std::min(per_chunk, n_clips);
     if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
+    if (h->cfg.frontend == MELSPEC_FRONTEND_KALDI && h->cfg.cmn && n_clips >= h->num_sms && per_chunk < h->num_sms) {
+        // keep every chunk at one clip per SM or more, so that all of them take the kernel with CMN fused in (faster, and
+        // the same arithmetic as a device-resident launch of the whole batch: results are bit-identical)
+        const int64_t k = n_clips / h->num_sms;
+        per_chunk = (n_clips + k - 1) / k;
+    }
     int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * clip_out * 4);
     if (rc) return rc;
     int slot = 0;
