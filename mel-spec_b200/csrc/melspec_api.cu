@@ -901,6 +901,11 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
     h->num_sms = prop.multiProcessorCount;
     h->plan = plan;
     build_filterbank(r, h->dense);
+    if (h->plan != 1) {   // the specialised kernels never form bin 0: a bank with a non-zero DC column runs on the general plan
+        const int nbins = r.fft / 2 + 1;
+        for (int m = 0; m < r.n_mels; ++m)
+            if (h->dense[(size_t)m * nbins] != 0.0) { h->plan = 1; break; }
+    }
     rc = build_tables(h);
     if (rc) {
         melspec_destroy(h);
