@@ -161,6 +161,7 @@ NEMO_CASES = [
     dict(n_fft=1024, win_length=800, hop_length=200, n_mels=128, htk=True, norm=False, f_min=50.0, f_max=7600.0,
          normalize_per_feature=True, preemphasis=0.97),
     dict(n_fft=768, win_length=601, hop_length=123, n_mels=96),                 # odd window, 2^8 * 3
+    dict(n_fft=512, win_length=400, hop_length=160, n_mels=40, f_min=-300.0),   # bank with a non-zero DC column -> general plan
 ]
 
 
@@ -192,3 +193,21 @@ def test_generic_interleaved_image_and_tga(m, jfk):
         assert np.all(img[:, f:] == 0.0)
         assert tga == o.tga_8bit_data(img.reshape(-1), n_mels), "device quantiser bytes == quant.rs arithmetic on the same f32 image"
     h.close()
+
+
+def test_reference_goldens_hold_on_the_general_plan():
+    """MELSPEC_FORCE_GENERIC=1 routes every configuration through the general kernel: the reference's own fixtures
+    (rust_jfk_golden.npy at fft 512, quantized_mel_golden.tga at fft 400, the Kaldi and NeMo contracts, the C++ host mirror's
+    restatement of the reference tests) must hold there too — a second, independent implementation of the same transforms.
+    Run in a child process because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MELSPEC_FORCE_GENERIC="1")
+    sel = "golden or jfk or readme or reference_cuda or nemo_shape or ringbuffer or streaming_matches"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"),
+                          os.path.join(root, "tests", "test_formats.py"), os.path.join(root, "tests", "test_cpp_host.py"),
+                          "-m", "gpu", "-q", "-x", "-k", sel], capture_output=True, text=True, env=env, cwd=root, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
