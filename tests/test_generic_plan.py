@@ -205,7 +205,7 @@ def test_reference_goldens_hold_on_the_general_plan():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MELSPEC_FORCE_GENERIC="1")
-    sel = "golden or jfk or readme or reference_cuda or nemo_shape or ringbuffer or streaming_matches"
+    sel = "golden or jfk or readme or reference_cuda or nemo_shape or ringbuffer or streaming_matches or cpp_host_mirror_reference"
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"),
                           os.path.join(root, "tests", "test_formats.py"), os.path.join(root, "tests", "test_cpp_host.py"),
                           "-m", "gpu", "-q", "-x", "-k", sel], capture_output=True, text=True, env=env, cwd=root, timeout=900)
