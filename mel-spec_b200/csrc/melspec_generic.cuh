@@ -57,8 +57,9 @@ __device__ __forceinline__ int gph(int i) { return i + (i >> 4); }
 __host__ __device__ inline int generic_buf_elems(int nf) { return ((nf + (nf >> 4) + 2) + 1) & ~1; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, fmaf(a.x, b.y, a.y * b.x)); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as one packed FADD2 (sm_100): half the issue slots of two scalar FADDs
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
 
 // forward 4-point DFT, natural order out
 __device__ __forceinline__ void gdft4(float2 b0, float2 b1, float2 b2, float2 b3, float2& y0, float2& y1, float2& y2, float2& y3) {
@@ -270,13 +271,14 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
 
         // ------------------------------------------------------------------ power (or magnitude) of bins 0..N/2 -> pw[k]
         float* pw = reinterpret_cast<float*>(dst);
-        for (int k = lane; k <= nb; k += 32) {
+        // bins 0 .. N/2 - 1 (k = lane + 32 i); the Nyquist bin of an even N, X[N/2] = Re Z[0] - Im Z[0], is written by lane 0
+        for (int k = lane; k < (packed ? nb : nb + 1); k += 32) {
             float xr, xi;
             if (packed) {   // X[k] = E[k] + W_N^k O[k]
-                const float2 zk = src[gph(k == Nf ? 0 : k)], zm = src[gph((k == 0 || k == Nf) ? 0 : Nf - k)];
+                const float2 zk = src[gph(k)], zm = src[gph(k == 0 ? 0 : Nf - k)];
                 const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
                 const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
-                const float2 w = k == Nf ? make_float2(-1.f, 0.f) : s_tw[k];
+                const float2 w = s_tw[k];
                 xr = er + (orr * w.x - oi * w.y);
                 xi = ei + fmaf(orr, w.y, oi * w.x);
             } else {
@@ -285,6 +287,11 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
             float e = fmaf(xr, xr, xi * xi);
             if (!g.use_power) e = sqrtf(e);   // src/fbank.rs:197-203
             pw[k] = e;
+        }
+        if (packed && lane == 0) {
+            const float2 z0 = src[0];
+            const float xn = z0.x - z0.y;
+            pw[nb] = g.use_power ? xn * xn : fabsf(xn);
         }
         __syncwarp();
 
