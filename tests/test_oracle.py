@@ -149,3 +149,15 @@ def test_nemo_oracle_f32_pipeline_distance(jfk):
     b = o.batch_log_mel(jfk[:48000], n_mels=128, preemphasis=0.97, log_zero_guard=2.0 ** -24, dtype=np.float32)
     assert a.shape == b.shape == (128, 301)
     assert np.abs(a - b).max() < 5e-3
+
+
+@pytest.mark.parametrize("fft,hop,n_mels", [(1024, 256, 128), (480, 160, 80), (441, 147, 64), (251, 100, 40), (256, 64, 40)])
+def test_c_oracle_matches_numpy_oracle_at_general_sizes(fft, hop, n_mels):
+    """The two restatements of src/stft.rs:89-169 + src/mel.rs agree at the sizes the general plan is checked on (the C
+    one is the timed CPU baseline, the numpy one the parity checker): own mixed-radix FFT vs numpy's pocketfft."""
+    import oracle_c as oc
+    oc.build()
+    x = np.stack([o.synth_clip(i, 30000) for i in range(2)])
+    a = oc.whisper_batch(x, fft, hop, n_mels, 16000.0, threads=2)
+    b = np.stack([o.whisper_mel_batch(x[i], fft, hop, n_mels, 16000.0) for i in range(2)])
+    assert a.shape == b.shape and np.abs(a - b).max() <= 1e-6
