@@ -145,7 +145,9 @@ int32_t melspec_filterbank(const melspec_handle* h, double* out, int64_t capacit
  *   d_out            frame-major: [n_clips][F][n_mels], mel-major: [n_clips][n_mels][F], F = melspec_num_frames(n_samples)
  *                    (NeMo frontend: mel-major [n_clips][n_mels][melspec_padded_frames(n_samples)], padding columns zeroed);
  *                    clip r at d_out + r*out_clip_stride (floats; 0 = dense F*n_mels).  Frames past a short clip's
- *                    own frame count are left untouched.
+ *                    own frame count are left untouched (Whisper, Kaldi) or zero like the pad_to columns (NeMo, where
+ *                    per-feature normalisation then runs over each clip's own valid frames; ragged NeMo batches run on
+ *                    the general kernel).
  * Fast path (TMA bulk copies) needs 16-byte aligned d_pcm/d_out, clip_stride % 4 == 0 and n_samples % 4 == 0;
  * otherwise a slower cooperative-copy path of the same kernel is used (results identical).
  */

@@ -588,7 +588,8 @@ int32_t launch_post_kernels(melspec_handle* h, const melspec::KParams& p, int64_
     if (c.frontend == MELSPEC_FRONTEND_NEMO && c.norm_feat) {
         const long long rows = (long long)n_clips * c.n_mels;
         melspec_featnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_out, p.out_clip_stride, p.out_row_stride,
-                                                                          p.frames_per_clip, c.n_mels, (int)rows);
+                                                                          p.frames_per_clip, c.n_mels, (int)rows, d_lens, p.n_samples,
+                                                                          c.hop, c.fft, c.center);
         MS_CUDA(cudaGetLastError());
         h->launches += 1;
     }
@@ -619,7 +620,7 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
         st *= h->radices[i];
     }
     g.mode = c.frontend == MELSPEC_FRONTEND_KALDI ? 1 : c.frontend == MELSPEC_FRONTEND_NEMO ? 2 : 0;
-    g.use_power = c.use_power; g.use_log = c.use_log;
+    g.use_power = c.use_power; g.use_log = c.use_log; g.center = c.center;
     g.n_units = (long long)p.frames_per_clip * n_clips;
     // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
     g.vec2 = ((uintptr_t)p.pcm % 8 == 0) && (p.clip_stride % 2 == 0) && (c.hop % 2 == 0) && (p.frame_offset % 2 == 0) && (c.fft % 2 == 0);
@@ -671,7 +672,6 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         return fail(MELSPEC_ERR_UNSUPPORTED, "the Kaldi frontend produces (T, n_mels) frame-major output only");
     if (nemo && layout != MELSPEC_LAYOUT_MEL_MAJOR)
         return fail(MELSPEC_ERR_UNSUPPORTED, "the NeMo frontend produces (n_mels, frames) feature-major output only");
-    if (nemo && d_lens) return fail(MELSPEC_ERR_UNSUPPORTED, "per-clip lengths are not supported by the NeMo frontend yet");
     const int64_t row_stride = row_stride_override > 0 ? row_stride_override : nemo ? padded_frames_for(c, n_samples) : frames_per_clip;
     const int fpw = h->plan == 400 ? p400::FPW : h->plan == 512 ? p512::FPW : 2;
     KParams p{};
@@ -702,7 +702,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
-    if (h->plan == 1) return launch_generic(h, p, n_clips, d_lens, d_out, row_stride, st);
+    // ragged NeMo batches (per-clip lengths) run on the general plan whatever the size: its tables exist for every NeMo handle
+    if (h->plan == 1 || (nemo && d_lens)) return launch_generic(h, p, n_clips, d_lens, d_out, row_stride, st);
     // shared-memory carve-up: [mbarriers | window | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
@@ -907,6 +908,11 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
             if (h->dense[(size_t)m * nbins] != 0.0) { h->plan = 1; break; }
     }
     rc = build_tables(h);
+    if (rc == MELSPEC_OK && h->plan != 1 && r.frontend == MELSPEC_FRONTEND_NEMO) {
+        const int mpl = h->mpl;
+        rc = build_tables_generic(h);   // for ragged batches (d_lens), which run on the general plan
+        h->mpl = mpl;
+    }
     if (rc) {
         melspec_destroy(h);
         return rc;

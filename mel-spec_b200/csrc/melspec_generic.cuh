@@ -50,6 +50,7 @@ struct GParams {
     int radix[kMaxStages];
     int sshift[kMaxStages]; // log2 of the stage's stride s when it is a power of two (shift instead of an integer division), else -1
     int vec2;               // Whisper prologue may use 64-bit loads (8-byte aligned rows, even hop and frame offset)
+    int center;             // NeMo: frames are centred (frame count len/hop + 1), for per-clip lengths
 };
 
 // physical position of element i in a ping-pong buffer (one pad slot per 16 elements)
@@ -131,10 +132,24 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
         const int clip = (int)(u / p.frames_per_clip);
         const int f0 = (int)(u - (long long)clip * p.frames_per_clip);
         int len = p.n_samples;
-        if (g.mode != 2 && p.lens) {
+        if (p.lens) {
             len = min(p.lens[clip], p.n_samples);
-            const int nfr = len < L ? 0 : (len - L) / p.hop + 1;
-            if (f0 >= nfr) continue;   // frames past a short clip's own frame count are left untouched
+            if (g.mode != 2) {
+                const int nfr = len < L ? 0 : (len - L) / p.hop + 1;
+                if (f0 >= nfr) continue;   // frames past a short clip's own frame count are left untouched
+            } else {
+                // NeMo, ragged batch: the clip's own frame count (src/mel.rs:387-395); the columns past it are zeros, like the
+                // pad_to columns of the reference's feature matrix (src/mel.rs:336)
+                const int nfr = len <= 0 ? 0 : g.center ? len / p.hop + 1 : (len < N ? 0 : (len - N) / p.hop + 1);
+                if (f0 >= nfr) {
+                    float* oc0 = p.out + (long long)clip * p.out_clip_stride;
+                    for (int mrow = lane; mrow < p.n_mels; mrow += 32) {
+                        if (p.layout == 0) oc0[(long long)f0 * p.n_mels + mrow] = 0.f;
+                        else oc0[(long long)mrow * p.out_row_stride + f0] = 0.f;
+                    }
+                    continue;
+                }
+            }
         }
         const float* x = p.pcm + (long long)clip * p.clip_stride;
         const long long sa = (long long)f0 * p.hop + p.frame_offset;

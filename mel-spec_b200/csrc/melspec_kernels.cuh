@@ -1304,10 +1304,17 @@ __global__ void __launch_bounds__(512, 2) melspec_cmn_kernel(float* out, long lo
 // x <- (x - mean) / (sqrt(sum (x - mean)^2 / max(F - 1, 1)) + 1e-5) over the F valid frames.  One warp per row
 // (mel-major rows are contiguous), fixed-order lane-strided sums + xor-shuffle tree: deterministic.
 __global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long long out_clip_stride, int row_stride, int frames,
-                                                               int n_mels, int n_rows_total) {
+                                                               int n_mels, int n_rows_total, const int32_t* lens, int n_samples,
+                                                               int hop, int n_fft, int center) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= n_rows_total || frames <= 0) return;
     const int clip = row / n_mels, mel = row - clip * n_mels;
+    if (lens) {   // ragged batch: statistics over the clip's own valid frames (src/mel.rs:387-395, 721-749)
+        const int len = min(lens[clip], n_samples);
+        const int nfr = len <= 0 ? 0 : center ? len / hop + 1 : (len < n_fft ? 0 : (len - n_fft) / hop + 1);
+        frames = min(frames, nfr);
+        if (frames <= 0) return;
+    }
     float* r = out + (long long)clip * out_clip_stride + (long long)mel * row_stride;
     float sum = 0.f;
     for (int f = lane; f < frames; f += 32) sum += r[f];

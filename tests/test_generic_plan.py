@@ -211,3 +211,31 @@ def test_reference_goldens_hold_on_the_general_plan():
                           "-m", "gpu", "-q", "-x", "-k", sel], capture_output=True, text=True, env=env, cwd=root, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+@pytest.mark.parametrize("kw", [dict(n_mels=80, pad_to=16), dict(n_mels=128, preemphasis=0.97, normalize_per_feature=True, pad_to=8),
+                                dict(n_fft=1024, win_length=1024, hop_length=256, n_mels=64, center=False)])
+def test_nemo_ragged_batch(m, torch, kw):
+    """Per-clip lengths for the NeMo frontend (a batch extension of the reference's single-waveform API): every clip must equal
+    `BatchLogMelSpectrogram::compute` of its own samples (src/mel.rs:321-385), zero-padded to the batch's common width."""
+    guard = 2.0 ** -24
+    fe = m.BatchLogMelSpectrogram(m.BatchLogMelConfig(log_zero_guard=guard, **kw))
+    s = 40000
+    lens = [40000, 0, 1, 159, 160, 12345, 39999, 20000, 1023, 1024]
+    rng = np.random.default_rng(21)
+    pcm = (rng.standard_normal((len(lens), s)) * 0.1).astype(np.float32)
+    cols = fe.padded_frames(s)
+    out = torch.full((len(lens), fe.n_mels, cols), float("nan"), dtype=torch.float32, device="cuda")
+    fe.compute_device(torch.from_numpy(pcm).cuda(), len(lens), s, s, out, layout=m.LAYOUT_MEL_MAJOR,
+                      d_lens=torch.tensor(lens, dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    for i, n in enumerate(lens):
+        want = o.batch_log_mel(pcm[i, :n], log_zero_guard=guard, **kw)
+        w = want.shape[1]
+        if w:
+            d = np.abs(got[i][:, :w] - want)
+            assert d.max() <= LN_TOL_MAX and (d <= LN_TOL_BULK).mean() >= 0.995, (i, n, d.max())
+        assert np.all(got[i][:, w:] == 0.0), (i, n)
+    fe.close()
