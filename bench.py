@@ -128,7 +128,7 @@ def run_reference(args, rank):
     import melspec_oracle as o
     import oracle_c as oc
     clips, n_samples, frontend, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1   # the host threads this process may actually use
     sample_clips = max(8 * cores, 128)          # ~0.3-1 s of host work per step with all cores
     pcm = np.stack([o.synth_clip(i, n_samples) for i in range(min(sample_clips, 16))])
     pcm = np.ascontiguousarray(np.tile(pcm, (sample_clips // pcm.shape[0] + 1, 1))[:sample_clips])
@@ -181,7 +181,7 @@ def cpu_baseline(workload):
     import melspec_oracle as o
     import oracle_c as oc
     clips, n_samples, frontend, _ = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1   # the host threads this process may actually use
     nclips = max(cores * 2, 16)
     base = np.stack([o.synth_clip(i, n_samples) for i in range(8)])
     pcm = np.ascontiguousarray(np.tile(base, (nclips // 8 + 1, 1))[:nclips])
