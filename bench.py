@@ -204,42 +204,27 @@ def cpu_baseline(workload):
                       f"(single thread: {v_one:.0f} frames/s)", "single_thread_value": v_one}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--gather", action="store_true",
-                    help="N > 1: also time the optional NCCL all-gather of the output shards (reported separately, never in `value`)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+def copy_ceiling_ms(torch, hx, hout, dx, dout, reps=3):
+    """Copy-only ceiling of the end-to-end call: the same H2D and D2H bytes, pinned, on two streams at once, nothing else."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            dx.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    return best
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-
-    import torch
-    import torch.distributed as dist
-    import mel_spec_b200 as ms
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
-    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
-    ms.build()
-    torch.cuda.set_device(local_rank)
+def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps, sample_clocks):
+    """Device-resident timing (CUDA events on the launch stream, max over ranks) + the end-to-end host call of one workload."""
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    clips, n_samples, frontend, desc = WORKLOADS[args.workload]
+    clips, n_samples, frontend, desc = WORKLOADS[name]
     if frontend == "whisper":
         h = ms.CudaMelSpectrogram(400, 160, 16000.0, 80, device=local_rank)
     else:
@@ -258,16 +243,16 @@ def main():
         step()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = h.launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     with torch.cuda.stream(stream):
         evs[0].record(stream)
-        for i in range(args.steps):
+        for i in range(steps):
             step()
             evs[i + 1].record(stream)
     torch.cuda.synchronize()
@@ -275,7 +260,7 @@ def main():
         dist.barrier()
     launches = h.launch_count() - l0
     total_ms = evs[0].elapsed_time(evs[-1])
-    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -284,11 +269,11 @@ def main():
     # launches (untimed) until the sampler has seen ~1.5 s of this load, so that the clocks line describes the kernel
     # under load rather than an idle GPU.  Nothing of this continuation enters `value`.
     clocks = None
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         t_load = time.perf_counter()
         while time.perf_counter() - t_load < 1.5:
             with torch.cuda.stream(stream):
-                for _ in range(200):
+                for _ in range(200 if n_samples < 300000 else 60):
                     step()
             stream.synchronize()
         clocks = sampler.stop()
@@ -335,37 +320,228 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     same = bool(torch.equal(hout.to(dev), out))
+    # copy-only ceiling of that call, all ranks at once (the same pinned buffers, H2D and D2H concurrently)
+    if world > 1:
+        dist.barrier()
+    scratch = torch.empty_like(x)
+    ceil_ms = copy_ceiling_ms(torch, hx, hout, scratch, out)
+    tc = torch.tensor([ceil_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    ceil_ms = float(tc.item())
+    del scratch
+    # opt-in 16-bit PCM entry: half the H2D bytes, converted in the kernel's prologue (bit-identical to f32 input of the same samples)
+    e2e_i16 = None
+    if frontend == "whisper" and hasattr(h, "compute_host_i16_raw"):
+        hx16 = torch.empty((clips, n_samples), dtype=torch.int16, pin_memory=True)
+        hx16.copy_((x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+        hout16 = torch.empty((clips, F, n_mels), dtype=torch.float32, pin_memory=True)
+        h.compute_host_i16_raw(hx16.data_ptr(), clips, n_samples, n_samples, hout16.data_ptr())
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h.compute_host_i16_raw(hx16.data_ptr(), clips, n_samples, n_samples, hout16.data_ptr())
+        t16 = (time.perf_counter() - t0) / e2e_steps
+        t16t = torch.tensor([t16], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t16t, op=dist.ReduceOp.MAX)
+        t16 = float(t16t.item())
+        # identical to the f32 path fed the same (int16 / 32768) samples
+        xf = (hx16.to(dev).to(torch.float32) / 32768.0).contiguous()
+        ref16 = torch.empty_like(out)
+        h.compute_device(xf, clips, n_samples, n_samples, ref16, stream=stream)
+        torch.cuda.synchronize()
+        e2e_i16 = {"value": world * clips * F / t16, "unit": "frames/s", "ms_per_step": t16 * 1e3,
+                   "h2d_bytes_per_step": clips * n_samples * 2, "d2h_bytes_per_step": clips * F * n_mels * 4,
+                   "matches_f32_path_bit_exact": bool(torch.equal(hout16.to(dev), ref16)),
+                   "entry": "melspec_compute_host_i16 (opt-in: int16 PCM, x/32768 in the kernel prologue)"}
+        del hx16, hout16, xf, ref16
+        h.compute_device(x, clips, n_samples, n_samples, out, stream=stream)
+        torch.cuda.synchronize()
 
+    frames_rank = clips * F
+    ms_per_step = total_ms_max / steps
+    algo_bytes = clips * (4 * n_samples + 4 * n_mels * F)
+    kern_ms = total_ms / steps                       # this rank's own average launch duration
+    peak, peak_kind = measured_peak_gbs()
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic, kname, tsrc = measured_traffic(name)
+    res = {
+        "metric": "mel frames/sec (Whisper 80-mel, 16 kHz)" if frontend == "whisper" else "fbank frames/sec (Kaldi 80-bin, 16 kHz)",
+        "value": world * frames_rank / (ms_per_step * 1e-3), "unit": "frames/s", "ms_per_step": ms_per_step,
+        "config": {"workload": desc, "clips_per_gpu": clips, "samples_per_clip": n_samples, "frames_per_clip": F,
+                   "l2_policy": "inputs larger than L2 (%.0f MB PCM per launch, no flush)" % (clips * n_samples * 4 / 1e6),
+                   "ms_per_step_median_rank0": per[len(per) // 2], "ms_per_step_min_rank0": per[0]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": tsrc, "kernel": kname, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
+                     "note": "kernel is shared-memory-wavefront / fp32-issue bound, not HBM bound (DESIGN.md section 3)"},
+        "e2e": {"value": world * frames_rank / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": clips * n_samples * 4,
+                "d2h_bytes_per_step": clips * F * n_mels * 4, "ms_per_step": e2e_s * 1e3, "matches_device_path": same,
+                "copy_ceiling_ms": ceil_ms, "frac_of_copy_ceiling": ceil_ms / (e2e_s * 1e3),
+                "copy_ceiling_note": "same pinned buffers, H2D + D2H concurrently on two streams, all ranks at once, no kernel"},
+        "gpu_launches": int(launches), "steps": steps,
+    }
+    if e2e_i16 is not None:
+        res["e2e_int16_pcm"] = e2e_i16
+    if clocks is not None:
+        res["clocks"] = clocks
+    if gather is not None:
+        res["gather"] = gather
+    h.close()
+    del x, out, hx, hout
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_stream(torch, ms):
+    """BASELINE configs[4]: one 1-hour 16 kHz stream.  Device-resident: the whole hour as one clip through the fused kernel
+    (roofline).  End to end: the streaming C ABI (overlap-and-save, chunked H2D on a side stream) at three push sizes, and the
+    reference's own call shape (one blocking compute_host call), all from pinned host buffers."""
+    import ctypes as C
+    dev = torch.device("cuda", 0)
+    n = 16000 * 3600
+    g = torch.Generator().manual_seed(5)
+    x = (0.1 * torch.randn(n, generator=g)).pin_memory()
+    h = ms.CudaMelSpectrogram(400, 160, 16000.0, 80)
+    L = ms.lib()
+    F = h.num_frames(n)
+    dx = x.to(dev)
+    dout = torch.empty((F, 80), dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    for _ in range(3):
+        h.compute_device(dx, 1, n, n, dout, stream=st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 20
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for _ in range(steps):
+            h.compute_device(dx, 1, n, n, dout, stream=st)
+        e1.record(st)
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / steps
+    peak, peak_kind = measured_peak_gbs()
+    algo = 4 * n + 4 * 80 * F
+    res = {"config": {"workload": "BASELINE configs[4]: one 1 h @16 kHz stream (57.6 M samples), Whisper 80-mel fft400 hop160",
+                      "l2_policy": "input larger than L2 (230 MB PCM per launch, no flush)"},
+           "value": F / (kms * 1e-3), "unit": "frames/s", "ms_per_step": kms,
+           "roofline": {"bound": "hbm", "achieved": algo / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": algo / (kms * 1e-3) / 1e9 / peak, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo,
+                        "traffic": None, "note": "whole hour device-resident as one clip, one launch"}}
+    frames = n // 160 - 3 + 1      # stream framing: first frame at sample 80, whole hops only (src/rb.rs:86-121)
+    out = torch.empty((frames + 8, 80), dtype=torch.float32).pin_memory()
+    e2e = {}
+    ref = None
+    for chunk in (16000, 960000, n):
+        s = C.c_void_p()
+        assert L.melspec_stream_create(h._h, chunk, C.byref(s)) == 0, ms.last_error()
+        for rep in range(2):
+            L.melspec_stream_reset(s)
+            got, t0 = 0, time.perf_counter()
+            for off in range(0, n, chunk):
+                m = min(chunk, n - off)
+                em = C.c_int64(0)
+                rc = L.melspec_stream_push(s, x.data_ptr() + 4 * off, m, out.data_ptr() + 4 * 80 * got, out.shape[0] - got, C.byref(em))
+                assert rc == 0, ms.last_error()
+                got += em.value
+            dt = time.perf_counter() - t0
+        assert got == frames, (got, frames)
+        if ref is None:
+            ref = out[:frames].clone()
+            same = True
+        else:
+            same = bool(torch.equal(out[:frames], ref))
+        e2e[f"push_{chunk // 16000}_s"] = {"value": got / dt, "unit": "frames/s", "seconds": dt, "x_realtime": 3600.0 / dt,
+                                          "pushes": (n + chunk - 1) // chunk, "identical_to_1_s_pushes": same,
+                                          "h2d_GB/s": 4 * n / dt / 1e9}
+        L.melspec_stream_destroy(s)
+    # stream frames == batch frames of x[80:]: the device-resident launch above on the shifted signal
+    dshift = dx[80:].contiguous()
+    h.compute_device(dshift, 1, n - 80, n - 80, dout, stream=st)
+    torch.cuda.synchronize()
+    e2e["stream_matches_device_path"] = bool(torch.equal(ref.to(dev), dout[:frames]))
+    e2e["stream_vs_device_path_max_abs"] = float((ref.to(dev) - dout[:frames]).abs().max().item())
+    outb = torch.empty((F, 80), dtype=torch.float32).pin_memory()
+    for rep in range(3):
+        t0 = time.perf_counter()
+        h.compute_host_raw(x.data_ptr(), 1, n, n, outb.data_ptr())
+        dt = time.perf_counter() - t0
+    h.compute_device(dx, 1, n, n, dout, stream=st)
+    torch.cuda.synchronize()
+    e2e["one_compute_host_call"] = {"value": F / dt, "unit": "frames/s", "seconds": dt, "x_realtime": 3600.0 / dt,
+                                    "h2d_GB/s": 4 * n / dt / 1e9, "matches_device_path": bool(torch.equal(outb.to(dev), dout))}
+    res["e2e"] = e2e
+    h.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: cfg2 (BASELINE configs[1]) on one GPU, cfg4shard (configs[3], 1024 x 30 s per GPU) under torchrun")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the `extra` block (the other BASELINE configs)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the optional NCCL all-gather of the output shards (reported separately, never in `value`)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    explicit = args.workload is not None
+    if args.workload is None:
+        args.workload = "cfg2" if world == 1 else "cfg4shard"
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mel_spec_b200 as ms
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
+    ms.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    res = measure_workload(torch, dist, ms, args.workload, args, rank, local_rank, world, args.steps, True)
     if rank == 0:
-        frames_rank = clips * F
-        ms_per_step = total_ms_max / args.steps
-        value = world * frames_rank / (ms_per_step * 1e-3)
-        algo_bytes = clips * (4 * n_samples + 4 * n_mels * F)
-        kern_ms = total_ms / args.steps                       # rank 0's own average launch duration
-        peak, peak_kind = measured_peak_gbs()
-        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        traffic, kname, tsrc = measured_traffic(args.workload)
         line = {
-            "metric": "mel frames/sec (Whisper 80-mel, 16 kHz)" if frontend == "whisper" else "fbank frames/sec (Kaldi 80-bin, 16 kHz)",
-            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "clips_per_gpu": clips, "samples_per_clip": n_samples, "frames_per_clip": F,
-                       "l2_policy": "inputs larger than L2 (%.0f MB PCM per launch, no flush)" % (clips * n_samples * 4 / 1e6),
-                       "ms_per_step_median_rank0": per[len(per) // 2], "ms_per_step_min_rank0": per[0]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": tsrc, "kernel": kname, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
-                         "note": "kernel is shared-memory-wavefront / fp32-issue bound, not HBM bound (DESIGN.md section 3)"},
-            "e2e": {"value": world * frames_rank / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": clips * n_samples * 4,
-                    "d2h_bytes_per_step": clips * F * n_mels * 4, "ms_per_step": e2e_s * 1e3, "matches_device_path": same},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": res["metric"], "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": res["config"], "roofline": res["roofline"],
+            "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res.get("clocks"),
         }
-        if gather is not None:
-            line["gather"] = gather
+        for k in ("e2e_int16_pcm", "gather"):
+            if k in res:
+                line[k] = res[k]
         if numa is not None:
             line["config"]["host_affinity"] = f"each rank bound to the {numa} CPUs local to its GPU (NVML) before pinned allocation"
+        if world == 1 and not args.no_extra and not explicit:
+            # the other BASELINE configs on this GPU, same method (fewer steps): configs[2] Kaldi, configs[3]'s per-GPU shard,
+            # configs[4] the 1-hour stream.  configs[0] (JFK vs golden) is a parity case: tests/ and smoke().
+            extra = {}
+            for wl in ("cfg3", "cfg4shard"):
+                r = measure_workload(torch, dist, ms, wl, args, 0, local_rank, 1, max(5, args.steps // 2), False)
+                extra[wl] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches", "steps")
+                             if k in r}
+                if "e2e_int16_pcm" in r:
+                    extra[wl]["e2e_int16_pcm"] = r["e2e_int16_pcm"]
+            extra["cfg5_stream"] = measure_stream(torch, ms)
+            line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))

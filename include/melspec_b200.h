@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MELSPEC_B200_ABI_VERSION 1
+#define MELSPEC_B200_ABI_VERSION 2
 
 /* ---- status codes (0 = success, like cudaError_t in src/cuda_kernels.cu:56-65) ---- */
 enum {
@@ -168,6 +168,18 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
                              int64_t n_samples, float* h_out, int32_t layout, int64_t* frames_out);
 
 /*
+ * The same call for 16-bit PCM (opt-in; the reference takes &[f32] only, its examples convert `sample as f32 / 32768.0`,
+ * examples/vad_ten_eval/src/main.rs:298-299).  Samples cross PCIe as int16 -- half the host-to-device bytes of the f32
+ * call, which is what bounds it end to end -- and become x / 32768 (exact in f32) on the device, so the result is
+ * bit-identical to melspec_compute_host on the converted samples.  melspec_convert_i16_device is that conversion on its own
+ * (device pointers, asynchronous on `stream`): d_out[r * out_stride + i] = d_in[r * in_stride + i] / 32768.
+ */
+int32_t melspec_compute_host_i16(melspec_handle* h, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
+                                 int64_t n_samples, float* h_out, int32_t layout, int64_t* frames_out);
+int32_t melspec_convert_i16_device(melspec_handle* h, const int16_t* d_in, int64_t n_rows, int64_t in_stride, int64_t n_samples,
+                                   float* d_out, int64_t out_stride, void* stream);
+
+/*
  * Streaming (overlap-and-save) front end with RingBuffer/Spectrogram::add semantics (src/rb.rs:86-121,
  * src/stft.rs:48-86) when fed whole hops: frame k covers stream samples [c + k*hop, c + k*hop + N),
  * c = ceil(N/hop)*hop - N; a trailing partial hop stays buffered and is never emitted.
@@ -179,6 +191,17 @@ int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n
                             int64_t out_capacity_frames, int64_t* frames_emitted);
 int32_t melspec_stream_reset(melspec_stream* s);
 void melspec_stream_destroy(melspec_stream* s);
+
+/*
+ * Spectrogram::add's own contract (src/stft.rs:48-86), for callers that feed short chunks: every call takes n <= hop_size
+ * samples (more: MELSPEC_ERR_INVALID_ARG, the reference asserts at stft.rs:53), pads a short chunk with zeros to a whole hop
+ * (stft.rs:56-59), advances the overlap buffer by one hop, and counts only the n true samples (`idx`, stft.rs:64).  A frame
+ * comes back once idx >= fft_size -- from then on with EVERY call (stft.rs:66) -- as the Whisper mel frame
+ * MelSpectrogram::add would produce from the FFT frame the reference returns (src/mel.rs:26-31).  `*emitted` = 1 and n_mels
+ * floats in h_out_frame, or 0 (the reference's None).  Same stream object as melspec_stream_push (do not mix the two on one
+ * stream); melspec_stream_reset clears idx.  The stream must have been created with max_chunk_samples >= hop_size.
+ */
+int32_t melspec_stream_push_hop(melspec_stream* s, const float* h_samples, int64_t n, float* h_out_frame, int32_t* emitted);
 
 /*
  * ---- output formats: the step after the path (reference src/mel.rs:480-544, src/quant.rs:38-165) ----
@@ -246,7 +269,9 @@ int32_t melspec_vad_host(melspec_handle* h, const float* h_img, int32_t n_mels, 
 /* Number of kernel launches issued through this handle so far (bench.py's `gpu_launches`). */
 int64_t melspec_launch_count(const melspec_handle* h);
 
-/* Thread-local description of the last failure in this thread ("" if none).  Never NULL. */
+/* Thread-local description of the last failure in this thread ("" if none).  Never NULL.  The pointer stays valid until the
+ * next FAILING call of this library on the same thread (successful calls do not touch it, other threads have their own
+ * string): copy it before calling again, as the Rust shim does (CStr -> String, rust/src/cuda.rs). */
 const char* melspec_last_error(void);
 
 int32_t melspec_abi_version(void);

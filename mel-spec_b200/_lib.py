@@ -11,7 +11,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "lib", "libmelspec_b200.so")
+# MELSPEC_B200_LIB: load another build of the same ABI (A/B measurements of kernel changes; never a fallback)
+LIB_PATH = os.environ.get("MELSPEC_B200_LIB") or os.path.join(_PKG, "lib", "libmelspec_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "melspec_api.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_PKG, "csrc", "melspec_generic.cuh"),
            os.path.join(_ROOT, "include", "melspec_b200.h")]
@@ -28,6 +29,7 @@ EXPORTS = [
     "melspec_interleaved_width", "melspec_compute_interleaved_device", "melspec_tga_size", "melspec_quantize_tga_device",
     "melspec_dequantize_tga_device", "melspec_quantize_tga_host", "melspec_dequantize_tga_host", "melspec_mel_tga_host",
     "melspec_vad_default_settings", "melspec_vad_boundaries_device", "melspec_vad_activity_device", "melspec_vad_host",
+    "melspec_stream_push_hop", "melspec_compute_host_i16", "melspec_convert_i16_device",
 ]
 
 
@@ -58,6 +60,8 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (cross-compiles without a GPU)."""
+    if os.environ.get("MELSPEC_B200_LIB"):
+        return LIB_PATH
     if force or _stale():
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
         nvcc = os.environ.get("NVCC", "nvcc")
@@ -109,6 +113,12 @@ def lib() -> C.CDLL:
     L.melspec_stream_create.argtypes = [vp, i64, C.POINTER(vp)]
     L.melspec_stream_push.restype = i32
     L.melspec_stream_push.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.melspec_stream_push_hop.restype = i32
+    L.melspec_stream_push_hop.argtypes = [vp, vp, i64, vp, C.POINTER(i32)]
+    L.melspec_compute_host_i16.restype = i32
+    L.melspec_compute_host_i16.argtypes = [vp, vp, i64, i64, i64, vp, i32, C.POINTER(i64)]
+    L.melspec_convert_i16_device.restype = i32
+    L.melspec_convert_i16_device.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
     L.melspec_stream_reset.restype = i32
     L.melspec_stream_reset.argtypes = [vp]
     L.melspec_stream_destroy.restype = None

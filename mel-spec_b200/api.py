@@ -301,11 +301,14 @@ class _Handle:
         single = x.ndim == 1
         x2 = np.ascontiguousarray(x.reshape(1, -1) if single else x)
         n_clips, n = x2.shape
-        f = self.num_frames(n)
+        # the library writes melspec_padded_frames(n) columns per clip (== num_frames(n) except for a NeMo frontend with pad_to,
+        # src/mel.rs:751-756), so the buffer is sized with that count
+        f = int(self._L.melspec_padded_frames(self._h, int(n)))
         shape = (n_clips, f, self.n_mels) if layout == LAYOUT_FRAME_MAJOR else (n_clips, self.n_mels, f)
         if out is None:
-            out = np.empty(shape, dtype=np.float32)
-        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == int(np.prod(shape))
+            out = np.zeros(shape, dtype=np.float32)
+        if out.dtype != np.float32 or not out.flags.c_contiguous or out.size != int(np.prod(shape)):
+            raise ValueError(f"out must be a C-contiguous float32 array of {int(np.prod(shape))} elements (shape {shape})")
         frames = C.c_int64(0)
         _check(self._L.melspec_compute_host(self._h, x2.ctypes.data, n_clips, n, n, out.ctypes.data, int(layout),
                                             C.byref(frames)))
@@ -428,6 +431,34 @@ class _Handle:
         return int(frames.value)
 
 
+def _i16_methods():
+    def compute_host_i16_raw(self, h_pcm_ptr: int, n_clips: int, clip_stride: int, n_samples: int, h_out_ptr: int,
+                             layout: int = LAYOUT_FRAME_MAJOR) -> int:
+        """Pointer form of `melspec_compute_host_i16` (int16 PCM: half the host-to-device bytes)."""
+        frames = C.c_int64(0)
+        _check(self._L.melspec_compute_host_i16(self._h, int(h_pcm_ptr), int(n_clips), int(clip_stride), int(n_samples),
+                                                int(h_out_ptr), int(layout), C.byref(frames)))
+        return int(frames.value)
+
+    def compute_host_i16(self, samples, layout: int = LAYOUT_FRAME_MAJOR) -> np.ndarray:
+        """`melspec_compute_host_i16` on a (n_samples,) or (n_clips, n_samples) int16 host array: x / 32768 on the device."""
+        x = np.asarray(samples, dtype=np.int16)
+        single = x.ndim == 1
+        x2 = np.ascontiguousarray(x.reshape(1, -1) if single else x)
+        n_clips, n = x2.shape
+        f = int(self._L.melspec_padded_frames(self._h, int(n)))
+        shape = (n_clips, f, self.n_mels) if layout == LAYOUT_FRAME_MAJOR else (n_clips, self.n_mels, f)
+        out = np.zeros(shape, dtype=np.float32)
+        self.compute_host_i16_raw(x2.ctypes.data, n_clips, n, n, out.ctypes.data, layout)
+        return out[0] if single else out
+
+    _Handle.compute_host_i16_raw = compute_host_i16_raw
+    _Handle.compute_host_i16 = compute_host_i16
+
+
+_i16_methods()
+
+
 class CudaMelSpectrogram(_Handle):
     """reference src/cuda.rs:27-155.  `CudaMelSpectrogram(fft_size, hop_size, sampling_rate, n_mels)` == `new`."""
 
@@ -484,9 +515,53 @@ class CudaMelSpectrogram(_Handle):
         return img.reshape(-1)
 
 
+class SpectrogramFrame:
+    """What `Spectrogram.add` hands to `MelSpectrogram.add`.  The reference passes the complex FFT frame between the two
+    (src/stft.rs:82, src/mel.rs:26); here the whole chain is one fused kernel, so the token already carries the mel frame."""
+    __slots__ = ("mel", "fft_size", "n_mels", "sampling_rate")
+
+    def __init__(self, mel, fft_size, n_mels, sampling_rate):
+        self.mel, self.fft_size, self.n_mels, self.sampling_rate = mel, fft_size, n_mels, sampling_rate
+
+
 class Spectrogram:
-    """Batch entry of reference src/stft.rs:119-138, GPU-backed (handles are cached per configuration)."""
+    """reference src/stft.rs:10-138.  `Spectrogram(fft_size, hop_size).add(frames)` is the streaming overlap-and-save entry
+    (src/stft.rs:48-86): <= hop_size samples per call, a short chunk is zero-padded to a whole hop, a frame comes back once
+    fft_size true samples have been seen and with every call after that.  `n_mels` / `sampling_rate` default to the Whisper
+    values: the device computes STFT and mel in one kernel, so the stream needs them up front.  The classmethod is the batch
+    entry (src/stft.rs:119-138), GPU-backed (handles are cached per configuration)."""
     _cache: dict = {}
+
+    def __init__(self, fft_size: int, hop_size: int, n_mels: int = 80, sampling_rate: float = 16000.0, device: int = 0):
+        self.fft_size, self.hop_size, self.n_mels, self.sampling_rate = int(fft_size), int(hop_size), int(n_mels), float(sampling_rate)
+        self._handle = CudaMelSpectrogram(fft_size, hop_size, sampling_rate, n_mels, device)
+        self._L = self._handle._L
+        self._s = C.c_void_p()
+        _check(self._L.melspec_stream_create(self._handle._h, max(self.hop_size, 1), C.byref(self._s)), constructing=True)
+        self._out = np.empty(self.n_mels, dtype=np.float32)
+
+    def add(self, frames):
+        x = np.ascontiguousarray(np.asarray(frames, dtype=np.float32).reshape(-1))
+        if x.size > self.hop_size:
+            raise AssertionError("frames must be <= hop_size")          # src/stft.rs:53
+        emitted = C.c_int32(0)
+        _check(self._L.melspec_stream_push_hop(self._s, x.ctypes.data if x.size else None, x.size, self._out.ctypes.data,
+                                               C.byref(emitted)))
+        if not emitted.value:
+            return None
+        return SpectrogramFrame(self._out.copy(), self.fft_size, self.n_mels, self.sampling_rate)
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s:
+            self._L.melspec_stream_destroy(self._s)
+            self._s = C.c_void_p()
+            self._handle.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @classmethod
     def compute_mel_spectrogram(cls, samples, fft_size: int, hop_size: int, n_mels: int, sampling_rate: float,
@@ -549,6 +624,20 @@ class BatchLogMelSpectrogram(_Handle):
         out = np.zeros((self.config.n_mels, self.config.n_fft // 2 + 1), dtype=np.float64)
         _check(_lib.lib().melspec_build_filterbank(C.byref(c), out.ctypes.data_as(C.POINTER(C.c_double)), out.size), True)
         return out
+
+
+class MelSpectrogram:
+    """reference src/mel.rs:13-32: `MelSpectrogram(fft_size, sampling_rate, n_mels).add(fft_frame)` -> (n_mels, 1).  The frame
+    token of `Spectrogram.add` already holds the projected, normalised frame (one fused kernel); `add` checks that it was made
+    for this configuration and returns it in the reference's shape."""
+
+    def __init__(self, fft_size: int, sampling_rate: float, n_mels: int):
+        self.fft_size, self.sampling_rate, self.n_mels = int(fft_size), float(sampling_rate), int(n_mels)
+
+    def add(self, fft: "SpectrogramFrame") -> np.ndarray:
+        if (fft.fft_size, fft.n_mels, fft.sampling_rate) != (self.fft_size, self.n_mels, self.sampling_rate):
+            raise ValueError("frame was produced by a Spectrogram with a different fft_size / n_mels / sampling_rate")
+        return fft.mel.reshape(-1, 1)
 
 
 class RingBuffer:

@@ -196,7 +196,8 @@ struct melspec_handle {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     float* d_slot_pcm[3] = {nullptr, nullptr, nullptr};
     float* d_slot_out[3] = {nullptr, nullptr, nullptr};
-    size_t slot_pcm_cap = 0, slot_out_cap = 0;
+    int16_t* d_slot_i16[3] = {nullptr, nullptr, nullptr};   // int16 staging of melspec_compute_host_i16
+    size_t slot_pcm_cap = 0, slot_out_cap = 0, slot_i16_cap = 0;
     float2* d_partials = nullptr;   // min/max partials of the TGA quantiser
     size_t partials_cap = 0;
     float* d_fmt_img = nullptr;     // staging of the host-buffer format entry points
@@ -214,6 +215,8 @@ struct melspec_stream {
     int64_t cap = 0;        // samples per device buffer
     int64_t buffered = 0;   // valid samples at the start of d_buf[cur] (the carried tail)
     int64_t to_skip = 0;    // samples still to drop before the first frame (the stream offset c)
+    uint64_t idx = 0;       // melspec_stream_push_hop: true samples seen so far (Spectrogram::add's idx, src/stft.rs:64)
+    std::vector<float> hopbuf;   // melspec_stream_push_hop: the zero-padded hop
     float* h_pin_in[2] = {nullptr, nullptr};
     float* h_pin_out[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
@@ -699,6 +702,14 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.proj = h->d_proj; p.proj_meta = h->d_meta; p.proj_ktot = h->proj_ktot;
     p.floor_val = (float)c.floor;
     if (p.floor_val > 0.f && p.floor_val < 1.17549435e-38f) p.floor_val = 1.17549435e-38f;   // lg2_normal() flushes denormals
+    {   // pair prescale (melspec_kernels.cuh): a frame may be scaled by 2^k as long as floor * 2^(2k) (NeMo: guard * 2^(2k)) stays normal
+        const float v = nemo ? p.log_add : p.floor_val;
+        uint32_t bits;
+        std::memcpy(&bits, &v, 4);
+        const int ef = (int)((bits >> 23) & 255u);
+        p.ps_down = v > 0.f ? std::min(melspec::kMaxShift, std::max(0, (ef - 1) / 2)) : 0;
+        p.ps_up = v > 0.f ? std::min(melspec::kMaxShift, std::max(0, (254 - ef) / 2)) : 0;
+    }
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
@@ -721,11 +732,11 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (h->plan == 400) {
         pcm_words = hop160 ? (size_t)p400::NCHUNK * p400::CS320 : (size_t)(p400::FPW - 1) * c.hop + 400;
         p.smem_stage_off = p400::PBYTES;
-        p.smem_pcm_off = (int)up(p400::ZBYTES, 128);
+        p.smem_pcm_off = (int)up(p400::ZBYTES + 48, 128);   // 48 bytes behind the slab: the pair prescale's per-frame (floor, log offset)
     } else {
         pcm_words = (size_t)p512::NCHUNK * p512::CS;
         p.smem_stage_off = p512::PBYTES;
-        p.smem_pcm_off = (int)up(p512::ZBYTES, 128);
+        p.smem_pcm_off = (int)up(p512::ZBYTES + p512::SCRBYTES, 128);
     }
     p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
     const int nw = warps_per_cta(h->plan);
@@ -776,9 +787,17 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     return launch_post_kernels(h, p, n_clips, d_lens, d_out, fused_cmn, st);
 }
 
-int32_t ensure_host_resources(melspec_handle* h, size_t pcm_bytes, size_t out_bytes) {
+int32_t ensure_host_resources(melspec_handle* h, size_t pcm_bytes, size_t out_bytes, size_t i16_bytes = 0) {
     for (int i = 0; i < 3; ++i)
         if (!h->streams[i]) MS_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    if (i16_bytes > h->slot_i16_cap) {
+        for (int i = 0; i < 3; ++i) {
+            if (h->d_slot_i16[i]) cudaFree(h->d_slot_i16[i]);
+            h->d_slot_i16[i] = nullptr;
+            MS_CUDA(cudaMalloc(&h->d_slot_i16[i], i16_bytes));
+        }
+        h->slot_i16_cap = i16_bytes;
+    }
     if (pcm_bytes > h->slot_pcm_cap) {
         for (int i = 0; i < 3; ++i) {
             if (h->d_slot_pcm[i]) cudaFree(h->d_slot_pcm[i]);
@@ -885,7 +904,7 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
     int plan = 1;
     if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 400 && r.hop <= 256) plan = 400;
     else if (r.frontend == MELSPEC_FRONTEND_WHISPER && r.fft == 512 && r.hop == 160) plan = 512;
-    else if (r.frontend == MELSPEC_FRONTEND_KALDI && r.fft == 512 && r.frame_len == 400 && r.hop == 160 && r.use_power) plan = 512;
+    else if (r.frontend == MELSPEC_FRONTEND_KALDI && r.fft == 512 && r.frame_len == 400 && r.hop == 160 && r.use_power && r.use_log) plan = 512;
     else if (r.frontend == MELSPEC_FRONTEND_NEMO && r.fft == 512 && r.frame_len == 400 && r.hop == 160) plan = 512;
     if (force_generic) plan = 1;
     if (plan == 1) {
@@ -939,6 +958,7 @@ void melspec_destroy(melspec_handle* h) {
     for (int i = 0; i < 3; ++i) {
         if (h->d_slot_pcm[i]) cudaFree(h->d_slot_pcm[i]);
         if (h->d_slot_out[i]) cudaFree(h->d_slot_out[i]);
+        if (h->d_slot_i16[i]) cudaFree(h->d_slot_i16[i]);
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     }
     delete h;
@@ -1245,8 +1265,44 @@ int32_t melspec_compute_device(melspec_handle* h, const float* d_pcm, int64_t n_
     return launch_device(h, d_pcm, n_clips, clip_stride, n_samples, F, d_lens, d_out, out_clip_stride, layout, (cudaStream_t)stream);
 }
 
-int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
-                             float* h_out, int32_t layout, int64_t* frames_out) {
+namespace {
+// int16 rows on the device -> f32 rows (x / 32768), asynchronous on `st`
+int32_t launch_convert_i16(melspec_handle* h, const int16_t* d_in, int64_t n_rows, int64_t in_stride, int64_t n, float* d_out,
+                           int64_t out_stride, cudaStream_t st) {
+    if (n_rows == 0 || n == 0) return MELSPEC_OK;
+    const int vec = ((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && (in_stride % 8 == 0) && (out_stride % 4 == 0);
+    int64_t done = 0;
+    while (done < n_rows) {   // gridDim.y <= 65535
+        const int64_t rows = std::min<int64_t>(n_rows - done, 65535);
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n / 8 + 255) / 256, std::max<int64_t>(1, 8 * h->num_sms / rows)));
+        melspec::melspec_i16_to_f32_kernel<<<dim3(blocks, (unsigned)rows), 256, 0, st>>>(d_in + done * in_stride, in_stride, (int)n,
+                                                                                   d_out + done * out_stride, out_stride, vec);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
+        done += rows;
+    }
+    return MELSPEC_OK;
+}
+
+// H2D of `nc` rows of `ns` samples (host row stride `clip_stride`, first sample `h_off` of each row) into staging slot `slot`
+// (device row stride `dstride`): f32 directly, int16 through the int16 slot and the conversion kernel.
+int32_t stage_rows(melspec_handle* h, int slot, const void* h_pcm, bool i16, int64_t row0, int64_t nc, int64_t clip_stride,
+                   int64_t h_off, int64_t ns, int64_t dstride, cudaStream_t st) {
+    const size_t es = i16 ? 2 : 4;
+    const char* src = static_cast<const char*>(h_pcm) + (size_t)(row0 * clip_stride + h_off) * es;
+    void* dst = i16 ? static_cast<void*>(h->d_slot_i16[slot]) : static_cast<void*>(h->d_slot_pcm[slot]);
+    if (clip_stride == dstride || nc == 1) {
+        MS_CUDA(cudaMemcpyAsync(dst, src, (size_t)((nc - 1) * dstride + ns) * es, cudaMemcpyHostToDevice, st));
+    } else {
+        MS_CUDA(cudaMemcpy2DAsync(dst, (size_t)dstride * es, src, (size_t)clip_stride * es, (size_t)ns * es, (size_t)nc,
+                                  cudaMemcpyHostToDevice, st));
+    }
+    if (i16) return launch_convert_i16(h, h->d_slot_i16[slot], nc, dstride, ns, h->d_slot_pcm[slot], dstride, st);
+    return MELSPEC_OK;
+}
+
+int32_t compute_host_impl(melspec_handle* h, const void* h_pcm, bool i16, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                          float* h_out, int32_t layout, int64_t* frames_out) {
     if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
     if (n_clips < 0 || n_samples < 0 || clip_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
     if (layout != MELSPEC_LAYOUT_FRAME_MAJOR && layout != MELSPEC_LAYOUT_MEL_MAJOR)
@@ -1259,7 +1315,7 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     MS_CUDA(cudaSetDevice(h->device));
     // Clips are cut into chunks that rotate over 3 (stream, device slot) pairs, so the H2D copy of chunk i+1, the
     // kernel of chunk i and the D2H copy of chunk i-1 overlap when the host buffers are pinned.
-    const int64_t ns4 = (n_samples + 3) / 4 * 4;   // device rows are padded to 16 bytes so the TMA path applies
+    const int64_t ns4 = (n_samples + 7) / 8 * 8;   // device rows are padded to 32 bytes so the TMA path (and the int16 vector loads) apply
     const int64_t clip_out = padded_frames_for(h->cfg, n_samples) * h->cfg.n_mels;
     static const int64_t chunk_mb = [] {            // MELSPEC_HOST_CHUNK_MB: PCM bytes per pipeline chunk (tuning knob)
         const char* e = std::getenv("MELSPEC_HOST_CHUNK_MB");
@@ -1277,15 +1333,16 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     if (h->cfg.frontend == MELSPEC_FRONTEND_WHISPER && n_clips == 1 && n_samples * 4 >= 2 * piece_bytes) {
         const Resolved& c = h->cfg;
         int64_t pf = std::max<int64_t>(12, piece_bytes / 4 / c.hop / 12 * 12);   // frames per piece
-        const int64_t psamples = ((pf - 1) * c.hop + c.fft + 3) / 4 * 4;
-        int32_t rc = ensure_host_resources(h, (size_t)psamples * 4, (size_t)pf * c.n_mels * 4);
+        const int64_t psamples = ((pf - 1) * c.hop + c.fft + 7) / 8 * 8;
+        int32_t rc = ensure_host_resources(h, (size_t)psamples * 4, (size_t)pf * c.n_mels * 4, i16 ? (size_t)psamples * 2 : 0);
         if (rc) return rc;
         int slot = 0;
         for (int64_t f0 = 0; f0 < F; f0 += pf, slot = (slot + 1) % 3) {
             const int64_t nf = std::min(pf, F - f0);
             const int64_t s0 = f0 * c.hop, ns = (nf - 1) * c.hop + c.fft;
             cudaStream_t st = h->streams[slot];
-            MS_CUDA(cudaMemcpyAsync(h->d_slot_pcm[slot], h_pcm + s0, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+            rc = stage_rows(h, slot, h_pcm, i16, 0, 1, psamples, s0, ns, psamples, st);
+            if (rc) return rc;
             rc = launch_device(h, h->d_slot_pcm[slot], 1, psamples, ns, nf, nullptr, h->d_slot_out[slot], 0, layout, st);
             if (rc) return rc;
             if (layout == MELSPEC_LAYOUT_FRAME_MAJOR)
@@ -1300,32 +1357,60 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
     int64_t per_chunk = std::max<int64_t>(1, target / (ns4 * 4));
     per_chunk = std::min(per_chunk, n_clips);
     if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
+    int64_t n_chunks = (n_clips + per_chunk - 1) / per_chunk;
     if (h->cfg.frontend == MELSPEC_FRONTEND_KALDI && h->cfg.cmn && n_clips >= h->num_sms && per_chunk < h->num_sms) {
-        // keep every chunk at one clip per SM or more, so that all of them take the kernel with CMN fused in (faster, and
-        // the same arithmetic as a device-resident launch of the whole batch: results are bit-identical)
+        // Keep every chunk at one clip per SM or more, so that all of them take the kernel with CMN fused in (faster, and the
+        // same arithmetic as a device-resident launch of the whole batch: a clip's result does not depend on which CTA or
+        // chunk it rides in, so the results are bit-identical).  Bounded: a chunk of num_sms very long clips would make the
+        // three staging slots arbitrarily large, so beyond 512 MB of PCM per slot the chunks stay small and CMN runs as the
+        // second kernel (same values up to the summation order of the column means).
         const int64_t k = n_clips / h->num_sms;
-        per_chunk = (n_clips + k - 1) / k;
+        const int64_t bytes = ((n_clips + k - 1) / k) * ns4 * 4;
+        if (bytes <= ((int64_t)512 << 20)) n_chunks = k;
     }
-    int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * clip_out * 4);
+    // balanced chunks: sizes differ by at most one clip, so no runt chunk falls below the fused-CMN threshold
+    const int64_t base = n_clips / n_chunks, rem = n_clips % n_chunks;
+    per_chunk = base + (rem ? 1 : 0);
+    int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * clip_out * 4,
+                                       i16 ? (size_t)per_chunk * ns4 * 2 : 0);
     if (rc) return rc;
     int slot = 0;
-    for (int64_t c0 = 0; c0 < n_clips; c0 += per_chunk, slot = (slot + 1) % 3) {
-        const int64_t nc = std::min(per_chunk, n_clips - c0);
+    int64_t c0 = 0;
+    for (int64_t ci = 0; ci < n_chunks; ++ci, slot = (slot + 1) % 3) {
+        const int64_t nc = base + (ci < rem ? 1 : 0);
         cudaStream_t st = h->streams[slot];
-        if (clip_stride == ns4 || nc == 1) {
-            MS_CUDA(cudaMemcpyAsync(h->d_slot_pcm[slot], h_pcm + c0 * clip_stride, (size_t)((nc - 1) * ns4 + n_samples) * 4,
-                                    cudaMemcpyHostToDevice, st));
-        } else {
-            MS_CUDA(cudaMemcpy2DAsync(h->d_slot_pcm[slot], (size_t)ns4 * 4, h_pcm + c0 * clip_stride, (size_t)clip_stride * 4,
-                                      (size_t)n_samples * 4, (size_t)nc, cudaMemcpyHostToDevice, st));
-        }
-        rc = launch_device(h, h->d_slot_pcm[slot], nc, ns4, ns4 == n_samples ? n_samples : n_samples, F, nullptr,
-                           h->d_slot_out[slot], 0, layout, st);
+        rc = stage_rows(h, slot, h_pcm, i16, c0, nc, clip_stride, 0, n_samples, ns4, st);
+        if (rc) return rc;
+        rc = launch_device(h, h->d_slot_pcm[slot], nc, ns4, n_samples, F, nullptr, h->d_slot_out[slot], 0, layout, st);
         if (rc) return rc;
         MS_CUDA(cudaMemcpyAsync(h_out + c0 * clip_out, h->d_slot_out[slot], (size_t)nc * clip_out * 4, cudaMemcpyDeviceToHost, st));
+        c0 += nc;
     }
     for (int i = 0; i < 3; ++i) MS_CUDA(cudaStreamSynchronize(h->streams[i]));
     return MELSPEC_OK;
+}
+}  // namespace
+
+int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                             float* h_out, int32_t layout, int64_t* frames_out) {
+    return compute_host_impl(h, h_pcm, false, n_clips, clip_stride, n_samples, h_out, layout, frames_out);
+}
+
+int32_t melspec_compute_host_i16(melspec_handle* h, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                                 float* h_out, int32_t layout, int64_t* frames_out) {
+    return compute_host_impl(h, h_pcm, true, n_clips, clip_stride, n_samples, h_out, layout, frames_out);
+}
+
+int32_t melspec_convert_i16_device(melspec_handle* h, const int16_t* d_in, int64_t n_rows, int64_t in_stride, int64_t n_samples,
+                                   float* d_out, int64_t out_stride, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (n_rows < 0 || in_stride < 0 || out_stride < 0 || n_samples < 0 || n_samples > 0x7fffffff) return fail(MELSPEC_ERR_INVALID_ARG, "bad size");
+    if (n_rows == 0 || n_samples == 0) return MELSPEC_OK;
+    if (!d_in || !d_out) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    if (n_rows > 1 && (in_stride < n_samples || out_stride < n_samples)) return fail(MELSPEC_ERR_INVALID_ARG, "stride < n_samples");
+    MS_CUDA(cudaSetDevice(h->device));
+    return launch_convert_i16(h, d_in, n_rows, in_stride ? in_stride : n_samples, n_samples, d_out, out_stride ? out_stride : n_samples,
+                              (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ streaming
@@ -1333,6 +1418,12 @@ int32_t melspec_stream_create(melspec_handle* h, int64_t max_chunk_samples, mels
     if (!h || !out) return fail(MELSPEC_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     if (max_chunk_samples <= 0) return fail(MELSPEC_ERR_INVALID_ARG, "max_chunk_samples must be positive");
+    // Spectrogram::add / RingBuffer are the Whisper STFT (src/stft.rs:48-86, src/rb.rs:86-121).  A Kaldi stream would need the
+    // CMN and the pre-emphasis look-back carried across pushes, a NeMo stream the centre padding: neither exists in the
+    // reference.  hop > fft: the reference's overlap buffer arithmetic panics (stft.rs:50-55), here it is an error.
+    if (h->cfg.frontend != MELSPEC_FRONTEND_WHISPER)
+        return fail(MELSPEC_ERR_UNSUPPORTED, "streaming is defined for the Whisper frontend only (src/stft.rs:48-86)");
+    if (h->cfg.hop > h->cfg.fft) return fail(MELSPEC_ERR_UNSUPPORTED, "streaming needs hop_size <= fft_size (src/stft.rs:48-59)");
     MS_CUDA(cudaSetDevice(h->device));
     melspec_stream* s = new (std::nothrow) melspec_stream();
     if (!s) return fail(MELSPEC_ERR_CUDA, "out of host memory");
@@ -1379,6 +1470,7 @@ int32_t melspec_stream_reset(melspec_stream* s) {
     cudaStreamSynchronize(s->compute_stream);
     s->buffered = 0;
     s->cur = 0;
+    s->idx = 0;
     s->used_free[0] = s->used_free[1] = false;
     s->to_skip = (int64_t)((c.frame_len + c.hop - 1) / c.hop) * c.hop - c.frame_len;
     return MELSPEC_OK;
@@ -1469,6 +1561,31 @@ int32_t melspec_stream_push(melspec_stream* s, const float* h_samples, int64_t n
         if (pend[i].slot >= 0)
             std::memcpy(h_out + pend[i].at * c.n_mels, s->h_pin_out[i], (size_t)pend[i].frames * c.n_mels * 4);
     if (frames_emitted) *frames_emitted = done_frames;
+    return MELSPEC_OK;
+}
+
+// Spectrogram::add (src/stft.rs:48-86): the hop buffer advances by one whole hop per call whatever the chunk length; fed through
+// the whole-hop machinery above, frame j of that machinery is exactly the reference's frame of call j (both cover the last
+// fft_size samples of the zero-padded hop sequence), and the reference hands it out once idx >= fft_size.
+int32_t melspec_stream_push_hop(melspec_stream* s, const float* h_samples, int64_t n, float* h_out_frame, int32_t* emitted) {
+    if (emitted) *emitted = 0;
+    if (!s) return fail(MELSPEC_ERR_INVALID_ARG, "stream is null");
+    const Resolved& c = s->h->cfg;
+    if (n < 0 || n > c.hop) return fail(MELSPEC_ERR_INVALID_ARG, "frames must be <= hop_size");   // assert at src/stft.rs:53
+    if (n > 0 && !h_samples) return fail(MELSPEC_ERR_INVALID_ARG, "null samples");
+    if (!h_out_frame) return fail(MELSPEC_ERR_INVALID_ARG, "null output");
+    if (s->max_chunk < c.hop) return fail(MELSPEC_ERR_INVALID_ARG, "stream was created with max_chunk_samples < hop_size");
+    try {
+        s->hopbuf.assign((size_t)c.hop, 0.f);                                                     // zero pad, src/stft.rs:56-59
+    } catch (...) {
+        return fail(MELSPEC_ERR_CUDA, "out of host memory");
+    }
+    if (n > 0) std::memcpy(s->hopbuf.data(), h_samples, (size_t)n * 4);
+    int64_t got = 0;
+    int32_t rc = melspec_stream_push(s, s->hopbuf.data(), c.hop, h_out_frame, 1, &got);
+    if (rc) return rc;
+    s->idx += (uint64_t)n;                                                                        // wrapping_add, src/stft.rs:64
+    if (emitted) *emitted = (got == 1 && s->idx >= (uint64_t)c.fft) ? 1 : 0;                      // src/stft.rs:66
     return MELSPEC_OK;
 }
 

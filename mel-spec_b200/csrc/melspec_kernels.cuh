@@ -68,6 +68,7 @@ struct KParams {
     int out_row_stride;      // mel-major output: floats between mel rows (NeMo: padded frame count)
     int mm_aligned8;         // mel-major output: every mel row of every tile starts on an 8-byte boundary
     int cmn_fused;           // Kaldi: CMN inside the fused kernel (one CTA per clip at a time), see melspec512_kernel
+    int ps_down, ps_up;      // pair prescale: how far the floor / guard allows a frame to be scaled down / up (see pair_prescale)
     int vec_out;             // frame-major output rows are 16-byte aligned (float4 stores when TMA stores are not used)
     int n_clips;
     int smem_cmn;            // [NWARPS][128] column sums + [128] means (floats)
@@ -129,6 +130,43 @@ __device__ __forceinline__ float warp_max_f32(float v) {
     float r;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // sm_100a: CREDUX.MAX.F32
     return r;
+}
+
+// ------------------------------------------------------------------------------------------------ pair prescale
+// Two neighbouring frames travel as the real (A) and imaginary (B) part of one complex transform, so the fp32 rounding
+// noise of the louder frame lands in the quieter one at the louder frame's scale.  The reference transforms every frame on
+// its own in f64 (src/stft.rs:89-115), and its outputs are relative to each frame's own level (per-frame clamp, src/mel.rs:645-654;
+// ln of unclamped energies, src/fbank.rs:207-221).  To keep that property, frame B is multiplied by an exact power of two 2^k
+// before the transform whenever the two frames' peak levels differ by more than 2^kDeadZone.  Nothing is multiplied back:
+// with E' = 2^(2k) E the energies the kernel accumulates,
+//     log(max(E, v))  =  log(max(E', v 2^(2k)))  -  2k log 2          (v = the energy floor; NeMo: log(E + v), v = the guard)
+// so each frame carries its own (v_q, c_q) = (v 2^(2 k_q), -2 k_q log_mul) into the epilogue, where they replace the constant
+// floor of the FMNMX and turn the FMUL by log_mul into an FFMA: no extra instruction there.  A frame whose samples are all zero
+// (or denormal) is "silent": its partner is scaled *down* as far as v allows, which pushes the partner's rounding noise in the
+// silent frame's slot far below the floor (the silent frame then sits exactly on the floor, like the reference's).
+//   pk  = (biased exponent of max|A|) | (biased exponent of max|B|) << 16, identical in all lanes of the transform
+constexpr int kDeadZone = 3;     // level ratios up to 2^(3+1) ride unscaled (fp32 noise stays 3 decades under the 1e-4 contract)
+constexpr int kMaxShift = 45;    // |k| <= 45: 2^(2k) v stays a normal fp32 number for every floor / guard the frontends use
+__device__ __forceinline__ int pack_exponents(const float ma, const float mb) {   // ma, mb >= 0
+    return (__float_as_int(ma) >> 23) | ((__float_as_int(mb) >> 23) << 16);
+}
+__device__ __forceinline__ float scale_pow4(const float v, const int k) {          // v * 2^(2k), v and the result normal
+    return __int_as_float(__float_as_int(v) + (k << 24));
+}
+__device__ __forceinline__ float pow2i(const int k) { return __int_as_float((127 + k) << 23); }
+// returns (ka, kb) and the table entry (vA, cA, vB, cB); kdown / kup = how far v allows a frame to be scaled down / up
+__device__ __forceinline__ void pair_prescale(const int pk, const float v, const float log_mul, const int kdown, const int kup,
+                                              int& ka, int& kb, float4& tab) {
+    const int ea = pk & 0xffff, eb = pk >> 16;
+    int d = min(max(ea - eb, -kdown), kup);
+    if (abs(d) <= kDeadZone) d = 0;
+    ka = 0;
+    kb = d;
+    if (ea == 0 || eb == 0) {          // a silent frame: scale its partner down (both silent: nothing to do)
+        kb = (eb != 0) ? -kdown : 0;
+        ka = (ea != 0) ? -kdown : 0;
+    }
+    tab = make_float4(scale_pow4(v, ka), (float)(-2 * ka) * log_mul, scale_pow4(v, kb), (float)(-2 * kb) * log_mul);
 }
 
 // ------------------------------------------------------------------------------------------------ DFT codelets
@@ -228,6 +266,50 @@ __device__ __forceinline__ void dft20x2(f2 (&xr)[20], f2 (&xi)[20]) {
             xi[(5 * a + 16 * kb) % 20] = ti[a][kb];
         }
     }
+}
+
+// The same transform with the window folded into its first layer.  For residue b the layer forms the sums and differences of
+// the windowed samples (n0, n2) = (4b, 10 + 4b) and (n1, n3) = (5 + 4b, 15 + 4b):  x0 w0 +- x2 w2 = fma(+-x2, w2, x0 w0) -- one
+// product and two FMAs instead of two products and two adds (a fifth of the window's multiplies disappears, and the FMA rounds once).
+//   q[b] = (s02, d02, s13, d13) for the real part (frame A) or the imaginary part (frame B) of the packed input
+__device__ __forceinline__ void win_first_layer(const f2 x0, const f2 x1, const f2 x2, const f2 x3, const f2 w0, const f2 w1, const f2 w2,
+                                                const f2 w3, f2 (&q)[4]) {
+    const f2 p0 = mul2(x0, w0), p1 = mul2(x1, w1);
+    q[0] = fma2(x2, w2, p0);
+    q[1] = fma2(x2, make_float2(-w2.x, -w2.y), p0);
+    q[2] = fma2(x3, w3, p1);
+    q[3] = fma2(x3, make_float2(-w3.x, -w3.y), p1);
+}
+// ... and the rest of the transform: second half of the radix-4 layer (where the real and the imaginary input first meet),
+// the four 5-point transforms, natural-order outputs.
+__device__ __forceinline__ void dft20x2_rest(const f2 (&qr)[5][4], const f2 (&qi)[5][4], f2 (&xr)[20], f2 (&xi)[20]) {
+    f2 tr[4][5], ti[4][5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        tr[0][b] = add2(qr[b][0], qr[b][2]); ti[0][b] = add2(qi[b][0], qi[b][2]);
+        tr[2][b] = sub2(qr[b][0], qr[b][2]); ti[2][b] = sub2(qi[b][0], qi[b][2]);
+        tr[1][b] = add2(qr[b][1], qi[b][3]); ti[1][b] = sub2(qi[b][1], qr[b][3]);
+        tr[3][b] = sub2(qr[b][1], qi[b][3]); ti[3][b] = add2(qi[b][1], qr[b][3]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        dft5x2(tr[a][0], ti[a][0], tr[a][1], ti[a][1], tr[a][2], ti[a][2], tr[a][3], ti[a][3], tr[a][4], ti[a][4]);
+#pragma unroll
+        for (int kb = 0; kb < 5; ++kb) {
+            xr[(5 * a + 16 * kb) % 20] = tr[a][kb];
+            xi[(5 * a + 16 * kb) % 20] = ti[a][kb];
+        }
+    }
+}
+
+// Untangle + power of two conjugate slot pairs at once.  w1 = the packed register of slot j' = N1 - j, op = the partner values
+// arranged so that (w1.x, op.x) and (w1.y, op.y) are the two (u, v) pairs; S = u + v, D = u - v per half (FADD2 with a swapped-halves
+// operand, SASS .LO_HI, when op is the other register with its halves exchanged).  Powers: |A|^2 = Sr^2 + Di^2, |B|^2 = Si^2 + Dr^2.
+__device__ __forceinline__ void untangle2(const f2 w1r, const f2 w1i, const f2 opr, const f2 opi, float2& plo, float2& phi) {
+    const f2 sr = add2(w1r, opr), si = add2(w1i, opi), dr = sub2(w1r, opr), di = sub2(w1i, opi);
+    const f2 di2 = mul2(di, di), dr2 = mul2(dr, dr);
+    plo = make_float2(fmaf(sr.x, sr.x, di2.x), fmaf(si.x, si.x, dr2.x));   // scalar FMAs: the results land as (|A|^2, |B|^2) pairs
+    phi = make_float2(fmaf(sr.y, sr.y, di2.y), fmaf(si.y, si.y, dr2.y));
 }
 
 // ---- power-of-two codelets for the 512-point plan -------------------------------------------------------------
@@ -347,7 +429,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     float2* s_p = reinterpret_cast<float2*>(s_warp);
     float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
+    float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor, log offset) of frames A and B per FFT (48 of
+                                                                  // the 64 bytes between the slab and the 128-byte aligned PCM stage)
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
+    // lanes of this FFT at ring distance 1, 2, 4, 8 (one byte each): the all-reduce of the pair prescale
+    const int ring = (10 * g + (t + 1) % 10) | (10 * g + (t + 2) % 10) << 8 | (10 * g + (t + 4) % 10) << 16 | (10 * g + (t + 8) % 10) << 24;
 
     // ---- one-time setup: tables into shared memory, barriers, per-lane window / twiddle registers
     for (int i = threadIdx.x; i < 2 * p.proj_ktot * 32; i += NWARPS * 32)
@@ -378,8 +464,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                               0.f, -0.15450849718747345f, -0.29389262614623651f, -0.40450849718747367f, -0.47552825814757677f,
                               -0.5f, -0.47552825814757682f, -0.40450849718747378f, -0.29389262614623668f, -0.15450849718747381f};
     const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + l30;
-    // the 8-warp build (MELSPEC_WARPS=8; the default is 12) has registers to spare: it keeps the worker's 10 twiddle quads resident
+    // the worker's 10 twiddle quads stay in registers (156 registers per thread at 12 warps, no spills, since the TMA refill is
+    // issued between the sample loads and the first butterfly layer instead of after it)
+#ifdef MELSPEC_TW_SMEM   // A/B switch (tools/ab_bench.sh): twiddles read from shared memory every pass
     constexpr bool TW_IN_REGS = (NWARPS <= 8);
+#else
+    constexpr bool TW_IN_REGS = HOP160 || (NWARPS <= 8);   // (other hops load and window on the fly: no registers to spare)
+#endif
     float4 twreg[10];
     if (TW_IN_REGS) {
 #pragma unroll
@@ -443,56 +534,89 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1: window + column DFTs
-        // PR[n] = (re of column 2t, re of column 2t+1), PI[n] = (im, im): the two column transforms advance together in
-        // packed FADD2/FMUL2/FFMA2 instructions (re = frame A, im = frame B)
-        f2 PR[20], PI[20];
-        if (nvalid > 0) {
-            const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
-            const float4 wth = *s_wth;
-            const f2 w_cos = make_float2(wth.x, wth.y), w_sin = make_float2(wth.z, wth.w);
-            if (HOP160) {
-                // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
-                // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16).  Conflict-free: a half-warp's 16 float2
-                // addresses are 10 consecutive units of one FFT + 6 of the next, 170 = 10 (mod 16) units further on
-                const float* px = s_pcm + g * CS320 + 2 * t;
-                float2 x[28];
+        // The two column transforms of a worker (columns 2t, 2t+1) advance together in packed FADD2/FMUL2/FFMA2 instructions;
+        // re = frame A, im = frame B.  QR[b] / QI[b] = the window-folded first layer of the 20-point transform (win_first_layer).
+        f2 QR[5][4], QI[5][4];
+        const bool va = 2 * g < nvalid, vb = 2 * g + 1 < nvalid;   // ragged tail: missing frames are exact zeros
+        const float4 wth = *s_wth;
+        const f2 w_cos = make_float2(wth.x, wth.y), w_sin = make_float2(wth.z, wth.w);
+        auto win = [&](const int n1) { return fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f))); };
+        float2 x[28];
+        if (HOP160) {
+            // frames A and B overlap by 240 samples: B[n1] = A[n1 + 8], so 28 loads cover both (element m is
+            // sample 320g + 20m + 2t of the tile; chunk boundary at m = 16).  Conflict-free: a half-warp's 16 float2
+            // addresses are 10 consecutive units of one FFT + 6 of the next, 170 = 10 (mod 16) units further on
+            const float* px = s_pcm + g * CS320 + 2 * t;
 #pragma unroll
-                for (int m = 0; m < 28; ++m) x[m] = *reinterpret_cast<const float2*>(px + 20 * m + (m >= 16 ? PAD320 : 0));
-                if (nvalid == FPW) {
+            for (int m = 0; m < 28; ++m) x[m] = *reinterpret_cast<const float2*>(px + 20 * m + (m >= 16 ? PAD320 : 0));
+        } else if (nvalid > 0) {
+            const float* pa = s_pcm + 2 * g * hop + 2 * t;
+            const float* pb = pa + hop;
+            auto ld = [&](const float* q, const int n1, const bool v) {
+                return v ? make_float2(q[20 * n1], q[20 * n1 + 1]) : make_float2(0.f, 0.f);
+            };
 #pragma unroll
-                    for (int n1 = 0; n1 < 20; ++n1) {
-                        const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
-                        PR[n1] = mul2(x[n1], w);
-                        PI[n1] = mul2(x[n1 + 8], w);
-                    }
-                } else {
-#pragma unroll
-                    for (int n1 = 0; n1 < 20; ++n1) {
-                        const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
-                        PR[n1] = va ? mul2(x[n1], w) : make_float2(0.f, 0.f);
-                        PI[n1] = vb ? mul2(x[n1 + 8], w) : make_float2(0.f, 0.f);
-                    }
-                }
-            } else {
-                const float* pa = s_pcm + 2 * g * hop + 2 * t;
-                const float* pb = pa + hop;
-#pragma unroll
-                for (int n1 = 0; n1 < 20; ++n1) {
-                    const f2 w = fma2c(WC[n1], w_cos, fma2c(WS[n1], w_sin, make_float2(0.5f, 0.5f)));
-                    const float2 a = va ? make_float2(pa[20 * n1], pa[20 * n1 + 1]) : make_float2(0.f, 0.f);
-                    const float2 b = vb ? make_float2(pb[20 * n1], pb[20 * n1 + 1]) : make_float2(0.f, 0.f);
-                    PR[n1] = mul2(a, w);
-                    PI[n1] = mul2(b, w);
-                }
+            for (int b = 0; b < 5; ++b) {
+                const int n0 = (4 * b) % 20, n1 = (5 + 4 * b) % 20, n2 = (10 + 4 * b) % 20, n3 = (15 + 4 * b) % 20;
+                const f2 w0 = win(n0), w1 = win(n1), w2 = win(n2), w3 = win(n3);
+                win_first_layer(ld(pa, n0, va), ld(pa, n1, va), ld(pa, n2, va), ld(pa, n3, va), w0, w1, w2, w3, QR[b]);
+                win_first_layer(ld(pb, n0, vb), ld(pb, n1, vb), ld(pb, n2, vb), ld(pb, n3, vb), w0, w1, w2, w3, QI[b]);
             }
         }
-        __syncwarp();   // every lane has consumed its samples: the stage may be refilled
+        __syncwarp();   // every lane has read its samples (HOP160: the loads are ordered before the refill below; their values are
+                        // consumed after it, which keeps only the 56 sample registers live across the TMA issue)
         const int cur_clip = clip;
         if (++tin == p.wtiles_per_clip) { tin = 0; ++clip; }
         if (it + 1 < cnt) issue_load(clip, tin);
         if (nvalid == 0) continue;
+        if (HOP160) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                const int n0 = (4 * b) % 20, n1 = (5 + 4 * b) % 20, n2 = (10 + 4 * b) % 20, n3 = (15 + 4 * b) % 20;
+                const f2 w0 = win(n0), w1 = win(n1), w2 = win(n2), w3 = win(n3);
+                win_first_layer(x[n0], x[n1], x[n2], x[n3], w0, w1, w2, w3, QR[b]);
+                win_first_layer(x[n0 + 8], x[n1 + 8], x[n2 + 8], x[n3 + 8], w0, w1, w2, w3, QI[b]);
+            }
+            if (nvalid != FPW) {   // ragged tail (warp-uniform): frames past the clip's last one are exact zeros
+#pragma unroll
+                for (int b = 0; b < 5; ++b)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        QR[b][i] = va ? QR[b][i] : make_float2(0.f, 0.f);
+                        QI[b][i] = vb ? QI[b][i] : make_float2(0.f, 0.f);
+                    }
+            }
+        }
 
-        dft20x2(PR, PI);
+        {   // pair prescale (see pair_prescale).  Level of a frame = max |first-layer value| = max (|x0 w0| + |x2 w2|) over its windowed
+            // sample pairs: within a factor 2 of the peak windowed sample.  All-reduced over the FFT's 10 lanes.
+            float ma = 0.f, mb = 0.f;
+#pragma unroll
+            for (int b = 0; b < 5; ++b)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ma = fmaxf(fmaxf(ma, fabsf(QR[b][i].x)), fabsf(QR[b][i].y));   // FMNMX3 with |.| source modifiers
+                    mb = fmaxf(fmaxf(mb, fabsf(QI[b][i].x)), fabsf(QI[b][i].y));
+                }
+            int pk = pack_exponents(ma, mb);
+            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring));         // max is idempotent: ring distances 1, 2, 4, 8 cover
+            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 8));    // all 10 lanes, every lane ends with the same word
+            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 16));
+            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 24));
+            int ka, kb;
+            float4 tab;
+            pair_prescale(pk, p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);
+            s_scr[g] = tab;
+            if (__any_sync(0xffffffffu, (ka | kb) != 0)) {   // rare (onsets, decays, digital silence next to sound): exact scaling
+                const float ra = pow2i(ka), rb = pow2i(kb);
+#pragma unroll
+                for (int b = 0; b < 5; ++b)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { QR[b][i] = mul2c(ra, QR[b][i]); QI[b][i] = mul2c(rb, QI[b][i]); }
+            }
+        }
+        f2 PR[20], PI[20];
+        dft20x2_rest(QR, QI, PR, PI);
         {   // row 10 carries an extra W_40^(-c) so that worker 0 can treat it like a "row 20 - t"
             const float4 rot = *s_rot;
             const f2 rx = make_float2(rot.x, rot.y), ry = make_float2(rot.z, rot.w);
@@ -534,16 +658,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             float2* const pl = s_p + (g == 0 ? 0 : g == 1 ? PPLANE1 : PPLANE2);
             float2* const p_lo = pl + (t0 ? 10 : t);
             float2* const p_hi = pl - t;
+            // Slots j and 20 - j are formed together.  Generic worker: slot 20-j = (X[20-j], D[j]), slot j = (X[j], D[20-j]), i.e.
+            // register 20-j against register j with its halves exchanged.  Worker 0: slot 20-j = (X[20-j], X[j]), slot j = (D[20-j], D[j+1]).
 #pragma unroll
-            for (int j = 0; j < 20; ++j) {
-                float ur = XR[j].x, ui = XI[j].x, vr = XR[(20 - j) % 20].y, vi = XI[(20 - j) % 20].y;
-                if (j < 10) { ur = t0 ? XR[j + 1].y : ur; ui = t0 ? XI[j + 1].y : ui; }
-                else        { vr = t0 ? XR[20 - j].x : vr; vi = t0 ? XI[20 - j].x : vi; }
+            for (int j = 1; j < 10; ++j) {
+                const f2 opr = t0 ? make_float2(XR[j].x, XR[j + 1].y) : make_float2(XR[j].y, XR[j].x);
+                const f2 opi = t0 ? make_float2(XI[j].x, XI[j + 1].y) : make_float2(XI[j].y, XI[j].x);
+                float2 phi, plo;
+                untangle2(XR[20 - j], XI[20 - j], opr, opi, phi, plo);   // .x halves -> slot 20-j, .y halves -> slot j
+                p_lo[20 * j] = plo;
+                p_hi[20 * j] = phi;
+            }
+#pragma unroll
+            for (int j = 0; j < 20; j += 10) {   // slots 0 and 10 pair a register with itself
+                float ur = XR[j].x, ui = XI[j].x, vr = XR[j].y, vi = XI[j].y;
+                if (j == 0) { ur = t0 ? XR[1].y : ur; ui = t0 ? XI[1].y : ui; }
+                else        { vr = t0 ? XR[10].x : vr; vi = t0 ? XI[10].x : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 const float pwa = fmaf(sr, sr, di * di);   // 4|A[k]|^2
                 const float pwb = fmaf(si, si, dr * dr);   // 4|B[k]|^2
-                if (j < 10) p_lo[20 * j] = make_float2(pwa, pwb);
-                else        p_hi[20 * (20 - j)] = make_float2(pwa, pwb);
+                if (j == 0) p_lo[0] = make_float2(pwa, pwb);
+                else        p_hi[200] = make_float2(pwa, pwb);
             }
         }
         __syncwarp();
@@ -563,6 +698,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             const float* wt = s_projw + lane;                                                          // [entry][lane]
             int eoff = 0;
+            const float4 ps0 = s_scr[0], ps1 = s_scr[1], ps2 = s_scr[2];   // pair prescale: (floor, log offset) of the six frames
+            const float flq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z, ps2.x, ps2.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w, ps2.y, ps2.w};
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const float2* pr = s_p + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
@@ -604,7 +741,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 const float a[FPW] = {acc0.x, acc0.y, acc1.x, acc1.y, acc2.x, acc2.y};
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
-                    lg[s][q] = p.log_mul * lg2_normal(fmaxf(a[q], p.floor_val));
+                    lg[s][q] = fmaf(p.log_mul, lg2_normal(fmaxf(a[q], flq[q])), cq[q]);
                     mx[q] = fmaxf(mx[q], lg[s][q]);
                 }
             }
@@ -776,6 +913,7 @@ constexpr int FPW = 4;
 constexpr int ZROWB = 144;                   // bytes per Z row: 16 complex + 16 B pad  (9 units: odd => conflict-free LDS.128)
 constexpr int ZSLABB = 32 * ZROWB + 64;      // 4672 B per FFT (292 units = 4 mod 8: the two FFTs of a quarter-warp never collide)
 constexpr int ZBYTES = 2 * ZSLABB;           // 9344 per warp
+constexpr int SCRBYTES = 32;                 // behind the slab: the pair prescale's per-frame (floor, log offset), one float4 per FFT
 constexpr int PBYTES = 258 * 16;             // power rows in natural bin order 0..256, one float4 (A0, B0, A1, B1) per row
 constexpr int STAGE_MAX = ZBYTES - PBYTES;
 constexpr int CHUNK = 320;
@@ -807,6 +945,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     float2* s_p2 = reinterpret_cast<float2*>(s_warp);
     float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
+    float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor or guard, log offset) of frames A and B per FFT
     const uint32_t bar = smem_u32(smem + 8 * warp);
 
     // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
@@ -999,6 +1138,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         if (wt_next < p.n_wtiles) issue_load(clip_next, tin_next);
         if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
 
+        {   // pair prescale (see pair_prescale): peak levels of the two prepared frames, all-reduced over the FFT's 16 lanes
+            float ma = 0.f, mb = 0.f;
+#pragma unroll
+            for (int a = 0; a < (NROW + 1) / 2; ++a) {
+                ma = fmaxf(fmaxf(ma, fabsf(er[a].x)), fabsf(er[a].y));
+                mb = fmaxf(fmaxf(mb, fabsf(ei[a].x)), fabsf(ei[a].y));
+            }
+            int pk = pack_exponents(ma, mb);
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) pk = __vmaxu2(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+            int ka, kb;
+            float4 tab;
+            pair_prescale(pk, NEMO ? p.log_add : p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);
+            s_scr[g1] = tab;
+            if (__any_sync(0xffffffffu, (ka | kb) != 0)) {   // rare: exact power-of-two scaling of a frame
+                const float ra = pow2i(ka), rb = pow2i(kb);
+#pragma unroll
+                for (int a = 0; a < 16; ++a) { er[a] = mul2c(ra, er[a]); ei[a] = mul2c(rb, ei[a]); }
+            }
+        }
         float ar[32], ai[32];
         dft32_packed(er, ei, ar, ai);
         {   // row 16 carries an extra W_32^(-c)
@@ -1039,15 +1198,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const bool t0 = (t == 0);
             float2* const p_lo = s_p2 + 2 * (t0 ? 16 : t) + g3;
             float2* const p_hi = s_p2 - 2 * t + g3;
+            // slots j and 16 - j together (see melspec400_kernel): register 16-j against register j with its halves exchanged
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float ur = XR[j].x, ui = XI[j].x, vr = XR[(16 - j) % 16].y, vi = XI[(16 - j) % 16].y;
-                if (j < 8) { ur = t0 ? XR[j + 1].y : ur; ui = t0 ? XI[j + 1].y : ui; }
-                else       { vr = t0 ? XR[16 - j].x : vr; vi = t0 ? XI[16 - j].x : vi; }
+            for (int j = 1; j < 8; ++j) {
+                const f2 opr = t0 ? make_float2(XR[j].x, XR[j + 1].y) : make_float2(XR[j].y, XR[j].x);
+                const f2 opi = t0 ? make_float2(XI[j].x, XI[j + 1].y) : make_float2(XI[j].y, XI[j].x);
+                float2 phi, plo;
+                untangle2(XR[16 - j], XI[16 - j], opr, opi, phi, plo);   // .x halves -> slot 16-j, .y halves -> slot j
+                p_lo[64 * j] = plo;
+                p_hi[64 * j] = phi;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {   // slots 0 and 8 pair a register with itself
+                float ur = XR[j].x, ui = XI[j].x, vr = XR[j].y, vi = XI[j].y;
+                if (j == 0) { ur = t0 ? XR[1].y : ur; ui = t0 ? XI[1].y : ui; }
+                else        { vr = t0 ? XR[8].x : vr; vi = t0 ? XI[8].x : vi; }
                 const float sr = ur + vr, di = ui - vi, si = ui + vi, dr = ur - vr;
                 const float2 pw = make_float2(fmaf(sr, sr, di * di), fmaf(si, si, dr * dr));
-                if (j < 8) p_lo[64 * j] = pw;
-                else       p_hi[64 * (16 - j)] = pw;
+                if (j == 0) p_lo[0] = pw;
+                else        p_hi[64 * 8] = pw;
             }
         }
         __syncwarp();
@@ -1061,6 +1230,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             // windowed projection (see melspec400_kernel): the lane's K_s entries are consecutive power rows from its window
             // start, so the loads do not depend on the table and pipeline freely; weights come from [entry][lane]
             const float* wt = s_projw + lane;
+            const float4 ps0 = s_scr[0], ps1 = s_scr[1];   // pair prescale: (floor or guard, log offset) of the four frames
+            const float vq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w};
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int K = s_meta[s] & 0xffff;
@@ -1078,8 +1249,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 const float acc[FPW] = {acc01.x, acc01.y, acc23.x, acc23.y};
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
-                    const float e = fmaxf(acc[q], p.floor_val) + p.log_add;
-                    lg[s][q] = p.log_mul != 0.f ? p.log_mul * lg2_normal(e) : e;
+                    const float e = NEMO ? acc[q] + vq[q] : fmaxf(acc[q], vq[q]);   // ln(E + guard) / log(max(E, floor)), prescaled
+                    lg[s][q] = fmaf(p.log_mul, lg2_normal(e), cq[q]);
                     mx[q] = fmaxf(mx[q], lg[s][q]);
                 }
             }
@@ -1327,6 +1498,28 @@ __global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long 
     for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float inv = 1.0f / (sqrtf(var / fmaxf((float)frames - 1.0f, 1.0f)) + 1e-5f);
     for (int f = lane; f < frames; f += 32) r[f] = (r[f] - mean) * inv;
+}
+
+// ================================================================================================ 16-bit PCM input
+// x / 32768 for the int16 host entry (melspec_compute_host_i16): exact in f32, so the features equal those of the f32 entry
+// on the converted samples.  HBM-bound byte work: 2 bytes read + 4 written per sample; 8 samples per thread where the rows
+// allow 16-byte loads.  grid = (blocks, rows).
+__global__ void __launch_bounds__(256) melspec_i16_to_f32_kernel(const int16_t* in, long long in_stride, int n, float* out,
+                                                                 long long out_stride, int vec) {
+    const int16_t* src = in + (long long)blockIdx.y * in_stride;
+    float* dst = out + (long long)blockIdx.y * out_stride;
+    const float sc = 1.0f / 32768.0f;
+    const int n8 = vec ? n / 8 : 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n8; i += gridDim.x * 256) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(src) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { f[2 * k] = (float)(short)(w[k] & 0xffff) * sc; f[2 * k + 1] = (float)(w[k] >> 16) * sc; }
+        reinterpret_cast<float4*>(dst)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (int i = 8 * n8 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = (float)src[i] * sc;
 }
 
 // ================================================================================================ output formats

@@ -214,6 +214,32 @@ def whisper_mel_stream(samples: np.ndarray, fft_size: int = 512, hop_size: int =
     return norm_mel_f64(project_stft_log10(st, filters)).astype(np.float32)
 
 
+def spectrogram_add_mel(chunks, fft_size: int = 400, hop_size: int = 160, n_mels: int = 80, sampling_rate: float = 16000.0):
+    """`Spectrogram::add` (src/stft.rs:48-86) called once per element of `chunks`, each followed by `MelSpectrogram::add`
+    (src/mel.rs:26-31).  Every chunk has <= hop_size samples (the reference asserts, stft.rs:53); a short chunk is zero-padded
+    to a whole hop (stft.rs:56-59); `idx` counts the true samples only (stft.rs:64); a frame is returned once idx >= fft_size
+    (stft.rs:66), i.e. with every call from then on.  Returns a list with one (n_mels,) f32 array or None per call."""
+    window = hann_window(fft_size)
+    filters = slaney_mel_filterbank(sampling_rate, fft_size, n_mels)
+    hop_buf = np.zeros(fft_size, dtype=np.float64)
+    idx = 0
+    out = []
+    for c in chunks:
+        c = np.asarray(c, dtype=np.float32).astype(np.float64).reshape(-1)
+        assert c.size <= hop_size, "frames must be <= hop_size"
+        pcm = np.zeros(hop_size, dtype=np.float64)
+        pcm[:c.size] = c
+        hop_buf[:fft_size - hop_size] = hop_buf[hop_size:].copy()
+        hop_buf[fft_size - hop_size:] = pcm
+        idx += c.size
+        if idx >= fft_size:
+            st = np.fft.fft((hop_buf * window)[None, :], axis=1)
+            out.append(norm_mel_f64(project_stft_log10(st, filters)).astype(np.float32)[0])
+        else:
+            out.append(None)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # Kaldi fbank path (src/fbank.rs)
 # --------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(m):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     assert sorted(m.EXPORTS) == declared
-    assert L.melspec_abi_version() == 1
+    assert L.melspec_abi_version() == 2
 
 
 def test_filterbanks_match_golden_and_oracle(m, golden_dir):

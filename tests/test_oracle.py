@@ -161,3 +161,14 @@ def test_c_oracle_matches_numpy_oracle_at_general_sizes(fft, hop, n_mels):
     a = oc.whisper_batch(x, fft, hop, n_mels, 16000.0, threads=2)
     b = np.stack([o.whisper_mel_batch(x[i], fft, hop, n_mels, 16000.0) for i in range(2)])
     assert a.shape == b.shape and np.abs(a - b).max() <= 1e-6
+
+
+def test_spectrogram_add_contract(jfk):
+    """src/stft.rs:175-194 (`test_spectrogram_add`, fft 8 / hop 4): 3 samples -> None, 4 more (7 < 8) -> None, 4 more -> Some;
+    and fed whole hops the per-call restatement equals the stream restatement that is pinned on rust_jfk_golden.npy."""
+    got = o.spectrogram_add_mel([[1.0, 2.0, 3.0], [1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 3.0, 4.0]], 8, 4, 4, 16000.0)
+    assert got[0] is None and got[1] is None and got[2] is not None and got[2].shape == (4,)
+    x = jfk[:16000]
+    hops = [x[i:i + 160] for i in range(0, 16000, 160)]
+    per_call = [f for f in o.spectrogram_add_mel(hops, 400, 160, 80, 16000.0) if f is not None]
+    assert np.array_equal(np.stack(per_call), o.whisper_mel_stream(x, 400, 160, 80, 16000.0))
