@@ -332,7 +332,7 @@ def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps
     del scratch
     # opt-in 16-bit PCM entry: half the H2D bytes, converted in the kernel's prologue (bit-identical to f32 input of the same samples)
     e2e_i16 = None
-    if frontend == "whisper" and hasattr(h, "compute_host_i16_raw"):
+    if frontend == "whisper" and hasattr(ms.lib(), "melspec_compute_host_i16"):
         hx16 = torch.empty((clips, n_samples), dtype=torch.int16, pin_memory=True)
         hx16.copy_((x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
         hout16 = torch.empty((clips, F, n_mels), dtype=torch.float32, pin_memory=True)

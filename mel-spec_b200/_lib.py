@@ -113,12 +113,6 @@ def lib() -> C.CDLL:
     L.melspec_stream_create.argtypes = [vp, i64, C.POINTER(vp)]
     L.melspec_stream_push.restype = i32
     L.melspec_stream_push.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
-    L.melspec_stream_push_hop.restype = i32
-    L.melspec_stream_push_hop.argtypes = [vp, vp, i64, vp, C.POINTER(i32)]
-    L.melspec_compute_host_i16.restype = i32
-    L.melspec_compute_host_i16.argtypes = [vp, vp, i64, i64, i64, vp, i32, C.POINTER(i64)]
-    L.melspec_convert_i16_device.restype = i32
-    L.melspec_convert_i16_device.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
     L.melspec_stream_reset.restype = i32
     L.melspec_stream_reset.argtypes = [vp]
     L.melspec_stream_destroy.restype = None
@@ -150,6 +144,14 @@ def lib() -> C.CDLL:
     L.melspec_vad_activity_device.argtypes = [vp, vp, i64, i64, i32, i64, vsp, vp, i64, vp]
     L.melspec_vad_host.restype = i32
     L.melspec_vad_host.argtypes = [vp, vp, i32, i64, vsp, vp, vp]
+    # ABI version 2 (an older build loaded through MELSPEC_B200_LIB for an A/B measurement does not have these)
+    if not (os.environ.get("MELSPEC_B200_LIB") and not hasattr(L, "melspec_stream_push_hop")):
+        L.melspec_stream_push_hop.restype = i32
+        L.melspec_stream_push_hop.argtypes = [vp, vp, i64, vp, C.POINTER(i32)]
+        L.melspec_compute_host_i16.restype = i32
+        L.melspec_compute_host_i16.argtypes = [vp, vp, i64, i64, i64, vp, i32, C.POINTER(i64)]
+        L.melspec_convert_i16_device.restype = i32
+        L.melspec_convert_i16_device.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
     _LIB = L
     return L
 

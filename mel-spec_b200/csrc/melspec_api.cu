@@ -724,7 +724,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * kMetaInts, 128);
     p.smem_cmn = (int)off;
-    if (h->plan == 512) off = up(off + sizeof(float) * 128 * (12 + 1), 128);   // fused CMN: column sums per warp + means
+    // fused CMN: mode 1 column sums per warp + means; mode 2 two sets of column sums + kCmnRows replicated rows of -mean
+    if (h->plan == 512) off = up(off + sizeof(float) * 128 * (size_t)(kaldi && c.cmn ? 2 * 12 + p512::kCmnRows : 12 + 1), 128);
     p.smem_warp0 = (int)off;
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
     static_assert(p512::FPW * 32 * kMaxMpl * 4 <= p512::STAGE_MAX, "output rows must fit behind the power rows");
@@ -742,13 +743,17 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     const int nw = warps_per_cta(h->plan);
     // Kaldi CMN inside the fused kernel: one CTA works through whole clips (see melspec512_kernel).  Needs enough clips to
     // fill the GPU, enough tiles per clip for every warp, and float4-addressable rows; otherwise CMN stays a second kernel.
-    static const bool cmn_fuse_enabled = [] { const char* e = std::getenv("MELSPEC_CMN_FUSED"); return !(e && e[0] == '0'); }();
+    // MELSPEC_CMN_FUSED: 0 = CMN as a second kernel, 1 = block barrier + in-place subtraction by the CTA (round 1), 2 (default) =
+    // no barrier, subtraction by TMA bulk reductions at the L2
+    static const int cmn_fuse_mode = [] { const char* e = std::getenv("MELSPEC_CMN_FUSED"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2; }();
+    const bool cmn_fuse_enabled = cmn_fuse_mode != 0;
     p.n_clips = (int)n_clips;
     p.vec_out = (layout == MELSPEC_LAYOUT_FRAME_MAJOR) && ((uintptr_t)d_out % 16 == 0) && (c.n_mels % 4 == 0) && (p.out_clip_stride % 4 == 0);
     const bool fused_cmn = cmn_fuse_enabled && kaldi && c.cmn && h->plan == 512 && layout == MELSPEC_LAYOUT_FRAME_MAJOR && p.vec_out &&
                            n_clips >= h->num_sms && p.wtiles_per_clip >= 2 * nw && c.n_mels <= 128;
-    p.cmn_fused = fused_cmn ? 1 : 0;
-    if (fused_cmn) p.bulk_out = 0;   // plain stores: the CTA re-reads its own rows after a block barrier
+    p.cmn_fused = fused_cmn ? cmn_fuse_mode : 0;
+    if (fused_cmn && cmn_fuse_mode == 1) p.bulk_out = 0;   // mode 1: plain stores, the CTA re-reads its own rows after a block barrier
+    if (fused_cmn && cmn_fuse_mode == 2 && !p.bulk_out) p.cmn_fused = 1;   // (bulk reductions need the bulk-store alignment)
     off += (size_t)p.smem_warp_stride * nw;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;

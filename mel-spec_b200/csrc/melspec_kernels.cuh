@@ -113,6 +113,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
+// L2 eviction policies for the bulk copies.  The PCM is read once (evict_first: it must not push the output rows of the clips in
+// flight out of L2); rows that a later pass touches again (Kaldi CMN) are written evict_last and released by that pass.
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+#ifdef MELSPEC_NO_L2_HINTS   // A/B switch
+    (void)pol;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+    return;
+#endif
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+// TMA bulk reduction: global[dst + i] += shared[src + i] for bytes / 4 floats, performed at the L2 (no data comes back to the SM).
+__device__ __forceinline__ void bulk_reduce_add_f32(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.f32 [%0], [%1], %2, %3;" ::"l"(dst), "r"(src),
+                 "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -432,8 +466,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor, log offset) of frames A and B per FFT (48 of
                                                                   // the 64 bytes between the slab and the 128-byte aligned PCM stage)
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
-    // lanes of this FFT at ring distance 1, 2, 4, 8 (one byte each): the all-reduce of the pair prescale
-    const int ring = (10 * g + (t + 1) % 10) | (10 * g + (t + 2) % 10) << 8 | (10 * g + (t + 4) % 10) << 16 | (10 * g + (t + 8) % 10) << 24;
+    const uint64_t pol_in = l2_evict_first();                 // PCM is read once: it must not displace output rows in L2
+    // lanes of this FFT at ring distance 1, 2 | 3, 6, 9 (six bits each): the two-round all-reduce of the pair prescale
+    const int ring = (10 * g + (t + 1) % 10) | (10 * g + (t + 2) % 10) << 6 | (10 * g + (t + 3) % 10) << 12 | (10 * g + (t + 6) % 10) << 18 |
+                     (10 * g + (t + 9) % 10) << 24;
 
     // ---- one-time setup: tables into shared memory, barriers, per-lane window / twiddle registers
     for (int i = threadIdx.x; i < 2 * p.proj_ktot * 32; i += NWARPS * 32)
@@ -497,9 +533,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
                     for (int k = 0; k < NCHUNK; ++k)
                         if (CHUNK * k < avail)
-                            bulk_g2s(smem_u32(s_pcm + k * CS320), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar);
+                            bulk_g2s_hint(smem_u32(s_pcm + k * CS320), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar, pol_in);
                 } else {
-                    bulk_g2s(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar);
+                    bulk_g2s_hint(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar, pol_in);
                 }
             }
         } else {   // unaligned input: cooperative copy (same layout), then a plain arrive
@@ -599,10 +635,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     mb = fmaxf(fmaxf(mb, fabsf(QI[b][i].x)), fabsf(QI[b][i].y));
                 }
             int pk = pack_exponents(ma, mb);
-            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring));         // max is idempotent: ring distances 1, 2, 4, 8 cover
-            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 8));    // all 10 lanes, every lane ends with the same word
-            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 16));
-            pk = __vmaxu2(pk, __shfl_sync(0xffffffffu, pk, ring >> 24));
+            {   // max is idempotent: ring distances {0, 1, 2} then {0, 3, 6, 9} of the result cover all 10 lanes in two dependent
+                // rounds (the shuffles of a round are independent), and every lane ends with the same word
+                const int a1 = __shfl_sync(0xffffffffu, pk, ring), a2 = __shfl_sync(0xffffffffu, pk, ring >> 6);
+                pk = __vmaxu2(__vmaxu2(pk, a1), a2);
+                const int b1 = __shfl_sync(0xffffffffu, pk, ring >> 12), b2 = __shfl_sync(0xffffffffu, pk, ring >> 18),
+                          b3 = __shfl_sync(0xffffffffu, pk, ring >> 24);
+                pk = __vmaxu2(__vmaxu2(pk, b1), __vmaxu2(b2, b3));
+            }
             int ka, kb;
             float4 tab;
             pair_prescale(pk, p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);
@@ -913,6 +953,7 @@ constexpr int FPW = 4;
 constexpr int ZROWB = 144;                   // bytes per Z row: 16 complex + 16 B pad  (9 units: odd => conflict-free LDS.128)
 constexpr int ZSLABB = 32 * ZROWB + 64;      // 4672 B per FFT (292 units = 4 mod 8: the two FFTs of a quarter-warp never collide)
 constexpr int ZBYTES = 2 * ZSLABB;           // 9344 per warp
+constexpr int kCmnRows = 24;                 // rows per bulk reduction of the fused CMN (24 x 80 floats = 7680 bytes)
 constexpr int SCRBYTES = 32;                 // behind the slab: the pair prescale's per-frame (floor, log offset), one float4 per FFT
 constexpr int PBYTES = 258 * 16;             // power rows in natural bin order 0..256, one float4 (A0, B0, A1, B1) per row
 constexpr int STAGE_MAX = ZBYTES - PBYTES;
@@ -925,6 +966,9 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 -
 
 // MODE 0: Whisper fft 512.  MODE 1: Kaldi fbank.  MODE 2: NeMo BatchLogMel (whole-waveform pre-emphasis, frames may
 // hang over both ends of the clip: the missing samples are zero-filled in the stage, reference src/mel.rs:344-348,685-706).
+#ifndef TWREG512
+#define TWREG512 true
+#endif
 template <int NWARPS, int MPL, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
@@ -947,6 +991,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
     float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor or guard, log offset) of frames A and B per FFT
     const uint32_t bar = smem_u32(smem + 8 * warp);
+    const uint64_t pol_in = l2_evict_first();                 // PCM is read once: it must not displace output rows in L2
 
     // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
     for (int i = threadIdx.x; i < 512; i += NWARPS * 32) reinterpret_cast<float*>(smem + p.smem_win)[i] = reinterpret_cast<const float*>(p.window)[i];
@@ -956,11 +1001,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     for (int i = threadIdx.x; i < kMetaInts; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
         mbar_init(bar, 1);
+        if (warp == 0) {   // fused CMN, mode 2: "all warps have finished clip" x 2 parities, "sums consumed" x 2 parities
+            mbar_init(smem_u32(smem + 8 * NWARPS), NWARPS);
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 1)), NWARPS);
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 2)), 1);
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 3)), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const float* s_win = reinterpret_cast<const float*>(smem + p.smem_win) + c;
     const float4* s_tw = reinterpret_cast<const float4*>(smem + p.smem_tw) + t;
     const float2 r16 = __ldg(p.rot10 + c);     // W_32^(-c): pre-rotation of row 16
+#ifdef MELSPEC_TW_SMEM
+    constexpr bool TW_IN_REGS = false;
+#else
+    constexpr bool TW_IN_REGS = TWREG512;
+#endif
+    float4 twreg[8];
+    if (TW_IN_REGS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) twreg[i] = __ldg(p.twiddle + 16 * i + t);
+    }
     __syncthreads();
 
     const int need = (FPW - 1) * 160 + p.frame_len;
@@ -990,7 +1051,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                     for (int k = 0; k < NCHUNK; ++k) {
                         const int a = max(lo, CHUNK * k), b = min(hi, CHUNK * (k + 1));
-                        if (a < b) bulk_g2s(smem_u32(s_pcm + k * CS + (a - CHUNK * k)), tsrc + a, (uint32_t)(b - a) * 4u, bar);
+                        if (a < b) bulk_g2s_hint(smem_u32(s_pcm + k * CS + (a - CHUNK * k)), tsrc + a, (uint32_t)(b - a) * 4u, bar, pol_in);
                     }
                 }
             } else {
@@ -1004,7 +1065,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                 for (int k = 0; k < NCHUNK; ++k)
                     if (CHUNK * k < avail)
-                        bulk_g2s(smem_u32(s_pcm + k * CS), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar);
+                        bulk_g2s_hint(smem_u32(s_pcm + k * CS), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar, pol_in);
             }
         } else {
             for (int i = lane; i < avail; i += 32) s_pcm[i + PAD * (i / CHUNK)] = __ldg(src + i);
@@ -1037,6 +1098,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         return cl * p.wtiles_per_clip + warp;
     };
     float csum[MPL];
+    int cmn_iter = 0;   // clips this CTA has finished (fused CMN, mode 2)
 #pragma unroll
     for (int s = 0; s < MPL; ++s) csum[s] = 0.f;
     if (wt < p.n_wtiles) issue_load(clip_f, tile_in_clip);
@@ -1060,26 +1122,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1
-        // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet
+        // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet.
+        // The samples (and their pre-emphasis partners) are read before the refill of the stage is issued; everything else
+        // happens after it, which keeps only the NLOAD sample registers live across the TMA issue.
         f2 er[16], ei[16];
+        const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
+        float x[NLOAD];
+        float sa = 0.f, sb = 0.f, x0 = 0.f;
         if (nvalid > 0) {
-            const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
             const float* px = s_pcm + g1 * CS + c;
-            float x[NLOAD];
 #pragma unroll
             for (int m = 0; m < NLOAD; ++m) x[m] = px[16 * m + PAD * (m / 20)];
-            if (!FRAME400) {
-#pragma unroll
-                for (int a = 0; a < 16; ++a) {
-                    const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
-                    er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
-                    ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
-                }
-            } else {
+            if (FRAME400) {
                 // d[m] = x[m] - preemph * x[m-1]; the previous sample is one word back (one chunk pad further back at a
                 // chunk start); frame sums for the DC removal are reduced over the 16 lanes of the FFT
-                float sa = 0.f, sb = 0.f;
-                const float x0 = x[0];
+                x0 = x[0];
 #pragma unroll
                 for (int m = 0; m < NLOAD; ++m) {
                     float xp;
@@ -1093,43 +1150,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     if (KALDI && m >= 10) sb += x[m];
                     x[m] = fmaf(-p.preemph, xp, x[m]);
                 }
-                float ka = 0.f, kb = 0.f;
-                if (KALDI) {
-#pragma unroll
-                    for (int o = 8; o >= 1; o >>= 1) {
-                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                    }
-                    const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
-                    if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
-                    ka = (1.0f - p.preemph) * mu_a; kb = (1.0f - p.preemph) * mu_b;
-                } else {
-                    // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
-                    // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
-                    const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
-                    if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
-#pragma unroll
-                        for (int m = 0; m < NLOAD; ++m)
-                            if (rel == 16 * m) x[m] = 0.f;
-                    }
-                    (void)x0;
-                }
-#pragma unroll
-                for (int a = 0; a < 16; ++a) {
-                    float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
-                    if (2 * a < NROW) {
-                        const float w0 = s_win[32 * a];
-                        r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
-                        i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
-                    }
-                    if (2 * a + 1 < NROW) {
-                        const float w1 = s_win[32 * a + 16];
-                        r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
-                        i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
-                    }
-                    er[a] = make_float2(r0, r1);
-                    ei[a] = make_float2(i0, i1);
-                }
             }
         }
         __syncwarp();
@@ -1137,6 +1157,52 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const int wt_next = next_tile(wt, tin_next, clip_next);
         if (wt_next < p.n_wtiles) issue_load(clip_next, tin_next);
         if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
+
+        if (!FRAME400) {
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
+                er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
+                ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
+            }
+        } else {
+            float ka = 0.f, kb = 0.f;
+            if (KALDI) {
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
+                if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
+                ka = (1.0f - p.preemph) * mu_a; kb = (1.0f - p.preemph) * mu_b;
+            } else {
+                // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
+                // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
+                const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
+                if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
+#pragma unroll
+                    for (int m = 0; m < NLOAD; ++m)
+                        if (rel == 16 * m) x[m] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
+                if (2 * a < NROW) {
+                    const float w0 = s_win[32 * a];
+                    r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
+                    i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
+                }
+                if (2 * a + 1 < NROW) {
+                    const float w1 = s_win[32 * a + 16];
+                    r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
+                    i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
+                }
+                er[a] = make_float2(r0, r1);
+                ei[a] = make_float2(i0, i1);
+            }
+        }
 
         {   // pair prescale (see pair_prescale): peak levels of the two prepared frames, all-reduced over the FFT's 16 lanes
             float ma = 0.f, mb = 0.f;
@@ -1181,7 +1247,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const float4* z2 = reinterpret_cast<const float4*>(s_warp + g3 * ZSLABB + ZROWB * (16 + t));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 v = z1[i], u = z2[i], w = s_tw[16 * i];
+                const float4 v = z1[i], u = z2[i], w = TW_IN_REGS ? twreg[i] : s_tw[16 * i];
                 const int n = 2 * i, m = 2 * i + 1;
                 XR[n] = make_float2(v.x * w.x - v.y * w.y, fmaf(u.x, w.x, u.y * w.y));
                 XI[n] = make_float2(fmaf(v.x, w.y, v.y * w.x), u.y * w.x - u.x * w.y);
@@ -1275,7 +1341,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
+                    if (fused) bulk_s2g_hint(dst, smem_u32(s_stage), (uint32_t)nout * 4u, l2_evict_last());   // the CMN reduction comes back for these rows
+                    else bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
                     bulk_commit();
                 }
             } else if (p.vec_out) {
@@ -1344,7 +1411,57 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         }   // nvalid != 0
 
         // ------------------------------------------------------------------ fused CMN: end of this warp's share of the clip
-        if (fused && clip_next != clip) {
+        // Mode 2 (default): no CTA-wide barrier and no second pass through the SM.  Every warp delivers its column sums and
+        // signals an mbarrier once its own bulk stores of the clip have completed, then carries on with the next clip.  Warp 0
+        // alone waits for the twelve arrivals, forms the means in a fixed order and hands the subtraction to the TMA engine:
+        // bulk reductions  out[row][mel] += -mean[mel]  (cp.reduce.async.bulk .add.f32, kCmnRows rows per operation) that the L2
+        // applies to the rows the CTA wrote a few microseconds earlier (written evict_last, released evict_first by the
+        // reduction).  x + (-m) rounds like x - m, so the result equals the two-pass form bit for bit.
+        if (fused && p.cmn_fused == 2 && clip_next != clip) {
+            const int par = cmn_iter & 1;
+            float* s_cs = reinterpret_cast<float*>(smem + p.smem_cmn) + par * (NWARPS * 128);   // [2][NWARPS][128]
+            float* s_neg = reinterpret_cast<float*>(smem + p.smem_cmn) + 2 * NWARPS * 128;      // [kCmnRows][n_mels]: -mean, replicated
+            const uint32_t bar_done = smem_u32(smem + 8 * (NWARPS + par)), bar_free = smem_u32(smem + 8 * (NWARPS + 2 + par));
+            if (cmn_iter >= 2) mbar_wait(bar_free, ((cmn_iter >> 1) - 1) & 1);   // warp 0 has consumed this buffer's previous sums
+#pragma unroll
+            for (int s = 0; s < MPL; ++s) {
+                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                if (mel >= 0) s_cs[warp * 128 + mel] = csum[s];
+                csum[s] = 0.f;
+            }
+            if (lane == 0) bulk_wait0();   // this warp's rows of the clip have landed
+            __syncwarp();                  // (orders every lane's sums before lane 0's arrival)
+            if (lane == 0) mbar_arrive(bar_done);
+            if (warp == 0) {
+                mbar_wait(bar_done, (cmn_iter >> 1) & 1);
+                if (lane == 0) bulk_wait_read0();   // the previous clip's reductions have read s_neg
+                __syncwarp();
+                if (nfr > 0) {
+                    for (int mel = lane; mel < p.n_mels; mel += 32) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int w = 0; w < NWARPS; ++w) sum += s_cs[w * 128 + mel];
+                        const float neg = -(sum / (float)nfr);
+                        for (int r = 0; r < kCmnRows; ++r) s_neg[r * p.n_mels + mel] = neg;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        float* base = p.out + (long long)clip * p.out_clip_stride;
+                        const uint64_t pol = l2_evict_first();
+                        for (int r0 = 0; r0 < nfr; r0 += kCmnRows) {
+                            const int rows = min(kCmnRows, nfr - r0);
+                            bulk_reduce_add_f32(base + (long long)r0 * p.n_mels, smem_u32(s_neg), (uint32_t)(rows * p.n_mels) * 4u, pol);
+                        }
+                        bulk_commit();   // (s_neg is rewritten one clip later; every pass waits for the reads of all groups first)
+                    }
+                }
+                if (lane == 0) mbar_arrive(bar_free);
+            }
+            ++cmn_iter;
+        }
+        // Mode 1 (MELSPEC_CMN_FUSED=1, the round-1 form, kept for A/B): block barrier, then all threads subtract in place.
+        if (fused && p.cmn_fused == 1 && clip_next != clip) {
             float* s_cs = reinterpret_cast<float*>(smem + p.smem_cmn);       // [NWARPS][128]
             float* s_mean = s_cs + NWARPS * 128;                             // [128]
 #pragma unroll

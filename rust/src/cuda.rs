@@ -1,17 +1,19 @@
 //! Drop-in replacement for the reference's `src/cuda.rs` (wavey-ai/mel-spec): same public items
-//! (`CudaError`, `CudaMelSpectrogram::{new, compute_mel_spectrogram, max_frames_per_batch}`), but the private
-//! `mod ffi` now binds the melspec_b200 C ABI (`include/melspec_b200.h`) instead of cudart + cuFFT +
-//! `launch_mel_kernel` (reference src/cuda.rs:185-220).
+//! (`CudaError`, `CudaMelSpectrogram::{new, compute_mel_spectrogram, max_frames_per_batch}`, reference src/cuda.rs:10-155),
+//! but everything below them is the melspec_b200 C ABI (`crate::ffi`) instead of cudart + cuFFT + `launch_mel_kernel`.
 //!
 //! SOURCE ONLY: this image has no cargo/rustc, so this file is not compiled or tested here; everything it calls
-//! is exercised through the same C ABI from Python (`tests/`) — see INTEGRATION.md.
-use std::ffi::{c_char, c_void, CStr};
+//! is exercised through the same C ABI from Python and C++ (`tests/`) — see INTEGRATION.md.
+use crate::ffi;
+use std::ffi::c_void;
 use std::ptr;
 
+/// Same shape as the reference's enum (src/cuda.rs:10-14): `Unavailable` carries a `&'static str`, so callers that match
+/// on it keep compiling.  The library's own (dynamic) error text goes into `Runtime`.
 #[derive(Debug)]
 pub enum CudaError {
     Runtime(String),
-    Unavailable(String),
+    Unavailable(&'static str),
 }
 
 impl std::fmt::Display for CudaError {
@@ -25,15 +27,33 @@ impl std::fmt::Display for CudaError {
 
 impl std::error::Error for CudaError {}
 
+/// Status code of a failed `melspec_create` -> the reference's error kinds.  Constructor failures that mean "this machine
+/// cannot run the backend" are `Unavailable` with a static text (the reference's own strings where one exists, src/cuda.rs:45-49,
+/// 242-294); anything else (bad argument, CUDA runtime error) is `Runtime` with the library's message.
+pub(crate) fn create_error(rc: i32) -> CudaError {
+    match rc {
+        ffi::ERR_NO_DEVICE => CudaError::Unavailable("no CUDA device of compute capability 10.0 (melspec_b200 has no CPU fallback)"),
+        ffi::ERR_INVALID_CONFIG => CudaError::Unavailable("fft_size, hop_size, and n_mels must be non-zero"),
+        ffi::ERR_UNSUPPORTED => CudaError::Unavailable("configuration not supported by this build of libmelspec_b200"),
+        _ => CudaError::Runtime(ffi::last_error()),
+    }
+}
+
 pub struct CudaMelSpectrogram {
-    handle: *mut ffi::MelspecHandle, // raw pointer => !Send + !Sync, like the reference struct
+    handle: *mut ffi::MelspecHandle, // raw pointer => !Send + !Sync, like the reference struct (src/cuda.rs:27-36)
     n_mels: usize,
 }
 
 impl CudaMelSpectrogram {
+    /// Reference signature (src/cuda.rs:39-44).  Uses device 0; `new_on_device` picks another GPU of the box (one handle per
+    /// GPU for the batch-sharded configuration).
     pub fn new(fft_size: usize, hop_size: usize, sampling_rate: f64, n_mels: usize) -> Result<Self, CudaError> {
+        Self::new_on_device(fft_size, hop_size, sampling_rate, n_mels, 0)
+    }
+
+    pub fn new_on_device(fft_size: usize, hop_size: usize, sampling_rate: f64, n_mels: usize, device: i32) -> Result<Self, CudaError> {
         if fft_size == 0 || hop_size == 0 || n_mels == 0 {
-            return Err(CudaError::Unavailable("fft_size, hop_size, and n_mels must be non-zero".into()));
+            return Err(CudaError::Unavailable("fft_size, hop_size, and n_mels must be non-zero")); // src/cuda.rs:45-49
         }
         let mut cfg = ffi::MelspecConfig::default();
         unsafe { ffi::melspec_default_config(ffi::FRONTEND_WHISPER, &mut cfg) };
@@ -42,9 +62,9 @@ impl CudaMelSpectrogram {
         cfg.n_mels = n_mels as i32;
         cfg.sampling_rate = sampling_rate;
         let mut handle = ptr::null_mut();
-        let rc = unsafe { ffi::melspec_create(&cfg, 0, &mut handle) };
-        if rc != 0 {
-            return Err(CudaError::Unavailable(ffi::last_error()));
+        let rc = unsafe { ffi::melspec_create(&cfg, device, &mut handle) };
+        if rc != ffi::OK {
+            return Err(create_error(rc));
         }
         Ok(Self { handle, n_mels })
     }
@@ -53,26 +73,40 @@ impl CudaMelSpectrogram {
         unsafe { ffi::melspec_max_frames_per_batch(self.handle) as usize }
     }
 
+    pub(crate) fn raw(&self) -> *mut ffi::MelspecHandle {
+        self.handle
+    }
+
     /// `&[f32]` -> `[frame][mel]`, the reference's signature (src/cuda.rs:88-101).
     pub fn compute_mel_spectrogram(&mut self, samples: &[f32]) -> Result<Vec<Vec<f32>>, CudaError> {
+        let frames = unsafe { ffi::melspec_num_frames(self.handle, samples.len() as i64) } as usize;
+        if frames == 0 {
+            return Ok(Vec::new()); // src/cuda.rs:91-93
+        }
+        let mut flat = vec![0.0f32; frames * self.n_mels];
+        let rc = unsafe {
+            ffi::melspec_compute_host(self.handle, samples.as_ptr(), 1, samples.len() as i64, samples.len() as i64, flat.as_mut_ptr(),
+                                      ffi::LAYOUT_FRAME_MAJOR, ptr::null_mut())
+        };
+        if rc != ffi::OK {
+            return Err(CudaError::Runtime(ffi::last_error()));
+        }
+        Ok(flat.chunks(self.n_mels).map(|row| row.to_vec()).collect())
+    }
+
+    /// The same call for 16-bit PCM (half the bytes over PCIe; `x / 32768` on the device, bit-identical to the f32 call on the
+    /// converted samples).
+    pub fn compute_mel_spectrogram_i16(&mut self, samples: &[i16]) -> Result<Vec<Vec<f32>>, CudaError> {
         let frames = unsafe { ffi::melspec_num_frames(self.handle, samples.len() as i64) } as usize;
         if frames == 0 {
             return Ok(Vec::new());
         }
         let mut flat = vec![0.0f32; frames * self.n_mels];
         let rc = unsafe {
-            ffi::melspec_compute_host(
-                self.handle,
-                samples.as_ptr(),
-                1,
-                samples.len() as i64,
-                samples.len() as i64,
-                flat.as_mut_ptr(),
-                ffi::LAYOUT_FRAME_MAJOR,
-                ptr::null_mut(),
-            )
+            ffi::melspec_compute_host_i16(self.handle, samples.as_ptr(), 1, samples.len() as i64, samples.len() as i64, flat.as_mut_ptr(),
+                                          ffi::LAYOUT_FRAME_MAJOR, ptr::null_mut())
         };
-        if rc != 0 {
+        if rc != ffi::OK {
             return Err(CudaError::Runtime(ffi::last_error()));
         }
         Ok(flat.chunks(self.n_mels).map(|row| row.to_vec()).collect())
@@ -82,35 +116,16 @@ impl CudaMelSpectrogram {
     ///
     /// # Safety
     /// The pointers must be valid device allocations of the sizes described in `include/melspec_b200.h`.
-    pub unsafe fn compute_device(
-        &mut self,
-        d_pcm: *const f32,
-        n_clips: usize,
-        clip_stride: usize,
-        n_samples: usize,
-        d_out: *mut f32,
-        stream: *mut c_void,
-    ) -> Result<(), CudaError> {
-        let rc = ffi::melspec_compute_device(
-            self.handle,
-            d_pcm,
-            n_clips as i64,
-            clip_stride as i64,
-            n_samples as i64,
-            ptr::null(),
-            d_out,
-            0,
-            ffi::LAYOUT_FRAME_MAJOR,
-            stream,
-        );
-        if rc != 0 {
+    pub unsafe fn compute_device(&mut self, d_pcm: *const f32, n_clips: usize, clip_stride: usize, n_samples: usize, d_out: *mut f32,
+                                 stream: *mut c_void) -> Result<(), CudaError> {
+        let rc = ffi::melspec_compute_device(self.handle, d_pcm, n_clips as i64, clip_stride as i64, n_samples as i64, ptr::null(), d_out, 0,
+                                             ffi::LAYOUT_FRAME_MAJOR, stream);
+        if rc != ffi::OK {
             return Err(CudaError::Runtime(ffi::last_error()));
         }
         Ok(())
     }
-}
 
-impl CudaMelSpectrogram {
     /// `interleave_frames(frames, false, min_width)` (reference src/mel.rs:480-544) + `tga_8bit_data` (src/quant.rs:38-64)
     /// of the mel frames of `samples`, computed on the device in one pipeline.  Returns (tga bytes, width).
     pub fn mel_tga(&mut self, samples: &[f32], min_width: usize) -> Result<(Vec<u8>, usize), CudaError> {
@@ -123,13 +138,38 @@ impl CudaMelSpectrogram {
         let mut out = vec![0u8; size as usize];
         let mut w = 0i64;
         let rc = unsafe {
-            ffi::melspec_mel_tga_host(self.handle, samples.as_ptr(), samples.len() as i64, min_width as i64, out.as_mut_ptr(),
-                                      size, &mut w, ptr::null_mut())
+            ffi::melspec_mel_tga_host(self.handle, samples.as_ptr(), samples.len() as i64, min_width as i64, out.as_mut_ptr(), size, &mut w,
+                                      ptr::null_mut())
         };
-        if rc != 0 {
+        if rc != ffi::OK {
             return Err(CudaError::Runtime(ffi::last_error()));
         }
         Ok((out, w as usize))
+    }
+
+    /// `tga_8bit` (reference src/quant.rs:100-137): images wider than a TARGA can hold are cut into strides of at most 65 534
+    /// columns (`chunk_frames_into_strides`), one TGA per stride.  `image` is row-major (n_mels, width).
+    pub fn tga_8bit(&mut self, image: &[f32], n_mels: usize) -> Result<Vec<Vec<u8>>, CudaError> {
+        const STRIDE: usize = 65_534;
+        let width = image.len() / n_mels;
+        let mut out = Vec::new();
+        let mut c0 = 0usize;
+        while c0 < width {
+            let w = STRIDE.min(width - c0);
+            let mut strip = vec![0.0f32; n_mels * w];
+            for m in 0..n_mels {
+                strip[m * w..(m + 1) * w].copy_from_slice(&image[m * width + c0..m * width + c0 + w]);
+            }
+            let size = unsafe { ffi::melspec_tga_size(n_mels as i32, w as i64) } as usize;
+            let mut tga = vec![0u8; size];
+            let rc = unsafe { ffi::melspec_quantize_tga_host(self.handle, strip.as_ptr(), n_mels as i32, w as i64, tga.as_mut_ptr()) };
+            if rc != ffi::OK {
+                return Err(CudaError::Runtime(ffi::last_error()));
+            }
+            out.push(tga);
+            c0 += w;
+        }
+        Ok(out)
     }
 
     /// `vad_boundaries` (reference src/vad.rs:251-338) on a row-major (n_mels, width) image: the smoothed per-column mask
@@ -144,7 +184,7 @@ impl CudaMelSpectrogram {
         let rc = unsafe {
             ffi::melspec_vad_host(self.handle, image.as_ptr(), self.n_mels as i32, width as i64, &vs, mask.as_mut_ptr(), ptr::null_mut())
         };
-        if rc != 0 {
+        if rc != ffi::OK {
             return Err(CudaError::Runtime(ffi::last_error()));
         }
         Ok(mask.into_iter().map(|b| b != 0).collect())
@@ -153,136 +193,6 @@ impl CudaMelSpectrogram {
 
 impl Drop for CudaMelSpectrogram {
     fn drop(&mut self) {
-        unsafe { ffi::melspec_destroy(self.handle) };
-    }
-}
-
-mod ffi {
-    use super::{c_char, c_void, CStr};
-
-    pub const FRONTEND_WHISPER: i32 = 0;
-    pub const LAYOUT_FRAME_MAJOR: i32 = 0;
-
-    #[repr(C)]
-    pub struct MelspecHandle {
-        _private: [u8; 0],
-    }
-
-    /// `struct melspec_config` of include/melspec_b200.h (field order and types must match exactly).
-    #[repr(C)]
-    #[derive(Default, Clone, Copy)]
-    pub struct MelspecConfig {
-        pub frontend: i32,
-        pub fft_size: i32,
-        pub hop_size: i32,
-        pub n_mels: i32,
-        pub sampling_rate: f64,
-        pub frame_length: i32,
-        pub apply_cmn: i32,
-        pub use_log_fbank: i32,
-        pub use_power: i32,
-        pub preemphasis: f64,
-        pub low_freq: f64,
-        pub high_freq: f64,
-        pub energy_floor: f64,
-        // NeMo block (BatchLogMelConfig, reference src/mel.rs:171-208)
-        pub win_length: i32,
-        pub center: i32,
-        pub pad_to: i32,
-        pub normalize_per_feature: i32,
-        pub htk: i32,
-        pub slaney_norm: i32,
-        pub log_zero_guard: f64,
-        pub f_min: f64,
-        pub f_max: f64,
-    }
-
-    #[repr(C)]
-    pub struct MelspecStream {
-        _private: [u8; 0],
-    }
-
-    /// `struct melspec_vad_settings` == DetectionSettings (reference src/vad.rs:5-22).
-    #[repr(C)]
-    #[derive(Clone, Copy)]
-    pub struct VadSettings {
-        pub min_energy: f64,
-        pub min_y: i32,
-        pub min_x: i32,
-        pub min_mel: i32,
-    }
-
-    #[link(name = "melspec_b200")]
-    unsafe extern "C" {
-        pub fn melspec_default_config(frontend: i32, cfg: *mut MelspecConfig) -> i32;
-        pub fn melspec_create(cfg: *const MelspecConfig, device: i32, out: *mut *mut MelspecHandle) -> i32;
-        pub fn melspec_destroy(h: *mut MelspecHandle);
-        pub fn melspec_num_frames(h: *const MelspecHandle, n_samples: i64) -> i64;
-        pub fn melspec_max_frames_per_batch(h: *const MelspecHandle) -> i32;
-        pub fn melspec_compute_device(
-            h: *mut MelspecHandle,
-            d_pcm: *const f32,
-            n_clips: i64,
-            clip_stride: i64,
-            n_samples: i64,
-            d_lens: *const i32,
-            d_out: *mut f32,
-            out_clip_stride: i64,
-            layout: i32,
-            stream: *mut c_void,
-        ) -> i32;
-        pub fn melspec_compute_host(
-            h: *mut MelspecHandle,
-            h_pcm: *const f32,
-            n_clips: i64,
-            clip_stride: i64,
-            n_samples: i64,
-            h_out: *mut f32,
-            layout: i32,
-            frames_out: *mut i64,
-        ) -> i32;
-        pub fn melspec_last_error() -> *const c_char;
-        // streaming: RingBuffer::maybe_mel / Spectrogram::add semantics (reference src/rb.rs:86-121, src/stft.rs:48-86)
-        pub fn melspec_stream_create(h: *mut MelspecHandle, max_chunk_samples: i64, out: *mut *mut MelspecStream) -> i32;
-        pub fn melspec_stream_push(
-            s: *mut MelspecStream,
-            h_samples: *const f32,
-            n: i64,
-            h_out: *mut f32,
-            out_capacity_frames: i64,
-            frames_emitted: *mut i64,
-        ) -> i32;
-        pub fn melspec_stream_reset(s: *mut MelspecStream) -> i32;
-        pub fn melspec_stream_destroy(s: *mut MelspecStream);
-        // output formats: interleave_frames (src/mel.rs:480-544) and the 8-bit TGA quantiser (src/quant.rs:38-165)
-        pub fn melspec_interleaved_width(n_frames: i64, min_width: i64) -> i64;
-        pub fn melspec_tga_size(n_mels: i32, width: i64) -> i64;
-        pub fn melspec_mel_tga_host(
-            h: *mut MelspecHandle,
-            h_pcm: *const f32,
-            n_samples: i64,
-            min_width: i64,
-            h_tga: *mut u8,
-            capacity: i64,
-            width_out: *mut i64,
-            h_img_opt: *mut f32,
-        ) -> i32;
-        pub fn melspec_quantize_tga_host(h: *mut MelspecHandle, h_img: *const f32, n_mels: i32, width: i64, h_tga: *mut u8) -> i32;
-        pub fn melspec_dequantize_tga_host(h: *mut MelspecHandle, h_tga: *const u8, tga_bytes: i64, h_img: *mut f32, capacity: i64) -> i32;
-        // VAD over the mel image (src/vad.rs:251-338, 163-207)
-        pub fn melspec_vad_default_settings(s: *mut VadSettings) -> i32;
-        pub fn melspec_vad_host(
-            h: *mut MelspecHandle,
-            h_img: *const f32,
-            n_mels: i32,
-            width: i64,
-            vs: *const VadSettings,
-            h_smoothed: *mut u8,
-            h_activity_opt: *mut i32,
-        ) -> i32;
-    }
-
-    pub fn last_error() -> String {
-        unsafe { CStr::from_ptr(melspec_last_error()).to_string_lossy().into_owned() }
+        unsafe { ffi::melspec_destroy(self.handle) }; // replaces src/cuda.rs:142-148
     }
 }
