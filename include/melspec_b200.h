@@ -222,7 +222,8 @@ int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm
  * device: 18-byte TGA header (type 3, 8 bpp, width/height little-endian u16) + 8-byte ID field holding f32 min and max of
  * the image + n_mels*width bytes ((v - min) * (255 / (max - min))).round().clamp(0, 255).  Bytes are bit-exact with the
  * reference for identical f32 input.  One image per clip: image r at d_img + r*img_stride floats (0 = dense), TGA r at
- * d_tga + r*tga_stride bytes (0 = melspec_tga_size).  width >= 65535 is rejected like save_tga_8bit's assert.
+ * d_tga + r*tga_stride bytes (0 = melspec_tga_size).  width and n_mels must fit the header's u16 fields (<= 65535: the stride
+ * tga_8bit cuts wider images into, src/quant.rs:29-36, 100-137; save_tga_8bit additionally asserts width < 65535, src/quant.rs:17-21).
  */
 int64_t melspec_tga_size(int32_t n_mels, int64_t width);                 /* 26 + n_mels*width, -1 if it cannot be a TGA */
 int32_t melspec_quantize_tga_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
@@ -265,6 +266,23 @@ int32_t melspec_vad_activity_device(melspec_handle* h, const uint8_t* d_raw, int
                                     void* stream);
 int32_t melspec_vad_host(melspec_handle* h, const float* h_img, int32_t n_mels, int64_t width, const melspec_vad_settings* vs,
                          uint8_t* h_smoothed, int32_t* h_activity_opt);
+
+/*
+ * ---- optional: gather of the output shards over NVLink / NVSwitch (one process per GPU, batch-sharded clips) ----
+ *
+ * The hot path has no collective: every GPU computes its own clips.  When one rank needs the whole batch, the shards are
+ * gathered with one ncclAllGather.  NCCL is not a link-time dependency: libnccl.so.2 is looked up at run time (the copy already
+ * loaded in the process -- e.g. PyTorch's -- is reused), and these entries return MELSPEC_ERR_UNSUPPORTED when none is found.
+ *   melspec_nccl_unique_id   rank 0 creates the 128-byte ncclUniqueId; the host program hands it to the other ranks (any channel)
+ *   melspec_nccl_init        every rank joins (collective call); the communicator belongs to the handle
+ *   melspec_gather_nccl      d_full[r*count .. (r+1)*count) = rank r's d_shard[0 .. count), equal `count` (floats) on all ranks,
+ *                            asynchronous on `stream`; uneven batches: pad the shard to the largest count
+ *   melspec_nccl_destroy     also done by melspec_destroy
+ */
+int32_t melspec_nccl_unique_id(uint8_t* id128);
+int32_t melspec_nccl_init(melspec_handle* h, const uint8_t* id128, int32_t rank, int32_t world_size);
+int32_t melspec_gather_nccl(melspec_handle* h, const float* d_shard, int64_t count, float* d_full, void* stream);
+int32_t melspec_nccl_destroy(melspec_handle* h);
 
 /* Number of kernel launches issued through this handle so far (bench.py's `gpu_launches`). */
 int64_t melspec_launch_count(const melspec_handle* h);

@@ -17,7 +17,7 @@ SOURCES = [os.path.join(_PKG, "csrc", "melspec_api.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_PKG, "csrc", "melspec_generic.cuh"),
            os.path.join(_ROOT, "include", "melspec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-ldl"]
 
 # every symbol include/melspec_b200.h declares
 EXPORTS = [
@@ -30,6 +30,7 @@ EXPORTS = [
     "melspec_dequantize_tga_device", "melspec_quantize_tga_host", "melspec_dequantize_tga_host", "melspec_mel_tga_host",
     "melspec_vad_default_settings", "melspec_vad_boundaries_device", "melspec_vad_activity_device", "melspec_vad_host",
     "melspec_stream_push_hop", "melspec_compute_host_i16", "melspec_convert_i16_device",
+    "melspec_nccl_unique_id", "melspec_nccl_init", "melspec_gather_nccl", "melspec_nccl_destroy",
 ]
 
 
@@ -152,6 +153,14 @@ def lib() -> C.CDLL:
         L.melspec_compute_host_i16.argtypes = [vp, vp, i64, i64, i64, vp, i32, C.POINTER(i64)]
         L.melspec_convert_i16_device.restype = i32
         L.melspec_convert_i16_device.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
+        L.melspec_nccl_unique_id.restype = i32
+        L.melspec_nccl_unique_id.argtypes = [vp]
+        L.melspec_nccl_init.restype = i32
+        L.melspec_nccl_init.argtypes = [vp, vp, i32, i32]
+        L.melspec_gather_nccl.restype = i32
+        L.melspec_gather_nccl.argtypes = [vp, vp, i64, vp, vp]
+        L.melspec_nccl_destroy.restype = i32
+        L.melspec_nccl_destroy.argtypes = [vp]
     _LIB = L
     return L
 

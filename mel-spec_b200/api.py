@@ -342,23 +342,54 @@ class _Handle:
             raise ValueError("data length must be a positive multiple of n_mels")
         width = x.size // n_mels
         size = int(self._L.melspec_tga_size(int(n_mels), int(width)))
-        if size < 0:
-            raise ValueError("width greater than TARGA max, use [`tga_8bit`]")      # src/quant.rs:18-21
+        if size < 0:      # the reference writes `width as u16` (a wrapped width, src/quant.rs:41); refused here
+            raise ValueError("width greater than TARGA max, use [`tga_8bit`]")
         out = np.empty(size, dtype=np.uint8)
         _check(self._L.melspec_quantize_tga_host(self._h, x.ctypes.data, int(n_mels), int(width), out.ctypes.data))
         return out.tobytes()
 
+    def tga_8bit(self, data, n_mels: int) -> list:
+        """src/quant.rs:29-36: images wider than a TARGA can hold are cut into strides of u16::MAX columns
+        (`chunk_frames_into_strides`, src/quant.rs:100-137: row blocks, then column blocks), one TGA per stride, each with
+        its own min / max."""
+        x = np.asarray(data, dtype=np.float32).reshape(-1)
+        if n_mels <= 0 or x.size % n_mels:
+            raise ValueError("data length must be a multiple of n_mels")
+        width, stride = x.size // n_mels, 65535
+        if width == stride:
+            return [self.tga_8bit_data(x, n_mels)]
+        img = x.reshape(n_mels, width)
+        out = []
+        for y in range(0, n_mels, stride):
+            for c in range(0, width, stride):
+                blk = np.ascontiguousarray(img[y:y + stride, c:c + stride])
+                out.append(self.tga_8bit_data(blk, blk.shape[0]))
+        return out
+
+    def save_tga_8bit(self, data, n_mels: int, path: str) -> None:
+        """src/quant.rs:15-28."""
+        x = np.asarray(data, dtype=np.float32).reshape(-1)
+        if x.size // n_mels >= 65535:
+            raise AssertionError("width greater than TARGA max, use [`tga_8bit`]")      # src/quant.rs:17-21
+        with open(path, "wb") as f:
+            f.write(self.tga_8bit_data(x, n_mels))
+
+    def load_tga_8bit(self, path: str) -> np.ndarray:
+        """src/quant.rs:90-98."""
+        with open(path, "rb") as f:
+            return self.parse_tga_8bit(f.read())
+
     def quantize(self, frame):
         """src/quant.rs:140-152: (u8 bytes, QuantizationRange)."""
         x = np.asarray(frame, dtype=np.float32).reshape(-1)
-        tga = np.frombuffer(self.tga_8bit_data(x, 1) if x.size < 65535 else self._quantize_rows(x), dtype=np.uint8)
+        tga = np.frombuffer(self.tga_8bit_data(x, 1) if x.size <= 65535 else self._quantize_rows(x), dtype=np.uint8)
         rng = QuantizationRange(*np.frombuffer(tga[18:26].tobytes(), dtype="<f4").tolist())
         return tga[26:].copy(), rng
 
     def _quantize_rows(self, x: np.ndarray) -> bytes:
         # a flat vector longer than a TGA row: use the widest factorisation that fits the u16 fields
         n = x.size
-        h = next((k for k in range(2, 65536) if n % k == 0 and n // k < 65535), None)
+        h = next((k for k in range(2, 65536) if n % k == 0 and n // k <= 65535), None)
         if h is None:
             raise ValueError("vector cannot be laid out as a TGA image")
         return self.tga_8bit_data(x, h)

@@ -7,6 +7,7 @@
 #include "../../include/melspec_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -204,6 +205,8 @@ struct melspec_handle {
     unsigned char* d_fmt_tga = nullptr;
     size_t fmt_img_cap = 0, fmt_tga_cap = 0;
     int64_t launches = 0;
+    void* nccl_comm = nullptr;      // ncclComm_t of the optional output gather (melspec_nccl_init)
+    int nccl_world = 0;
 };
 
 struct melspec_stream {
@@ -948,6 +951,7 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
 void melspec_destroy(melspec_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    melspec_nccl_destroy(h);
     cudaFree(h->d_window);
     cudaFree(h->d_twiddle);
     cudaFree(h->d_rot10);
@@ -1019,7 +1023,7 @@ int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm
 }
 
 int64_t melspec_tga_size(int32_t n_mels, int64_t width) {
-    if (n_mels <= 0 || width <= 0 || n_mels > 65535 || width >= 65535) return -1;   // u16 fields; src/quant.rs:17-21
+    if (n_mels <= 0 || width <= 0 || n_mels > 65535 || width > 65535) return -1;   // u16 header fields (src/quant.rs:44-57)
     return (int64_t)melspec::kTgaHeader + (int64_t)n_mels * width;
 }
 
@@ -1241,6 +1245,82 @@ int32_t melspec_vad_host(melspec_handle* h, const float* h_img, int32_t n_mels, 
         rc = melspec_vad_activity_device(h, d_raw, 1, 0, n_mels, width, vs, d_act, 0, nullptr);
         if (rc) return rc;
         MS_CUDA(cudaMemcpy(h_activity_opt, d_act, 12 * (size_t)width, cudaMemcpyDeviceToHost));
+    }
+    return MELSPEC_OK;
+}
+
+// ---- optional NCCL gather of the output shards: libnccl.so.2 resolved at run time -------------------------
+namespace {
+struct NcclId128 { char b[128]; };   // ncclUniqueId (passed by value to ncclCommInitRank)
+struct NcclApi {
+    int (*get_unique_id)(void*) = nullptr;
+    int (*comm_init_rank)(void**, int, NcclId128, int) = nullptr;
+    int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*comm_destroy)(void*) = nullptr;
+    const char* (*error_string)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already has (PyTorch's), if any
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return a;
+        a.get_unique_id = reinterpret_cast<decltype(a.get_unique_id)>(dlsym(lib, "ncclGetUniqueId"));
+        a.comm_init_rank = reinterpret_cast<decltype(a.comm_init_rank)>(dlsym(lib, "ncclCommInitRank"));
+        a.all_gather = reinterpret_cast<decltype(a.all_gather)>(dlsym(lib, "ncclAllGather"));
+        a.comm_destroy = reinterpret_cast<decltype(a.comm_destroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.error_string = reinterpret_cast<decltype(a.error_string)>(dlsym(lib, "ncclGetErrorString"));
+        a.ok = a.get_unique_id && a.comm_init_rank && a.all_gather && a.comm_destroy && a.error_string;
+        return a;
+    }();
+    return api;
+}
+int32_t fail_nccl(int rc, const char* what) {
+    return fail(MELSPEC_ERR_CUDA, std::string(what) + ": " + nccl_api().error_string(rc));
+}
+}  // namespace
+
+int32_t melspec_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(MELSPEC_ERR_INVALID_ARG, "id is null");
+    if (!nccl_api().ok) return fail(MELSPEC_ERR_UNSUPPORTED, "libnccl.so.2 not found (the gather is optional; the hot path has no collective)");
+    const int rc = nccl_api().get_unique_id(id128);
+    return rc ? fail_nccl(rc, "ncclGetUniqueId") : MELSPEC_OK;
+}
+
+int32_t melspec_nccl_init(melspec_handle* h, const uint8_t* id128, int32_t rank, int32_t world_size) {
+    if (!h || !id128) return fail(MELSPEC_ERR_INVALID_ARG, "null argument");
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(MELSPEC_ERR_INVALID_ARG, "rank outside [0, world_size)");
+    if (!nccl_api().ok) return fail(MELSPEC_ERR_UNSUPPORTED, "libnccl.so.2 not found (the gather is optional; the hot path has no collective)");
+    if (h->nccl_comm) return fail(MELSPEC_ERR_INVALID_ARG, "communicator already initialised for this handle");
+    MS_CUDA(cudaSetDevice(h->device));
+    NcclId128 id;
+    std::memcpy(id.b, id128, 128);
+    const int rc = nccl_api().comm_init_rank(&h->nccl_comm, world_size, id, rank);
+    if (rc) { h->nccl_comm = nullptr; return fail_nccl(rc, "ncclCommInitRank"); }
+    h->nccl_world = world_size;
+    return MELSPEC_OK;
+}
+
+int32_t melspec_gather_nccl(melspec_handle* h, const float* d_shard, int64_t count, float* d_full, void* stream) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (!h->nccl_comm) return fail(MELSPEC_ERR_INVALID_ARG, "melspec_nccl_init has not been called on this handle");
+    if (count < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative count");
+    if (count == 0) return MELSPEC_OK;
+    if (!d_shard || !d_full) return fail(MELSPEC_ERR_INVALID_ARG, "null device pointer");
+    MS_CUDA(cudaSetDevice(h->device));
+    const int rc = nccl_api().all_gather(d_shard, d_full, (size_t)count, /* ncclFloat32 */ 7, h->nccl_comm, (cudaStream_t)stream);
+    return rc ? fail_nccl(rc, "ncclAllGather") : MELSPEC_OK;
+}
+
+int32_t melspec_nccl_destroy(melspec_handle* h) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (h->nccl_comm) {
+        cudaSetDevice(h->device);
+        nccl_api().comm_destroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+        h->nccl_world = 0;
     }
     return MELSPEC_OK;
 }

@@ -967,7 +967,7 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 -
 // MODE 0: Whisper fft 512.  MODE 1: Kaldi fbank.  MODE 2: NeMo BatchLogMel (whole-waveform pre-emphasis, frames may
 // hang over both ends of the clip: the missing samples are zero-filled in the stage, reference src/mel.rs:344-348,685-706).
 #ifndef TWREG512
-#define TWREG512 true
+#define TWREG512 false   // A/B switch: twiddles of the row transforms in registers (measured 3 % slower for the Whisper mode)
 #endif
 template <int NWARPS, int MPL, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
@@ -1122,21 +1122,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         mbar_wait(bar, it & 1);
 
         // ------------------------------------------------------------------ step 1
-        // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet.
-        // The samples (and their pre-emphasis partners) are read before the refill of the stage is issued; everything else
-        // happens after it, which keeps only the NLOAD sample registers live across the TMA issue.
+        // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet
         f2 er[16], ei[16];
-        const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
-        float x[NLOAD];
-        float sa = 0.f, sb = 0.f, x0 = 0.f;
         if (nvalid > 0) {
+            const bool va = 2 * g1 < nvalid, vb = 2 * g1 + 1 < nvalid;
             const float* px = s_pcm + g1 * CS + c;
+            float x[NLOAD];
 #pragma unroll
             for (int m = 0; m < NLOAD; ++m) x[m] = px[16 * m + PAD * (m / 20)];
-            if (FRAME400) {
+            if (!FRAME400) {
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
+                    er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
+                    ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
+                }
+            } else {
                 // d[m] = x[m] - preemph * x[m-1]; the previous sample is one word back (one chunk pad further back at a
                 // chunk start); frame sums for the DC removal are reduced over the 16 lanes of the FFT
-                x0 = x[0];
+                float sa = 0.f, sb = 0.f;
+                const float x0 = x[0];
 #pragma unroll
                 for (int m = 0; m < NLOAD; ++m) {
                     float xp;
@@ -1150,6 +1155,43 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     if (KALDI && m >= 10) sb += x[m];
                     x[m] = fmaf(-p.preemph, xp, x[m]);
                 }
+                float ka = 0.f, kb = 0.f;
+                if (KALDI) {
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    }
+                    const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
+                    if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
+                    ka = (1.0f - p.preemph) * mu_a; kb = (1.0f - p.preemph) * mu_b;
+                } else {
+                    // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
+                    // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
+                    const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
+                    if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
+#pragma unroll
+                        for (int m = 0; m < NLOAD; ++m)
+                            if (rel == 16 * m) x[m] = 0.f;
+                    }
+                    (void)x0;
+                }
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
+                    if (2 * a < NROW) {
+                        const float w0 = s_win[32 * a];
+                        r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
+                        i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
+                    }
+                    if (2 * a + 1 < NROW) {
+                        const float w1 = s_win[32 * a + 16];
+                        r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
+                        i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
+                    }
+                    er[a] = make_float2(r0, r1);
+                    ei[a] = make_float2(i0, i1);
+                }
             }
         }
         __syncwarp();
@@ -1157,52 +1199,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const int wt_next = next_tile(wt, tin_next, clip_next);
         if (wt_next < p.n_wtiles) issue_load(clip_next, tin_next);
         if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
-
-        if (!FRAME400) {
-#pragma unroll
-            for (int a = 0; a < 16; ++a) {
-                const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
-                er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
-                ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
-            }
-        } else {
-            float ka = 0.f, kb = 0.f;
-            if (KALDI) {
-#pragma unroll
-                for (int o = 8; o >= 1; o >>= 1) {
-                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                }
-                const float mu_a = sa * (1.0f / 400.0f), mu_b = sb * (1.0f / 400.0f);
-                if (owns_first && fw0 == 0) x[0] = fmaf(-p.preemph, mu_a, x0);   // first frame of the clip: no look-back
-                ka = (1.0f - p.preemph) * mu_a; kb = (1.0f - p.preemph) * mu_b;
-            } else {
-                // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
-                // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
-                const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
-                if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
-#pragma unroll
-                    for (int m = 0; m < NLOAD; ++m)
-                        if (rel == 16 * m) x[m] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 16; ++a) {
-                float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
-                if (2 * a < NROW) {
-                    const float w0 = s_win[32 * a];
-                    r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
-                    i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
-                }
-                if (2 * a + 1 < NROW) {
-                    const float w1 = s_win[32 * a + 16];
-                    r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
-                    i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
-                }
-                er[a] = make_float2(r0, r1);
-                ei[a] = make_float2(i0, i1);
-            }
-        }
 
         {   // pair prescale (see pair_prescale): peak levels of the two prepared frames, all-reduced over the FFT's 16 lanes
             float ma = 0.f, mb = 0.f;
@@ -1212,8 +1208,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 mb = fmaxf(fmaxf(mb, fabsf(ei[a].x)), fabsf(ei[a].y));
             }
             int pk = pack_exponents(ma, mb);
-#pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) pk = __vmaxu2(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+            {   // two dependent rounds instead of four: lanes at xor distance {1, 2, 3}, then {4, 8, 12} of the result
+                const int a1 = __shfl_xor_sync(0xffffffffu, pk, 1), a2 = __shfl_xor_sync(0xffffffffu, pk, 2), a3 = __shfl_xor_sync(0xffffffffu, pk, 3);
+                pk = __vmaxu2(__vmaxu2(pk, a1), __vmaxu2(a2, a3));
+                const int b1 = __shfl_xor_sync(0xffffffffu, pk, 4), b2 = __shfl_xor_sync(0xffffffffu, pk, 8), b3 = __shfl_xor_sync(0xffffffffu, pk, 12);
+                pk = __vmaxu2(__vmaxu2(pk, b1), __vmaxu2(b2, b3));
+            }
             int ka, kb;
             float4 tab;
             pair_prescale(pk, NEMO ? p.log_add : p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);

@@ -150,7 +150,7 @@ impl CudaMelSpectrogram {
     /// `tga_8bit` (reference src/quant.rs:100-137): images wider than a TARGA can hold are cut into strides of at most 65 534
     /// columns (`chunk_frames_into_strides`), one TGA per stride.  `image` is row-major (n_mels, width).
     pub fn tga_8bit(&mut self, image: &[f32], n_mels: usize) -> Result<Vec<Vec<u8>>, CudaError> {
-        const STRIDE: usize = 65_534;
+        const STRIDE: usize = u16::MAX as usize; // src/quant.rs:31
         let width = image.len() / n_mels;
         let mut out = Vec::new();
         let mut c0 = 0usize;

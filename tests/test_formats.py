@@ -75,7 +75,7 @@ def test_abi_exports_format_symbols():
     assert L.melspec_interleaved_width(1098, 0) == 1098 and L.melspec_interleaved_width(1097, 0) == 1097
     assert L.melspec_interleaved_width(1097, 2) == 1098 and L.melspec_interleaved_width(1097, 3000) == 3000
     assert L.melspec_interleaved_width(10, 3) == -1 and L.melspec_interleaved_width(0, 0) == -1
-    assert L.melspec_tga_size(80, 1100) == 88026 and L.melspec_tga_size(80, 65535) == -1 and L.melspec_tga_size(80, 65534) > 0
+    assert L.melspec_tga_size(80, 1100) == 88026 and L.melspec_tga_size(80, 65536) == -1 and L.melspec_tga_size(80, 65535) > 0
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -155,6 +155,27 @@ def test_gpu_format_errors(mel400, jfk):
     with pytest.raises(ValueError):
         mel400.mel_tga(jfk[:100], 0)                                       # no frame (src/mel.rs:487)
     with pytest.raises(ValueError):
-        mel400.tga_8bit_data(np.zeros(80 * 65535, np.float32), 80)         # width >= u16::MAX (src/quant.rs:18-21)
+        mel400.tga_8bit_data(np.zeros(80 * 65536, np.float32), 80)         # width does not fit the u16 header field
     with pytest.raises(IOError):
         mel400.parse_tga_8bit(b"\0" * 10)
+
+
+@pytest.mark.gpu
+def test_tga_8bit_chunks_wide_images_like_the_reference(mel400, tmp_path):
+    """src/quant.rs:29-36, 100-137: strides of u16::MAX columns, one TGA (own min / max) per stride; save_tga_8bit asserts
+    width < u16::MAX (src/quant.rs:17-21)."""
+    rng = np.random.default_rng(5)
+    n_mels, width = 4, 65535 + 1000
+    img = (rng.standard_normal((n_mels, width)) * 0.5).astype(np.float32)
+    img[:, 65535:] += 3.0                                                  # the second stride has its own range
+    chunks = mel400.tga_8bit(img.reshape(-1), n_mels)
+    assert len(chunks) == 2
+    for blob, blk in zip(chunks, (img[:, :65535], img[:, 65535:])):
+        want = o.tga_8bit_data(np.ascontiguousarray(blk).reshape(-1), n_mels)
+        assert blob == want
+    assert len(mel400.tga_8bit(img[:, :65535].reshape(-1), n_mels)) == 1   # stride_size == width: a single image
+    with pytest.raises(AssertionError):
+        mel400.save_tga_8bit(img[:, :65535].reshape(-1), n_mels, str(tmp_path / "x.tga"))
+    mel400.save_tga_8bit(img[:, :2000].reshape(-1), n_mels, str(tmp_path / "y.tga"))
+    back = mel400.load_tga_8bit(str(tmp_path / "y.tga"))
+    assert back.shape == (n_mels * 2000,) and np.abs(back - img[:, :2000].reshape(-1)).max() <= (img[:, :2000].max() - img[:, :2000].min()) / 255.0
