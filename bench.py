@@ -350,6 +350,7 @@ def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps
         # identical to the f32 path fed the same (int16 / 32768) samples
         xf = (hx16.to(dev).to(torch.float32) / 32768.0).contiguous()
         ref16 = torch.empty_like(out)
+        torch.cuda.synchronize()       # xf was produced on torch's default stream, the launch below is on a non-blocking stream
         h.compute_device(xf, clips, n_samples, n_samples, ref16, stream=stream)
         torch.cuda.synchronize()
         e2e_i16 = {"value": world * clips * F / t16, "unit": "frames/s", "ms_per_step": t16 * 1e3,

@@ -570,7 +570,7 @@ int warps_per_cta(int plan) {
     static int forced = [] {
         const char* e = std::getenv("MELSPEC_WARPS");
         const int v = e ? std::atoi(e) : 0;
-        return (v == 8 || v == 12) ? v : 0;
+        return (v == 8 || v == 12) ? v : 0;   // (16: see launch_device, plan 400 only)
     }();
     (void)plan;
     return forced ? forced : 12;
@@ -716,8 +716,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
     else { p.log_mul = (float)std::log10(2.0); p.normalize = 1; }                         // log10 + per-frame clamp, src/mel.rs:148-168,645-654
-    // ragged NeMo batches (per-clip lengths) run on the general plan whatever the size: its tables exist for every NeMo handle
-    if (h->plan == 1 || (nemo && d_lens)) return launch_generic(h, p, n_clips, d_lens, d_out, row_stride, st);
+    if (h->plan == 1) return launch_generic(h, p, n_clips, d_lens, d_out, row_stride, st);
     // shared-memory carve-up: [mbarriers | window | twiddles | projection program | meta | per-warp slabs]
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 128;
@@ -733,17 +732,33 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     static_assert(p400::FPW * 32 * kMaxMpl * 4 <= p400::STAGE_MAX, "output rows must fit behind the power rows");
     static_assert(p512::FPW * 32 * kMaxMpl * 4 <= p512::STAGE_MAX, "output rows must fit behind the power rows");
     size_t pcm_words;
+    int nw = warps_per_cta(h->plan);
     if (h->plan == 400) {
         pcm_words = hop160 ? (size_t)p400::NCHUNK * p400::CS320 : (size_t)(p400::FPW - 1) * c.hop + 400;
         p.smem_stage_off = p400::PBYTES;
-        p.smem_pcm_off = (int)up(p400::ZBYTES + 48, 128);   // 48 bytes behind the slab: the pair prescale's per-frame (floor, log offset)
+        // 16 warps per SM (four per scheduler) for the headline configuration (Whisper 80-mel, hop 160): 111 registers per thread
+        // with the twiddles read from shared memory, and a per-warp footprint of 12.4 KB instead of 16 KB because the PCM stage
+        // starts inside the exchange slab, right behind the output rows (the refill is issued once the slab's tail is dead).
+        // Measured (profiles/README.md, r2): 0.4017 ms against 0.4010 ms with 12 warps -- the fourth warp per scheduler buys nothing
+        // because the kernel is bound by the shared-memory pipe, not by latency -- so it is opt-in (MELSPEC_WARPS=16).
+        static const bool w16 = [] { const char* e = std::getenv("MELSPEC_WARPS"); return e && std::atoi(e) == 16; }();
+        if (w16 && hop160 && h->kspec == 1 && h->mpl == 3) nw = 16;
+        if (nw == 16) {
+            p.smem_pcm_off = p400::PBYTES + p400::FPW * 32 * 3 * 4;               // behind the staged output rows (80 mels: 6864)
+            p.smem_scr_off = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 16);   // 48 bytes: the pair prescale's (floor, log offset)
+            p.smem_warp_stride = (int)up((size_t)p.smem_scr_off + 48, 128);
+        } else {
+            p.smem_scr_off = p400::ZBYTES;
+            p.smem_pcm_off = (int)up(p400::ZBYTES + 48, 128);
+            p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
+        }
     } else {
         pcm_words = (size_t)p512::NCHUNK * p512::CS;
         p.smem_stage_off = p512::PBYTES;
+        p.smem_scr_off = p512::ZBYTES;
         p.smem_pcm_off = (int)up(p512::ZBYTES + p512::SCRBYTES, 128);
+        p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
     }
-    p.smem_warp_stride = (int)up((size_t)p.smem_pcm_off + pcm_words * 4, 128);
-    const int nw = warps_per_cta(h->plan);
     // Kaldi CMN inside the fused kernel: one CTA works through whole clips (see melspec512_kernel).  Needs enough clips to
     // fill the GPU, enough tiles per clip for every warp, and float4-addressable rows; otherwise CMN stays a second kernel.
     // MELSPEC_CMN_FUSED: 0 = CMN as a second kernel, 1 = block barrier + in-place subtraction by the CTA (round 1), 2 (default) =
@@ -771,7 +786,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
                     : launch_kernel(melspec400_kernel<NW, 3, false, 0>, p, grid, NW * 32, off, st))                   \
           : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true, 0>, p, grid, NW * 32, off, st)                    \
                     : launch_kernel(melspec400_kernel<NW, 4, false, 0>, p, grid, NW * 32, off, st)))
-        rc = nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
+        rc = nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
     } else {
 #define MS_DISPATCH(NW, MODE)                                                                                       \
@@ -935,11 +950,6 @@ int32_t melspec_create(const melspec_config* cfg, int32_t device, melspec_handle
             if (h->dense[(size_t)m * nbins] != 0.0) { h->plan = 1; break; }
     }
     rc = build_tables(h);
-    if (rc == MELSPEC_OK && h->plan != 1 && r.frontend == MELSPEC_FRONTEND_NEMO) {
-        const int mpl = h->mpl;
-        rc = build_tables_generic(h);   // for ragged batches (d_lens), which run on the general plan
-        h->mpl = mpl;
-    }
     if (rc) {
         melspec_destroy(h);
         return rc;

@@ -73,7 +73,7 @@ struct KParams {
     int n_clips;
     int smem_cmn;            // [NWARPS][128] column sums + [128] means (floats)
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
-    int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off;
+    int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off, smem_scr_off;
 };
 
 constexpr int kMaxMpl = 4;
@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     float2* s_p = reinterpret_cast<float2*>(s_warp);
     float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
-    float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor, log offset) of frames A and B per FFT (48 of
-                                                                  // the 64 bytes between the slab and the 128-byte aligned PCM stage)
+    float4* s_scr = reinterpret_cast<float4*>(s_warp + p.smem_scr_off);   // pair prescale: (floor, log offset) of frames A and B per FFT
+    constexpr bool LATE_LOAD = (NWARPS == 16);   // see the tile loop
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
     const uint64_t pol_in = l2_evict_first();                 // PCM is read once: it must not displace output rows in L2
     // lanes of this FFT at ring distance 1, 2 | 3, 6, 9 (six bits each): the two-round all-reduce of the pair prescale
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #ifdef MELSPEC_TW_SMEM   // A/B switch (tools/ab_bench.sh): twiddles read from shared memory every pass
     constexpr bool TW_IN_REGS = (NWARPS <= 8);
 #else
-    constexpr bool TW_IN_REGS = HOP160 || (NWARPS <= 8);   // (other hops load and window on the fly: no registers to spare)
+    constexpr bool TW_IN_REGS = (HOP160 && NWARPS <= 12) || (NWARPS <= 8);   // (other hops load and window on the fly, 16 warps have 128 registers)
 #endif
     float4 twreg[10];
     if (TW_IN_REGS) {
@@ -603,7 +603,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                         // consumed after it, which keeps only the 56 sample registers live across the TMA issue)
         const int cur_clip = clip;
         if (++tin == p.wtiles_per_clip) { tin = 0; ++clip; }
-        if (it + 1 < cnt) issue_load(clip, tin);
+        // 12-warp build: the refill goes out now.  16-warp build (LATE_LOAD): the PCM stage shares its first 3.7 KB with the tail
+        // of the exchange slab, which is live until the row loads of step 3 are done, so the refill goes out after those.
+        if ((!LATE_LOAD || nvalid == 0) && it + 1 < cnt) issue_load(clip, tin);
         if (nvalid == 0) continue;
         if (HOP160) {
 #pragma unroll
@@ -688,6 +690,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             }
         }
         __syncwarp();   // every lane has its rows in registers: the slab may now be overwritten with powers
+        if (LATE_LOAD && it + 1 < cnt) issue_load(clip, tin);
         dft20x2(XR, XI);   // .x = X (row t); .y = D with the row's spectrum Y[m] = D[(m + 1) % 20]
         {
             // Pair slot j: generic worker (rows a, 20-a): (X[j], Y[19-j])  -> bin a+20j (j<10) or its mirror.
@@ -989,7 +992,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     float2* s_p2 = reinterpret_cast<float2*>(s_warp);
     float* s_stage = reinterpret_cast<float*>(s_warp + p.smem_stage_off);
     float* s_pcm = reinterpret_cast<float*>(s_warp + p.smem_pcm_off);
-    float4* s_scr = reinterpret_cast<float4*>(s_warp + ZBYTES);   // pair prescale: (floor or guard, log offset) of frames A and B per FFT
+    float4* s_scr = reinterpret_cast<float4*>(s_warp + p.smem_scr_off);   // pair prescale: (floor or guard, log offset) of frames A and B per FFT
     const uint32_t bar = smem_u32(smem + 8 * warp);
     const uint64_t pol_in = l2_evict_first();                 // PCM is read once: it must not displace output rows in L2
 
@@ -1026,6 +1029,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 
     const int need = (FPW - 1) * 160 + p.frame_len;
 
+    // NeMo, ragged batch (per-clip lengths): every clip is its own waveform zero-padded to the common width, with its own frame
+    // count (src/mel.rs:387-395); samples past its length read as zeros, columns past its frame count are written as zeros
+    auto clip_len = [&](int clip) -> int { return (NEMO && p.lens) ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };
     auto issue_load = [&](int clip, int tin) {
         const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * 160;
@@ -1037,7 +1043,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             // frames hanging over the end)
             const long long t0 = s0 + p.frame_offset;
             const int lo = t0 < 0 ? (int)(-t0) : 0;
-            const long long endl = (long long)p.n_samples - t0;
+            const long long endl = (long long)clip_len(clip) - t0;
             const int hi = endl < need ? (endl < lo ? lo : (int)endl) : need;
             const float* tsrc = p.pcm + (long long)clip * p.clip_stride + t0;
             if (lo > 0 || hi < need) {   // warp-uniform
@@ -1045,7 +1051,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     if (i < lo || i >= hi) s_pcm[i + PAD * (i / CHUNK)] = 0.f;
                 __syncwarp();   // the zeros are read by other lanes; the mbarrier below only orders the TMA bytes
             }
-            if (p.bulk_in && hi > lo) {
+            if (p.bulk_in && hi > lo && (hi & 3) == 0) {   // (a ragged clip's last tile ends on any sample: bulk copies move whole 16-byte units)
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)(hi - lo) * 4u);
 #pragma unroll
@@ -1107,17 +1113,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const int clip = clip_f;
         const int fw0 = tile_in_clip * FPW;
         int nfr = p.frames_per_clip;
+        const int len_c = clip_len(clip);
         if (!NEMO && p.lens) {
             const int len = min(p.lens[clip], p.n_samples);
             nfr = len < p.frame_len ? 0 : (len - p.frame_len) / 160 + 1;
         }
+        if (NEMO && p.lens)   // centred (frame_offset < 0): len / hop + 1 frames; otherwise whole n_fft windows only
+            nfr = min(nfr, len_c <= 0 ? 0 : p.frame_offset < 0 ? len_c / 160 + 1 : (len_c < N ? 0 : (len_c - N) / 160 + 1));
         const int nvalid = max(0, min(FPW, nfr - fw0));
 
         // pre-emphasis look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it)
         float lead = 0.f;
         const bool owns_first = FRAME400 && g1 == 0 && c == 0;
         const long long tile0 = (long long)fw0 * 160 + (NEMO ? p.frame_offset : 0);   // clip index of tile sample 0
-        if (owns_first && tile0 > 0) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + tile0 - 1);
+        if (owns_first && tile0 > 0 && tile0 - 1 < len_c) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + tile0 - 1);
 
         mbar_wait(bar, it & 1);
 
@@ -1168,7 +1177,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 } else {
                     // NeMo pre-emphasises the waveform before padding: the first padding sample after the clip stays zero
                     // (it would otherwise pick up -c * x[len-1]); every other padded position is 0 - c*0 already
-                    const long long rel = (long long)p.n_samples - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
+                    const long long rel = (long long)len_c - tile0 - 320 * g1 - c;   // tile-relative index of sample `len`
                     if (rel >= 0 && rel < 16 * NLOAD && (rel & 15) == 0) {
 #pragma unroll
                         for (int m = 0; m < NLOAD; ++m)
@@ -1409,6 +1418,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             __syncwarp();
         }
         }   // nvalid != 0
+        if (NEMO && p.lens && nvalid < FPW) {   // columns past a short clip's own frame count are zeros, like the pad_to columns
+            const int q1 = min(FPW, p.frames_per_clip - fw0);
+            float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
+            for (int mel = lane; mel < p.n_mels; mel += 32)
+                for (int q = nvalid; q < q1; ++q) dst[(long long)mel * p.out_row_stride + q] = 0.f;
+        }
 
         // ------------------------------------------------------------------ fused CMN: end of this warp's share of the clip
         // Mode 2 (default): no CTA-wide barrier and no second pass through the SM.  Every warp delivers its column sums and

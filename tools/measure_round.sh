@@ -1,23 +1,27 @@
 #!/bin/bash
 # Round measurement pass (run on the GPU box through gpurun): bench lines, launch lists and ncu captures into gpurun_out/m/.
+#   tools/measure_round.sh [full]      (full: also the `ncu --set full` captures and the sanitizer runs)
+# Every command runs under its own `timeout`.
 set -x
 cd ${GRAFT_REPO_ROOT:-.}
-mkdir -p gpurun_out/m
-python bench.py > gpurun_out/m/bench_cfg2.json 2> gpurun_out/m/bench.err
-python bench.py --workload cfg3 > gpurun_out/m/bench_cfg3.json 2>> gpurun_out/m/bench.err
-python bench.py --workload cfg4shard --no-cpu-baseline > gpurun_out/m/bench_cfg4shard.json 2>> gpurun_out/m/bench.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/m/bench_reference.json 2>> gpurun_out/m/bench.err
-python tools/stream_bench.py > gpurun_out/m/stream_cfg5.json 2>> gpurun_out/m/bench.err
-python tools/bench_next_rows.py > gpurun_out/m/next_rows.jsonl 2>> gpurun_out/m/bench.err
+O=gpurun_out/m
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv > $O/gpu.txt
+timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench.err                                   # cfg2 + extra (cfg3, cfg4shard, cfg5 stream) + cpu_baseline
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference.json 2>> $O/bench.err
+timeout 600 python tools/bench_next_rows.py > $O/next_rows.jsonl 2>> $O/bench.err
+timeout 300 python tools/bench512.py > $O/bench512.txt 2>> $O/bench.err
 # launch lists: only kernels of the library (the torch kernels of the same command generate the synthetic PCM before the
 # timed region and would exhaust any launch-count limit)
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-ncu --metrics $M --clock-control none -k regex:melspec -c 60 --csv --log-file gpurun_out/m/launches_cfg2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/m/l2.log 2>&1
-ncu --metrics $M --clock-control none -k regex:melspec -c 60 --csv --log-file gpurun_out/m/launches_cfg3.csv python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/m/l3.log 2>&1
+for W in cfg2 cfg3 cfg4shard; do
+  timeout 600 ncu --metrics $M --clock-control none -k regex:melspec -c 30 --csv --log-file $O/launches_$W.csv python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/l_$W.log 2>&1
+done
 if [ "$1" = "full" ]; then
-ncu --set full --clock-control none --import-source on -k regex:melspec400 -c 1 -f -o gpurun_out/m/full400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/m/f400.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:melspec512 -c 1 -f -o gpurun_out/m/full512 python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/m/f512.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:melspec_cmn -c 1 -f -o gpurun_out/m/fullcmn python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/m/fcmn.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:melspec_generic -c 1 -f -o gpurun_out/m/fullgeneric python tools/bench_next_rows.py > gpurun_out/m/fgen.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:melspec400 -c 1 -f -o $O/full400 python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/f400.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:melspec512 -c 1 -f -o $O/full512 python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/f512.log 2>&1
+for T in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $T python -m pytest tests/test_gpu_parity.py tests/test_onset_parity.py tests/test_boundary_r2.py -m gpu -x -q -k "synthetic_batch or ragged_lengths or kaldi_fused or kaldi_batch or nemo_features or click_and_silence or int16_host or spectrogram_add_reference" > $O/san_$T.log 2>&1
+done
 fi
-cut -c1-300 gpurun_out/m/bench_cfg2.json
+cut -c1-300 $O/bench_n1.json
