@@ -140,6 +140,17 @@ public:
     melspec_handle* raw() const { return h_.get(); }
 
     // &[f32] -> Vec<Vec<f32>> [frame][mel] (src/cuda.rs:88-101); empty / too-short input => empty vector
+    // opt-in 16-bit PCM (x / 32768 on the device; bit-identical to the f32 call on the converted samples)
+    std::vector<std::vector<float>> compute_mel_spectrogram_i16(const std::vector<int16_t>& samples) {
+        const int64_t frames = melspec_num_frames(h_.get(), (int64_t)samples.size());
+        std::vector<std::vector<float>> out;
+        if (frames <= 0) return out;
+        std::vector<float> flat((size_t)frames * n_mels_);
+        detail::check(melspec_compute_host_i16(h_.get(), samples.data(), 1, (int64_t)samples.size(), (int64_t)samples.size(), flat.data(),
+                                               MELSPEC_LAYOUT_FRAME_MAJOR, nullptr));
+        for (int64_t f = 0; f < frames; ++f) out.emplace_back(flat.begin() + f * (long)n_mels_, flat.begin() + (f + 1) * (long)n_mels_);
+        return out;
+    }
     std::vector<std::vector<float>> compute_mel_spectrogram(const std::vector<float>& samples) {
         const size_t f = num_frames(samples.size());
         std::vector<std::vector<float>> out;
@@ -241,13 +252,61 @@ private:
     size_t n_mels_;
 };
 
-// reference src/stft.rs:119-138 (batch entry; GPU-backed, a handle per call like the reference re-plans per call)
-struct Spectrogram {
+// What Spectrogram::add hands to MelSpectrogram::add.  The reference passes the complex FFT frame (src/stft.rs:82, src/mel.rs:26);
+// here the chain is one fused kernel, so the token already holds the mel frame.
+struct SpectrogramFrame {
+    std::vector<float> mel;
+    size_t fft_size = 0;
+};
+
+// reference src/stft.rs:10-138.  The static member is the batch entry (src/stft.rs:119-138; a handle per call like the reference
+// re-plans per call); an instance is the streaming overlap-and-save entry with Spectrogram::add's own contract (src/stft.rs:48-86).
+class Spectrogram {
+public:
     static std::vector<std::vector<float>> compute_mel_spectrogram(const std::vector<float>& samples, size_t fft_size, size_t hop_size,
                                                                    size_t n_mels, double sampling_rate) {
         CudaMelSpectrogram m(fft_size, hop_size, sampling_rate, n_mels);
         return m.compute_mel_spectrogram(samples);
     }
+    Spectrogram(size_t fft_size, size_t hop_size, size_t n_mels = 80, double sampling_rate = 16000.0, int device = 0)
+        : fft_size_(fft_size), hop_size_(hop_size), n_mels_(n_mels), mel_(fft_size, hop_size, sampling_rate, n_mels, device) {
+        detail::check(melspec_stream_create(mel_.raw(), (int64_t)hop_size, &s_), true);
+    }
+    Spectrogram(const Spectrogram&) = delete;
+    Spectrogram& operator=(const Spectrogram&) = delete;
+    ~Spectrogram() {
+        if (s_) melspec_stream_destroy(s_);
+    }
+    // <= hop_size samples per call (more: std::invalid_argument, the reference asserts at src/stft.rs:53); a short chunk is
+    // zero-padded to a whole hop; a frame once fft_size true samples have been seen and with every call after that
+    std::optional<SpectrogramFrame> add(const std::vector<float>& frames) {
+        if (frames.size() > hop_size_) throw std::invalid_argument("frames must be <= hop_size");
+        SpectrogramFrame f;
+        f.mel.resize(n_mels_);
+        f.fft_size = fft_size_;
+        int32_t emitted = 0;
+        detail::check(melspec_stream_push_hop(s_, frames.data(), (int64_t)frames.size(), f.mel.data(), &emitted));
+        if (!emitted) return std::nullopt;
+        return f;
+    }
+
+private:
+    size_t fft_size_, hop_size_, n_mels_;
+    CudaMelSpectrogram mel_;
+    melspec_stream* s_ = nullptr;
+};
+
+// reference src/mel.rs:13-32: add(fft_frame) -> n_mels values (the reference's (n_mels, 1) array)
+class MelSpectrogram {
+public:
+    MelSpectrogram(size_t fft_size, double /*sampling_rate*/, size_t n_mels) : fft_size_(fft_size), n_mels_(n_mels) {}
+    std::vector<float> add(const SpectrogramFrame& fft) const {
+        if (fft.fft_size != fft_size_ || fft.mel.size() != n_mels_) throw std::invalid_argument("frame from a different configuration");
+        return fft.mel;
+    }
+
+private:
+    size_t fft_size_, n_mels_;
 };
 
 // reference src/fbank.rs:25-64 with its Default

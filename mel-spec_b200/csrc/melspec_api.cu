@@ -797,7 +797,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
             if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
                 MS_CUDA(cudaMemset2DAsync(d_out + frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - frames_per_clip) * 4,
                                           (size_t)n_clips * c.n_mels, st));
-            rc = nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
+            if (d_lens) rc = nw == 8 ? MS_DISPATCH(8, 3) : MS_DISPATCH(12, 3);   // ragged batch (per-clip lengths)
+            else rc = nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
         } else if (kaldi) {
             rc = nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
         } else {

@@ -113,8 +113,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
-// L2 eviction policies for the bulk copies.  The PCM is read once (evict_first: it must not push the output rows of the clips in
-// flight out of L2); rows that a later pass touches again (Kaldi CMN) are written evict_last and released by that pass.
+// L2 eviction policies for the bulk copies of the plan-512 kernel.  There the PCM is loaded evict_first (it must not push the output
+// rows of the clips in flight out of L2), and rows that a later pass touches again (Kaldi CMN) are written evict_last and released
+// by that pass.  Plan 400 uses plain loads: measured with the hint, the 240-sample halo a warp re-reads one pass later missed L2
+// (DRAM reads 657 -> 750 MB per cfg2 launch, profiles/README.md).
 __device__ __forceinline__ uint64_t l2_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -466,7 +468,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     float4* s_scr = reinterpret_cast<float4*>(s_warp + p.smem_scr_off);   // pair prescale: (floor, log offset) of frames A and B per FFT
     constexpr bool LATE_LOAD = (NWARPS == 16);   // see the tile loop
     const uint32_t bar = smem_u32(smem + 8 * warp);           // this warp's "PCM landed" mbarrier
-    const uint64_t pol_in = l2_evict_first();                 // PCM is read once: it must not displace output rows in L2
     // lanes of this FFT at ring distance 1, 2 | 3, 6, 9 (six bits each): the two-round all-reduce of the pair prescale
     const int ring = (10 * g + (t + 1) % 10) | (10 * g + (t + 2) % 10) << 6 | (10 * g + (t + 3) % 10) << 12 | (10 * g + (t + 6) % 10) << 18 |
                      (10 * g + (t + 9) % 10) << 24;
@@ -533,9 +534,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
                     for (int k = 0; k < NCHUNK; ++k)
                         if (CHUNK * k < avail)
-                            bulk_g2s_hint(smem_u32(s_pcm + k * CS320), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar, pol_in);
+                            bulk_g2s(smem_u32(s_pcm + k * CS320), src + CHUNK * k, (uint32_t)min(CHUNK, avail - CHUNK * k) * 4u, bar);
                 } else {
-                    bulk_g2s_hint(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar, pol_in);
+                    bulk_g2s(smem_u32(s_pcm), src, (uint32_t)avail * 4u, bar);
                 }
             }
         } else {   // unaligned input: cooperative copy (same layout), then a plain arrive
@@ -969,6 +970,7 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 -
 
 // MODE 0: Whisper fft 512.  MODE 1: Kaldi fbank.  MODE 2: NeMo BatchLogMel (whole-waveform pre-emphasis, frames may
 // hang over both ends of the clip: the missing samples are zero-filled in the stage, reference src/mel.rs:344-348,685-706).
+// MODE 3: the same with per-clip lengths (ragged batch), its own instantiation so that the dense mode pays nothing for it.
 #ifndef TWREG512
 #define TWREG512 false   // A/B switch: twiddles of the row transforms in registers (measured 3 % slower for the Whisper mode)
 #endif
@@ -976,7 +978,7 @@ template <int NWARPS, int MPL, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr bool KALDI = MODE == 1, NEMO = MODE == 2, FRAME400 = MODE != 0;
+    constexpr bool KALDI = MODE == 1, NEMO = MODE == 2 || MODE == 3, RAGGED = MODE == 3, FRAME400 = MODE != 0;
     constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
     constexpr int NROW = FRAME400 ? 25 : 32;   // non-zero rows of a frame (400 samples zero-padded to 512)
 
@@ -1005,10 +1007,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     if (lane == 0) {
         mbar_init(bar, 1);
         if (warp == 0) {   // fused CMN, mode 2: "all warps have finished clip" x 2 parities, "sums consumed" x 2 parities
-            mbar_init(smem_u32(smem + 8 * NWARPS), NWARPS);
-            mbar_init(smem_u32(smem + 8 * (NWARPS + 1)), NWARPS);
-            mbar_init(smem_u32(smem + 8 * (NWARPS + 2)), 1);
-            mbar_init(smem_u32(smem + 8 * (NWARPS + 3)), 1);
+            mbar_init(smem_u32(smem + 8 * NWARPS), NWARPS * 32);         // every thread arrives with its own sums (its own release)
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 1)), NWARPS * 32);
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 2)), 32);                // the 32 threads of warp 0
+            mbar_init(smem_u32(smem + 8 * (NWARPS + 3)), 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1031,7 +1033,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 
     // NeMo, ragged batch (per-clip lengths): every clip is its own waveform zero-padded to the common width, with its own frame
     // count (src/mel.rs:387-395); samples past its length read as zeros, columns past its frame count are written as zeros
-    auto clip_len = [&](int clip) -> int { return (NEMO && p.lens) ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };
+    auto clip_len = [&](int clip) -> int { return RAGGED ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };
     auto issue_load = [&](int clip, int tin) {
         const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * 160;
@@ -1051,7 +1053,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     if (i < lo || i >= hi) s_pcm[i + PAD * (i / CHUNK)] = 0.f;
                 __syncwarp();   // the zeros are read by other lanes; the mbarrier below only orders the TMA bytes
             }
-            if (p.bulk_in && hi > lo && (hi & 3) == 0) {   // (a ragged clip's last tile ends on any sample: bulk copies move whole 16-byte units)
+            if (p.bulk_in && hi > lo && (!RAGGED || (hi & 3) == 0)) {   // (a ragged clip's last tile ends on any sample: bulk copies move whole 16-byte units)
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)(hi - lo) * 4u);
 #pragma unroll
@@ -1118,7 +1120,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const int len = min(p.lens[clip], p.n_samples);
             nfr = len < p.frame_len ? 0 : (len - p.frame_len) / 160 + 1;
         }
-        if (NEMO && p.lens)   // centred (frame_offset < 0): len / hop + 1 frames; otherwise whole n_fft windows only
+        if (RAGGED)   // centred (frame_offset < 0): len / hop + 1 frames; otherwise whole n_fft windows only
             nfr = min(nfr, len_c <= 0 ? 0 : p.frame_offset < 0 ? len_c / 160 + 1 : (len_c < N ? 0 : (len_c - N) / 160 + 1));
         const int nvalid = max(0, min(FPW, nfr - fw0));
 
@@ -1418,7 +1420,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             __syncwarp();
         }
         }   // nvalid != 0
-        if (NEMO && p.lens && nvalid < FPW) {   // columns past a short clip's own frame count are zeros, like the pad_to columns
+        if (RAGGED && nvalid < FPW) {   // columns past a short clip's own frame count are zeros, like the pad_to columns
             const int q1 = min(FPW, p.frames_per_clip - fw0);
             float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
             for (int mel = lane; mel < p.n_mels; mel += 32)
@@ -1445,8 +1447,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 csum[s] = 0.f;
             }
             if (lane == 0) bulk_wait0();   // this warp's rows of the clip have landed
-            __syncwarp();                  // (orders every lane's sums before lane 0's arrival)
-            if (lane == 0) mbar_arrive(bar_done);
+            mbar_arrive(bar_done);         // every thread: release of its own column sums (lane 0: after its stores)
             if (warp == 0) {
                 mbar_wait(bar_done, (cmn_iter >> 1) & 1);
                 if (lane == 0) bulk_wait_read0();   // the previous clip's reductions have read s_neg
@@ -1471,7 +1472,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                         bulk_commit();   // (s_neg is rewritten one clip later; every pass waits for the reads of all groups first)
                     }
                 }
-                if (lane == 0) mbar_arrive(bar_free);
+                mbar_arrive(bar_free);     // every thread of warp 0: its reads of the sums are done
             }
             ++cmn_iter;
         }
@@ -1619,6 +1620,28 @@ __global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long 
         if (frames <= 0) return;
     }
     float* r = out + (long long)clip * out_clip_stride + (long long)mel * row_stride;
+    if (frames <= 1024) {   // the row fits the warp's registers (32 values per lane): one read and one write, same summation order
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = lane + 32 * k < frames ? __ldcs(r + lane + 32 * k) : 0.f;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sum += v[k];   // (the masked tail adds exact zeros)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)frames;
+        float var = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (lane + 32 * k < frames) { const float d = v[k] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float inv = 1.0f / (sqrtf(var / fmaxf((float)frames - 1.0f, 1.0f)) + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (lane + 32 * k < frames) r[lane + 32 * k] = (v[k] - mean) * inv;
+        return;
+    }
     float sum = 0.f;
     for (int f = lane; f < frames; f += 32) sum += r[f];
 #pragma unroll

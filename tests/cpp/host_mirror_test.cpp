@@ -124,6 +124,38 @@ int main(int argc, char** argv) {
         std::printf("ringbuffer fft512 vs rust_jfk_golden.npy: %zu frames, max abs diff %.3g\n", k, md);
     }
 
+    // ---- Spectrogram::add's own contract (src/stft.rs:175-194: fft 8, hop 4 -> None, None (7 < 8 true samples), Some), and fed
+    //      whole hops it equals the batch path on samples[80..] (stream offset c = 80 for 400 / 160)
+    {
+        Spectrogram sp(8, 4, 4, 16000.0);
+        MelSpectrogram ms(8, 16000.0, 4);
+        CHECK(!sp.add({1.f, 2.f, 3.f}).has_value(), "3 samples: None");
+        CHECK(!sp.add({1.f, 2.f, 3.f, 4.f}).has_value(), "7 samples: None");
+        auto f = sp.add({1.f, 2.f, 3.f, 4.f});
+        CHECK(f.has_value() && ms.add(*f).size() == 4, "11 samples: Some");
+        bool threw = false;
+        try { sp.add(std::vector<float>(5, 0.f)); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw, "frames must be <= hop_size");
+        Spectrogram s400(400, 160);
+        MelSpectrogram m400(400, 16000.0, 80);
+        std::vector<float> tail(jfk.begin() + 80, jfk.begin() + 80 + 160 * 60 + 240);
+        auto batch = mel.compute_mel_spectrogram(tail);
+        size_t k = 0;
+        float md = 0;
+        for (size_t off = 0; off + 160 <= 160 * 62; off += 160) {
+            auto fr = s400.add(std::vector<float>(jfk.begin() + off, jfk.begin() + off + 160));
+            if (!fr) continue;
+            auto col = m400.add(*fr);
+            if (k < batch.size()) for (size_t m = 0; m < 80; ++m) md = std::fmax(md, std::fabs(col[m] - batch[k][m]));
+            ++k;
+        }
+        CHECK(k == 60 && md <= 5e-5f, "Spectrogram::add fed whole hops == batch path on samples[80..]: " + std::to_string(k) + " frames, " + std::to_string(md));
+        std::vector<int16_t> pcm16(16000);
+        std::vector<float> pcmf(16000);
+        for (size_t i = 0; i < pcm16.size(); ++i) { pcm16[i] = (int16_t)std::lround(jfk[i] * 32767.0f); pcmf[i] = (float)pcm16[i] / 32768.0f; }
+        CHECK(mel.compute_mel_spectrogram_i16(pcm16) == mel.compute_mel_spectrogram(pcmf), "int16 entry == f32 entry on x / 32768");
+    }
+
     // ---- PCM -> TGA vs quantized_mel_golden.tga (fft 400 stream framing = batch framing on samples[80..])
     {
         const std::vector<uint8_t> gold = read_file(g + "/quantized_mel_golden.tga");
