@@ -11,6 +11,14 @@ timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench.err                  
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference.json 2>> $O/bench.err
 timeout 600 python tools/bench_next_rows.py > $O/next_rows.jsonl 2>> $O/bench.err
 timeout 300 python tools/bench512.py > $O/bench512.txt 2>> $O/bench.err
+# worst-case parity of the two-frames-per-transform packing: the new tests against this build and against the round-1 build
+timeout 300 python -m pytest tests/test_onset_parity.py -m gpu -q -s 2>&1 | grep -E "worst|passed|failed" > $O/onset_parity.txt
+if [ -f mel-spec_b200/lib/libmelspec_r1.so ]; then
+  echo "--- the same tests against the round-1 library (before the pair prescale)" >> $O/onset_parity.txt
+  MELSPEC_B200_LIB=$PWD/mel-spec_b200/lib/libmelspec_r1.so timeout 300 python -m pytest tests/test_onset_parity.py -m gpu -q 2>&1 | grep -E "^E   +Assertion|^FAILED|passed|failed" >> $O/onset_parity.txt
+  # A/B of the headline kernel: round-1 build vs this build, alternating
+  timeout 600 tools/ab_bench.sh mel-spec_b200/lib/libmelspec_r1.so mel-spec_b200/lib/libmelspec_b200.so cfg2 3 > $O/ab_r1_vs_r2.txt 2>&1
+fi
 # launch lists: only kernels of the library (the torch kernels of the same command generate the synthetic PCM before the
 # timed region and would exhaust any launch-count limit)
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
