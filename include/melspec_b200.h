@@ -222,7 +222,8 @@ int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm
  * device: 18-byte TGA header (type 3, 8 bpp, width/height little-endian u16) + 8-byte ID field holding f32 min and max of
  * the image + n_mels*width bytes ((v - min) * (255 / (max - min))).round().clamp(0, 255).  Bytes are bit-exact with the
  * reference for identical f32 input.  One image per clip: image r at d_img + r*img_stride floats (0 = dense), TGA r at
- * d_tga + r*tga_stride bytes (0 = melspec_tga_size).  width and n_mels must fit the header's u16 fields (<= 65535: the stride
+ * d_tga + r*tga_stride bytes (0 = melspec_tga_size).  The quantiser keeps its min / max partials in one workspace per handle: calls on
+ * the same handle must be issued on one stream (or otherwise serialised); use one handle per stream for concurrent quantisation.  width and n_mels must fit the header's u16 fields (<= 65535: the stride
  * tga_8bit cuts wider images into, src/quant.rs:29-36, 100-137; save_tga_8bit additionally asserts width < 65535, src/quant.rs:17-21).
  */
 int64_t melspec_tga_size(int32_t n_mels, int64_t width);                 /* 26 + n_mels*width, -1 if it cannot be a TGA */
