@@ -319,19 +319,8 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
             v[sl] = -INFINITY;
             if (mrow < p.n_mels) {
                 const int b0 = __ldg(g.bands + 3 * mrow), cnt = __ldg(g.bands + 3 * mrow + 1), wo = __ldg(g.bands + 3 * mrow + 2);
-                // four independent partial sums (ascending bins within each): the loads of an unrolled step are in flight together
-                // and the FMA chain is a quarter as long; fp32 summation order differs from the reference's f64 sum either way
-                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                const float* wp = g.weights + wo;
-                const float* pp = pw + b0;
-                int i = 0;
-                for (; i + 4 <= cnt; i += 4) {
-                    const float w0 = __ldg(wp + i), w1 = __ldg(wp + i + 1), w2 = __ldg(wp + i + 2), w3 = __ldg(wp + i + 3);
-                    const float q0 = pp[i], q1 = pp[i + 1], q2 = pp[i + 2], q3 = pp[i + 3];
-                    e0 = fmaf(w0, q0, e0); e1 = fmaf(w1, q1, e1); e2 = fmaf(w2, q2, e2); e3 = fmaf(w3, q3, e3);
-                }
-                for (; i < cnt; ++i) e0 = fmaf(__ldg(wp + i), pp[i], e0);
-                float e = (e0 + e1) + (e2 + e3);
+                float e = 0.f;
+                for (int i = 0; i < cnt; ++i) e = fmaf(__ldg(g.weights + wo + i), pw[b0 + i], e);
                 if (g.mode == 2) e = logf(e + p.log_add);                    // ln(E + guard), src/mel.rs:365-368
                 else if (g.mode == 1) {                                      // max(E, floor), optional ln, src/fbank.rs:207-221
                     e = fmaxf(e, p.floor_val);
