@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
     const int hop = HOP160 ? 160 : p.hop;
     const int need = (FPW - 1) * hop + N;    // samples a warp tile spans
+    int pr_off[MPL], mel_of[MPL];
+#pragma unroll
+    for (int s = 0; s < MPL; ++s) { pr_off[s] = s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane]; mel_of[s] = s_meta[kMaxMpl + s * 32 + lane]; }
 
     // Stage the PCM of warp tile `wt` into this warp's buffer (TMA bulk copies issued by one lane).
     auto issue_load = [&](int clip, int tin) {
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const float flq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z, ps2.x, ps2.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w, ps2.y, ps2.w};
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const float2* pr = s_p + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
+                const float2* pr = s_p + pr_off[s];
                 f2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0;
                 if (KSPEC != 0) {
                     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -801,7 +804,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             // Z exchange starts; the wait above orders the bulk store against that)
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of[s];
                 if (mel >= 0) {
 #pragma unroll
                     for (int q = 0; q < FPW; ++q) {
@@ -832,7 +835,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             float2* st2 = reinterpret_cast<float2*>(s_stage);
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of[s];
                 if (mel >= 0) {
 #pragma unroll
                     for (int u = 0; u < 3; ++u) {
@@ -869,7 +872,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of[s];
                 if (mel >= 0) {
 #pragma unroll
                     for (int q = 0; q < FPW; ++q) {
