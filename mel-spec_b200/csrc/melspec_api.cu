@@ -786,7 +786,11 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
                     : launch_kernel(melspec400_kernel<NW, 3, false, 0>, p, grid, NW * 32, off, st))                   \
           : (hop160 ? launch_kernel(melspec400_kernel<NW, 4, true, 0>, p, grid, NW * 32, off, st)                    \
                     : launch_kernel(melspec400_kernel<NW, 4, false, 0>, p, grid, NW * 32, off, st)))
-        rc = nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
+        // the launch shape of every large batch (frame-major, both TMA paths, no per-clip lengths) has its own instantiation with
+        // those switches compiled in (KSPEC 3)
+        const bool fast = h->kspec == 1 && hop160 && nw == 12 && p.bulk_in && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR && !d_lens && p.normalize;
+        rc = fast ? launch_kernel(melspec400_kernel<12, 3, true, 3>, p, grid, 12 * 32, off, st)
+             : nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
     } else {
 #define MS_DISPATCH(NW, MODE)                                                                                       \

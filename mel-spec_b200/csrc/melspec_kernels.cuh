@@ -152,6 +152,17 @@ __device__ __forceinline__ void bulk_reduce_add_f32(void* dst, uint32_t src, uin
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0_if(bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::"r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_commit_if(bool pred, void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+        "@q cp.async.bulk.global.shared::cta.bulk_group [%1], [%2], %3;\n\t"
+        "@q cp.async.bulk.commit_group;\n\t}" ::"r"((uint32_t)pred),
+        "l"(dst), "r"(src), "r"(bytes)
+        : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // log2 of a normal, positive number: the energies are floored (>= 1e-10 / FLT_EPSILON / log_zero_guard) before the
@@ -451,6 +462,13 @@ template <int NWARPS, int MPL, bool HOP160, int KSPEC>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParams p) {
     using namespace p400;
     extern __shared__ __align__(128) unsigned char smem[];
+    // KSPEC 3 = KSPEC 1 for the launch shape every large batch has (frame-major output, aligned buffers so that both TMA paths
+    // apply, no per-clip lengths): those run-time switches become compile-time constants
+    constexpr bool FAST = KSPEC == 3;
+    constexpr int KS_ = FAST ? 1 : KSPEC;
+    const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_bulk_out = FAST ? true : (p.bulk_out != 0), f_norm = FAST ? true : (p.normalize != 0);
+    const int f_layout = FAST ? 0 : p.layout;
+    const int32_t* const f_lens = FAST ? nullptr : p.lens;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the tile-loop state lives in uniform registers
     const int lane = threadIdx.x & 31;
@@ -530,7 +548,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
         const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
-        if (p.bulk_in) {
+        if (f_bulk_in) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
                 if (HOP160) {
@@ -565,8 +583,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     for (int it = 0; it < cnt; ++it) {
         const int fw0 = tin * FPW;   // first frame of this pass
         int nfr = p.frames_per_clip;
-        if (p.lens) {
-            const int len = min(p.lens[clip], p.n_samples);
+        if (f_lens) {
+            const int len = min(f_lens[clip], p.n_samples);
             nfr = len < p.fft_size ? 0 : (len - p.fft_size) / hop + 1;
         }
         const int nvalid = max(0, min(FPW, nfr - fw0));          // warp-uniform
@@ -670,7 +688,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const f2 ni = fma2(PR[10], ry, mul2(PI[10], rx));
             PR[10] = nr; PI[10] = ni;
         }
-        if (lane == 0) bulk_wait_read0();   // the previous pass's bulk store (its rows live inside this slab) is done
+        bulk_wait_read0_if(lane == 0);   // the previous pass's bulk store (its rows live inside this slab) is done (predicated, no branch)
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 20; ++k1)     // unit = (re col 2t, re col 2t+1, im col 2t, im col 2t+1)
@@ -740,8 +758,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
         {
-            constexpr int KS[4] = {KSPEC == 2 ? 8 : 14, KSPEC == 2 ? 5 : 4, 2, 0};   // KSPEC != 0: the Whisper 80-mel / fft-400 bank
-            constexpr bool EXS[4] = {KSPEC == 2, KSPEC == 2, false, false};         // slots whose split bands are summed by shuffle
+            constexpr int KS[4] = {KS_ == 2 ? 8 : 14, KS_ == 2 ? 5 : 4, 2, 0};   // KS_ != 0: the Whisper 80-mel / fft-400 bank
+            constexpr bool EXS[4] = {KS_ == 2, KS_ == 2, false, false};         // slots whose split bands are summed by shuffle
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             const float* wt = s_projw + lane;                                                          // [entry][lane]
             int eoff = 0;
@@ -751,7 +769,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             for (int s = 0; s < MPL; ++s) {
                 const float2* pr = s_p + pr_off[s];
                 f2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0;
-                if (KSPEC != 0) {
+                if (KS_ != 0) {
                     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int e = 0; e < KS[s]; ++e) {
@@ -776,7 +794,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                     }
                     eoff += K;
                 }
-                if (KSPEC != 0 ? EXS[s] : (s_meta[s] >> 16) != 0) {   // warp-uniform: add the other half of split bands
+                if (KS_ != 0 ? EXS[s] : (s_meta[s] >> 16) != 0) {   // warp-uniform: add the other half of split bands
                     const int pl = s_meta[kMaxMpl + 2 * kMaxMpl * 32 + s * 32 + lane];
                     const float sel = pl != lane ? 1.0f : 0.0f;
                     const f2 o0 = make_float2(__shfl_sync(0xffffffffu, acc0.x, pl), __shfl_sync(0xffffffffu, acc0.y, pl));
@@ -793,13 +811,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 }
             }
         }
-        if (p.normalize) {
+        if (f_norm) {
 #pragma unroll
             for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
         }
 
         // ------------------------------------------------------------------ store
-        if (p.layout == 0) {
+        if (f_layout == 0) {
             // the output rows are staged in the slab right behind the power rows (both dead once the next pass's
             // Z exchange starts; the wait above orders the bulk store against that)
 #pragma unroll
@@ -808,20 +826,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 if (mel >= 0) {
 #pragma unroll
                     for (int q = 0; q < FPW; ++q) {
-                        const float v = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                        const float v = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
                         s_stage[q * p.n_mels + mel] = v;
                     }
                 }
             }
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
             const int nout = nvalid * p.n_mels;
-            if (p.bulk_out) {
+            if (f_bulk_out) {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
-                    bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
-                    bulk_commit();
-                }
+                bulk_s2g_commit_if(lane == 0, dst, smem_u32(s_stage), (uint32_t)nout * 4u);   // (predicated, no branch)
             } else {
                 __syncwarp();
                 for (int i = lane; i < nout; i += 32) dst[i] = s_stage[i];
@@ -839,8 +854,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 if (mel >= 0) {
 #pragma unroll
                     for (int u = 0; u < 3; ++u) {
-                        const float v0 = p.normalize ? fmaf(fmaxf(lg[s][2 * u], mx[2 * u]), 0.25f, 1.0f) : lg[s][2 * u];
-                        const float v1 = p.normalize ? fmaf(fmaxf(lg[s][2 * u + 1], mx[2 * u + 1]), 0.25f, 1.0f) : lg[s][2 * u + 1];
+                        const float v0 = f_norm ? fmaf(fmaxf(lg[s][2 * u], mx[2 * u]), 0.25f, 1.0f) : lg[s][2 * u];
+                        const float v1 = f_norm ? fmaf(fmaxf(lg[s][2 * u + 1], mx[2 * u + 1]), 0.25f, 1.0f) : lg[s][2 * u + 1];
                         st2[3 * mel + u] = make_float2(v0, v1);
                     }
                 }
@@ -876,7 +891,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 if (mel >= 0) {
 #pragma unroll
                     for (int q = 0; q < FPW; ++q) {
-                        const float v = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                        const float v = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
                         if (q < nvalid) dst[(long long)mel * p.out_row_stride + q] = v;
                     }
                 }
