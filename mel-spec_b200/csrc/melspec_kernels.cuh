@@ -152,6 +152,35 @@ __device__ __forceinline__ void bulk_reduce_add_f32(void* dst, uint32_t src, uin
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// One elected lane of the (converged) warp arms the mbarrier with the tile's byte count and issues its chunk copies; a chunk of 0
+// bytes is skipped.  A single predicated instruction sequence: no divergent region, no per-copy election loop.
+__device__ __forceinline__ void tma_load_chunks4(uint32_t bar, uint32_t total, uint32_t dst0, uint32_t dst_stride, const void* src,
+                                                 uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t src_stride) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 d;\n\t"
+        ".reg .b64 s, st;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t"
+        "setp.ne.and.u32 q, %5, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], %5, [%0];\n\t"
+        "add.u32 d, %2, %3;\n\t"
+        "add.u64 s, %4, %9;\n\t"
+        "setp.ne.and.u32 q, %6, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [s], %6, [%0];\n\t"
+        "add.u32 d, d, %3;\n\t"
+        "add.u64 s, s, %9;\n\t"
+        "setp.ne.and.u32 q, %7, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [s], %7, [%0];\n\t"
+        "add.u32 d, d, %3;\n\t"
+        "add.u64 s, s, %9;\n\t"
+        "setp.ne.and.u32 q, %8, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [s], %8, [%0];\n\t"
+        "}" ::"r"(bar),
+        "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_wait_read0_if(bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::"r"((uint32_t)pred) : "memory");
 }
@@ -548,7 +577,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
         const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
-        if (f_bulk_in) {
+        if (FAST) {   // (HOP160, aligned: the whole warp is converged here)
+            const int a0 = min(CHUNK, avail), a1 = max(0, min(CHUNK, avail - CHUNK)), a2 = max(0, min(CHUNK, avail - 2 * CHUNK)),
+                      a3 = max(0, min(CHUNK, avail - 3 * CHUNK));
+            tma_load_chunks4(bar, (uint32_t)avail * 4u, smem_u32(s_pcm), CS320 * 4u, src, a0 * 4u, a1 * 4u, a2 * 4u, a3 * 4u, CHUNK * 4u);
+        } else if (f_bulk_in) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
                 if (HOP160) {
@@ -823,13 +856,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int mel = mel_of[s];
-                if (mel >= 0) {
+                float v[FPW];
 #pragma unroll
-                    for (int q = 0; q < FPW; ++q) {
-                        const float v = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
-                        s_stage[q * p.n_mels + mel] = v;
-                    }
-                }
+                for (int q = 0; q < FPW; ++q) v[q] = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                // six predicated stores (lanes without a mel in this slot skip them) instead of a divergent region per slot
+                const uint32_t a0 = smem_u32(s_stage + max(mel, 0)), rs = (uint32_t)p.n_mels * 4u;
+                asm volatile(
+                    "{\n\t.reg .pred q;\n\t.reg .b32 a;\n\t"
+                    "setp.ge.s32 q, %0, 0;\n\t"
+                    "@q st.shared.f32 [%1], %3;\n\t"
+                    "add.u32 a, %1, %2;\n\t@q st.shared.f32 [a], %4;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %5;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %6;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %7;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %8;\n\t}" ::"r"(mel),
+                    "r"(a0), "r"(rs), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5])
+                    : "memory");
             }
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
             const int nout = nvalid * p.n_mels;
