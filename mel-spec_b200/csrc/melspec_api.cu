@@ -796,19 +796,26 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
 #define MS_DISPATCH(NW, MODE)                                                                                       \
     (m3 ? launch_kernel(melspec512_kernel<NW, 3, MODE>, p, grid, NW * 32, off, st)                                   \
         : launch_kernel(melspec512_kernel<NW, 4, MODE>, p, grid, NW * 32, off, st))
+#define MS_DISPATCH_FAST(MODE)                                                                                      \
+    (m3 ? launch_kernel(melspec512_kernel<12, 3, MODE, true>, p, grid, 12 * 32, off, st)                             \
+        : launch_kernel(melspec512_kernel<12, 4, MODE, true>, p, grid, 12 * 32, off, st))
+        // the launch shape of every large dense batch (aligned buffers: both TMA paths, no per-clip lengths) has its own
+        // instantiation with those switches compiled in
+        const bool fast = nw == 12 && p.bulk_in && !d_lens && (nemo || p.bulk_out || fused_cmn) && !(fused_cmn && p.cmn_fused == 1);
         if (nemo) {
             // padding columns (pad_to) are zeros in the reference's feature matrix (src/mel.rs:336)
             if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
                 MS_CUDA(cudaMemset2DAsync(d_out + frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - frames_per_clip) * 4,
                                           (size_t)n_clips * c.n_mels, st));
             if (d_lens) rc = nw == 8 ? MS_DISPATCH(8, 3) : MS_DISPATCH(12, 3);   // ragged batch (per-clip lengths)
-            else rc = nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
+            else rc = fast ? MS_DISPATCH_FAST(2) : nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
         } else if (kaldi) {
-            rc = nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
+            rc = fast && p.bulk_out ? MS_DISPATCH_FAST(1) : nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
         } else {
-            rc = nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
+            rc = fast && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR ? MS_DISPATCH_FAST(0) : nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
         }
 #undef MS_DISPATCH
+#undef MS_DISPATCH_FAST
     }
     if (rc != MELSPEC_OK) return rc;
     h->launches += 1;

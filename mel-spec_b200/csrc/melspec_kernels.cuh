@@ -181,6 +181,42 @@ __device__ __forceinline__ void tma_load_chunks4(uint32_t bar, uint32_t total, u
         "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride)
         : "memory");
 }
+// the same with an L2 eviction policy on the copies (plan 512)
+__device__ __forceinline__ void tma_load_chunks4_hint(uint32_t bar, uint32_t total, uint32_t dst0, uint32_t dst_stride, const void* src,
+                                                      uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t src_stride, uint64_t pol) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 d;\n\t"
+        ".reg .b64 s, st;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t"
+        "setp.ne.and.u32 q, %5, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%2], [%4], %5, [%0], %10;\n\t"
+        "add.u32 d, %2, %3;\n\t"
+        "add.u64 s, %4, %9;\n\t"
+        "setp.ne.and.u32 q, %6, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [d], [s], %6, [%0], %10;\n\t"
+        "add.u32 d, d, %3;\n\t"
+        "add.u64 s, s, %9;\n\t"
+        "setp.ne.and.u32 q, %7, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [d], [s], %7, [%0], %10;\n\t"
+        "add.u32 d, d, %3;\n\t"
+        "add.u64 s, s, %9;\n\t"
+        "setp.ne.and.u32 q, %8, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [d], [s], %8, [%0], %10;\n\t"
+        "}" ::"r"(bar),
+        "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint_commit_if(bool pred, void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t"
+        "@q cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%1], [%2], %3, %4;\n\t"
+        "@q cp.async.bulk.commit_group;\n\t}" ::"r"((uint32_t)pred),
+        "l"(dst), "r"(src), "r"(bytes), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_wait_read0_if(bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::"r"((uint32_t)pred) : "memory");
 }
@@ -1034,10 +1070,16 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 -
 #ifndef TWREG512
 #define TWREG512 false   // A/B switch: twiddles of the row transforms in registers (measured 3 % slower for the Whisper mode)
 #endif
-template <int NWARPS, int MPL, int MODE>
+// FAST: the launch shape every large dense batch has (aligned buffers so that the TMA paths apply, no per-clip lengths, the
+// frontend's own layout) compiled in, like KSPEC 3 of melspec400_kernel.
+template <int NWARPS, int MPL, int MODE, bool FAST = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
     extern __shared__ __align__(128) unsigned char smem[];
+    const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_norm = FAST ? (MODE == 0) : (p.normalize != 0);
+    const int f_layout = FAST ? (MODE >= 2 ? 1 : 0) : p.layout;
+    const bool f_bulk_out = FAST ? (MODE < 2) : (p.bulk_out != 0);
+    const int32_t* const f_lens = FAST ? nullptr : p.lens;
     constexpr bool KALDI = MODE == 1, NEMO = MODE == 2 || MODE == 3, RAGGED = MODE == 3, FRAME400 = MODE != 0;
     constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
     constexpr int NROW = FRAME400 ? 25 : 32;   // non-zero rows of a frame (400 samples zero-padded to 512)
@@ -1093,7 +1135,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 
     // NeMo, ragged batch (per-clip lengths): every clip is its own waveform zero-padded to the common width, with its own frame
     // count (src/mel.rs:387-395); samples past its length read as zeros, columns past its frame count are written as zeros
-    auto clip_len = [&](int clip) -> int { return RAGGED ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };
+    auto clip_len = [&](int clip) -> int { return RAGGED ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };   // (RAGGED is never FAST)
     auto issue_load = [&](int clip, int tin) {
         const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * 160;
@@ -1113,7 +1155,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     if (i < lo || i >= hi) s_pcm[i + PAD * (i / CHUNK)] = 0.f;
                 __syncwarp();   // the zeros are read by other lanes; the mbarrier below only orders the TMA bytes
             }
-            if (p.bulk_in && hi > lo && (!RAGGED || (hi & 3) == 0)) {   // (a ragged clip's last tile ends on any sample: bulk copies move whole 16-byte units)
+            if (FAST && lo == 0 && hi == need) {   // interior tile: one elected lane, one predicated sequence (warp converged)
+                tma_load_chunks4_hint(bar, (uint32_t)need * 4u, smem_u32(s_pcm), CS * 4u, tsrc, min(CHUNK, need) * 4u,
+                                      max(0, min(CHUNK, need - CHUNK)) * 4u, max(0, min(CHUNK, need - 2 * CHUNK)) * 4u,
+                                      max(0, min(CHUNK, need - 3 * CHUNK)) * 4u, CHUNK * 4u, pol_in);
+            } else if (f_bulk_in && hi > lo && (!RAGGED || (hi & 3) == 0)) {   // (a ragged clip's last tile ends on any sample: bulk copies move whole 16-byte units)
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)(hi - lo) * 4u);
 #pragma unroll
@@ -1127,7 +1173,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);
             }
-        } else if (p.bulk_in) {
+        } else if (FAST) {   // the whole warp is converged here: one elected lane, one predicated sequence
+            const int a0 = min(CHUNK, avail), a1 = max(0, min(CHUNK, avail - CHUNK)), a2 = max(0, min(CHUNK, avail - 2 * CHUNK)),
+                      a3 = max(0, min(CHUNK, avail - 3 * CHUNK));
+            tma_load_chunks4_hint(bar, (uint32_t)avail * 4u, smem_u32(s_pcm), CS * 4u, src, a0 * 4u, a1 * 4u, a2 * 4u, a3 * 4u, CHUNK * 4u, pol_in);
+        } else if (f_bulk_in) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
 #pragma unroll
@@ -1176,8 +1226,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         const int fw0 = tile_in_clip * FPW;
         int nfr = p.frames_per_clip;
         const int len_c = clip_len(clip);
-        if (!NEMO && p.lens) {
-            const int len = min(p.lens[clip], p.n_samples);
+        if (!NEMO && f_lens) {
+            const int len = min(f_lens[clip], p.n_samples);
             nfr = len < p.frame_len ? 0 : (len - p.frame_len) / 160 + 1;
         }
         if (RAGGED)   // centred (frame_offset < 0): len / hop + 1 frames; otherwise whole n_fft windows only
@@ -1301,7 +1351,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const float r = ar[16] * r16.x - ai[16] * r16.y, i = fmaf(ar[16], r16.y, ai[16] * r16.x);
             ar[16] = r; ai[16] = i;
         }
-        if (lane == 0) bulk_wait_read0();
+        bulk_wait_read0_if(lane == 0);
         __syncwarp();
         {
             unsigned char* zw = s_warp + g1 * ZSLABB + 8 * c;
@@ -1392,30 +1442,36 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 }
             }
         }
-        if (p.normalize) {
+        if (f_norm) {
 #pragma unroll
             for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
         }
-        if (p.layout == 0) {
+        if (f_layout == 0) {
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const int mel = s_meta[kMaxMpl + s * 32 + lane];
-                if (mel >= 0) {
+                float v[FPW];
 #pragma unroll
-                    for (int q = 0; q < FPW; ++q)
-                        s_stage[q * p.n_mels + mel] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
-                }
+                for (int q = 0; q < FPW; ++q) v[q] = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                // four predicated stores (lanes without a mel in this slot skip them) instead of a divergent region per slot
+                const uint32_t a0 = smem_u32(s_stage + max(mel, 0)), rs = (uint32_t)p.n_mels * 4u;
+                asm volatile(
+                    "{\n\t.reg .pred q;\n\t.reg .b32 a;\n\t"
+                    "setp.ge.s32 q, %0, 0;\n\t"
+                    "@q st.shared.f32 [%1], %3;\n\t"
+                    "add.u32 a, %1, %2;\n\t@q st.shared.f32 [a], %4;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %5;\n\t"
+                    "add.u32 a, a, %2;\n\t@q st.shared.f32 [a], %6;\n\t}" ::"r"(mel),
+                    "r"(a0), "r"(rs), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                    : "memory");
             }
             float* dst = p.out + (long long)clip * p.out_clip_stride + (long long)fw0 * p.n_mels;
             const int nout = nvalid * p.n_mels;
-            if (p.bulk_out) {
+            if (f_bulk_out) {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
-                    if (fused) bulk_s2g_hint(dst, smem_u32(s_stage), (uint32_t)nout * 4u, l2_evict_last());   // the CMN reduction comes back for these rows
-                    else bulk_s2g(dst, smem_u32(s_stage), (uint32_t)nout * 4u);
-                    bulk_commit();
-                }
+                if (fused) bulk_s2g_hint_commit_if(lane == 0, dst, smem_u32(s_stage), (uint32_t)nout * 4u, l2_evict_last());   // the CMN reduction comes back for these rows
+                else bulk_s2g_commit_if(lane == 0, dst, smem_u32(s_stage), (uint32_t)nout * 4u);
             } else if (p.vec_out) {
                 __syncwarp();
                 for (int i = lane; i < nout / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_stage)[i];
@@ -1443,7 +1499,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 if (mel >= 0) {
                     float v[FPW];
 #pragma unroll
-                    for (int q = 0; q < FPW; ++q) v[q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                    for (int q = 0; q < FPW; ++q) v[q] = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
                     st4[mel] = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
@@ -1474,7 +1530,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                     for (int q = 0; q < FPW; ++q)
                         if (q < nvalid)
-                            dst[(long long)mel * p.out_row_stride + q] = p.normalize ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
+                            dst[(long long)mel * p.out_row_stride + q] = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
                 }
             }
             __syncwarp();
