@@ -717,6 +717,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             }
         }
 
+        bool resc;   // warp-uniform: some pair of this pass is scaled
         {   // pair prescale (see pair_prescale).  Level of a frame = max |first-layer value| = max (|x0 w0| + |x2 w2|) over its windowed
             // sample pairs: within a factor 2 of the peak windowed sample.  All-reduced over the FFT's 10 lanes.
             float ma = 0.f, mb = 0.f;
@@ -739,8 +740,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             int ka, kb;
             float4 tab;
             pair_prescale(pk, p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);
-            s_scr[g] = tab;
-            if (__any_sync(0xffffffffu, (ka | kb) != 0)) {   // rare (onsets, decays, digital silence next to sound): exact scaling
+            resc = __any_sync(0xffffffffu, (ka | kb) != 0);
+            if (resc) {   // rare (onsets, decays, digital silence next to sound): exact scaling; only then does the epilogue read the table
+                s_scr[g] = tab;
                 const float ra = pow2i(ka), rb = pow2i(kb);
 #pragma unroll
                 for (int b = 0; b < 5; ++b)
@@ -832,8 +834,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             const float* wt = s_projw + lane;                                                          // [entry][lane]
             int eoff = 0;
-            const float4 ps0 = s_scr[0], ps1 = s_scr[1], ps2 = s_scr[2];   // pair prescale: (floor, log offset) of the six frames
-            const float flq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z, ps2.x, ps2.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w, ps2.y, ps2.w};
+            float flq[FPW], cq[FPW];   // pair prescale: (floor, log offset) of the six frames
+#pragma unroll
+            for (int q = 0; q < FPW; ++q) { flq[q] = p.floor_val; cq[q] = 0.f; }
+            if (resc) {
+                const float4 ps0 = s_scr[0], ps1 = s_scr[1], ps2 = s_scr[2];
+                flq[0] = ps0.x; flq[1] = ps0.z; flq[2] = ps1.x; flq[3] = ps1.z; flq[4] = ps2.x; flq[5] = ps2.z;
+                cq[0] = ps0.y; cq[1] = ps0.w; cq[2] = ps1.y; cq[3] = ps1.w; cq[4] = ps2.y; cq[5] = ps2.w;
+            }
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
                 const float2* pr = s_p + pr_off[s];
