@@ -191,6 +191,7 @@ struct melspec_handle {
     int* d_meta = nullptr;
     int proj_ktot = 0;
     int kspec = 0;                 // compile-time projection schedule the table matches (1: Whisper-80/fft-400: 14,4,2)
+    int ksched512 = 0;             // plan 512: index into melspec::ksched512 (0: none, counts are read from the table)
     int proj_wavefront_cost = 0;   // half-warp wavefronts per LDS.64 of the projection loop, summed over entries (ideal: 2 per entry)
     int mpl = 0;
     // host-path resources (lazily created)
@@ -547,6 +548,12 @@ int32_t build_tables(melspec_handle* h) {
             if (K[0] == 14 && K[1] == 4 && K[2] == 2 && !EX[0] && !EX[1] && !EX[2]) h->kspec = 1;
             if (K[0] == 8 && K[1] == 5 && K[2] == 2 && EX[0] && EX[1] && !EX[2]) h->kspec = 2;
         }
+        h->ksched512 = 0;
+        if (N == 512 && !EX[0] && !EX[1] && !EX[2] && !EX[3])
+            for (int k = 1; k < 5; ++k)
+                if (K[0] == melspec::ksched512(k, 0) && K[1] == melspec::ksched512(k, 1) && K[2] == melspec::ksched512(k, 2) &&
+                    K[3] == melspec::ksched512(k, 3))
+                    h->ksched512 = k;
         proj.resize(wtab.size() / 2);
         std::memcpy(proj.data(), wtab.data(), wtab.size() * sizeof(float));
     }
@@ -802,17 +809,27 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         // the launch shape of every large dense batch (aligned buffers: both TMA paths, no per-clip lengths) has its own
         // instantiation with those switches compiled in
         const bool fast = nw == 12 && p.bulk_in && !d_lens && (nemo || p.bulk_out || fused_cmn) && !(fused_cmn && p.cmn_fused == 1);
+        // ... and the filterbanks of the frontends' defaults have their projection schedule compiled in (melspec::ksched512);
+        // MELSPEC_KSCHED=0 falls back to the table-driven loop (A/B)
+        static const bool ksched_on = [] { const char* e = std::getenv("MELSPEC_KSCHED"); return !(e && e[0] == '0'); }();
+        const int ks = ksched_on ? h->ksched512 : 0;
         if (nemo) {
             // padding columns (pad_to) are zeros in the reference's feature matrix (src/mel.rs:336)
             if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
                 MS_CUDA(cudaMemset2DAsync(d_out + frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - frames_per_clip) * 4,
                                           (size_t)n_clips * c.n_mels, st));
             if (d_lens) rc = nw == 8 ? MS_DISPATCH(8, 3) : MS_DISPATCH(12, 3);   // ragged batch (per-clip lengths)
+            else if (fast && ks == 3) rc = launch_kernel(melspec512_kernel<12, 3, 2, true, 3>, p, grid, 12 * 32, off, st);
+            else if (fast && ks == 4) rc = launch_kernel(melspec512_kernel<12, 4, 2, true, 4>, p, grid, 12 * 32, off, st);
             else rc = fast ? MS_DISPATCH_FAST(2) : nw == 8 ? MS_DISPATCH(8, 2) : MS_DISPATCH(12, 2);
         } else if (kaldi) {
-            rc = fast && p.bulk_out ? MS_DISPATCH_FAST(1) : nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
+            if (fast && p.bulk_out && ks == 2) rc = launch_kernel(melspec512_kernel<12, 3, 1, true, 2>, p, grid, 12 * 32, off, st);
+            else rc = fast && p.bulk_out ? MS_DISPATCH_FAST(1) : nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
         } else {
-            rc = fast && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR ? MS_DISPATCH_FAST(0) : nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
+            const bool f0 = fast && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR;
+            if (f0 && ks == 1) rc = launch_kernel(melspec512_kernel<12, 3, 0, true, 1>, p, grid, 12 * 32, off, st);
+            else if (f0 && ks == 4) rc = launch_kernel(melspec512_kernel<12, 4, 0, true, 4>, p, grid, 12 * 32, off, st);
+            else rc = f0 ? MS_DISPATCH_FAST(0) : nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
         }
 #undef MS_DISPATCH
 #undef MS_DISPATCH_FAST

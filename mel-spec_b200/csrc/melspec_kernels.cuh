@@ -1080,7 +1080,16 @@ __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 -
 #endif
 // FAST: the launch shape every large dense batch has (aligned buffers so that the TMA paths apply, no per-clip lengths, the
 // frontend's own layout) compiled in, like KSPEC 3 of melspec400_kernel.
-template <int NWARPS, int MPL, int MODE, bool FAST = false>
+// KSCHED: compile-time projection schedule (entries per slot), like KSPEC of melspec400_kernel: 0 = counts read from the table (any
+// filterbank), 1 = Slaney 80-mel without the Nyquist bin (Whisper fft 512: 18, 5, 2), 2 = the Kaldi 80-bin bank (16, 6, 2), 3 = Slaney
+// 80-mel with the Nyquist bin (NeMo: 19, 5, 2), 4 = Slaney 128-mel (NeMo 128 / Whisper large-v3 style at fft 512: 12, 6, 3, 2).  The
+// loops are then fully unrolled (no loop control, weights read as LDS.128 quads, all loads of a slot in flight together); the host
+// picks the schedule by comparing the counts of the table it built.
+__host__ __device__ constexpr int ksched512(int k, int s) {
+    constexpr int T[5][4] = {{0, 0, 0, 0}, {18, 5, 2, 0}, {16, 6, 2, 0}, {19, 5, 2, 0}, {12, 6, 3, 2}};
+    return T[k][s];
+}
+template <int NWARPS, int MPL, int MODE, bool FAST = false, int KSCHED = 0>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1111,7 +1120,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     // tables: window [32][16] floats, twiddles [8 i][16 t] float4 = (W_512^(t*2i), W_512^(t*(2i+1)))
     for (int i = threadIdx.x; i < 512; i += NWARPS * 32) reinterpret_cast<float*>(smem + p.smem_win)[i] = reinterpret_cast<const float*>(p.window)[i];
     for (int i = threadIdx.x; i < 128; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_tw)[i] = p.twiddle[i];
-    for (int i = threadIdx.x; i < p.proj_ktot * 32; i += NWARPS * 32)   // weights, [entry][lane]
+    for (int i = threadIdx.x; i < (KSCHED != 0 ? 2 : 1) * p.proj_ktot * 32; i += NWARPS * 32)   // weights, [entry][lane] (+ [quad][lane][4])
         reinterpret_cast<float*>(smem + p.smem_proj)[i] = reinterpret_cast<const float*>(p.proj)[i];
     for (int i = threadIdx.x; i < kMetaInts; i += NWARPS * 32) reinterpret_cast<int*>(smem + p.smem_meta)[i] = p.proj_meta[i];
     if (lane == 0) {
@@ -1263,13 +1272,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
                 for (int a = 0; a < 16; ++a) {
                     const float w0 = s_win[32 * a], w1 = s_win[32 * a + 16];
-                    er[a] = va ? make_float2(x[2 * a] * w0, x[2 * a + 1] * w1) : make_float2(0.f, 0.f);
-                    ei[a] = vb ? make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1) : make_float2(0.f, 0.f);
+                    er[a] = make_float2(x[2 * a] * w0, x[2 * a + 1] * w1);
+                    ei[a] = make_float2(x[2 * a + 10] * w0, x[2 * a + 11] * w1);
                 }
             } else {
                 // d[m] = x[m] - preemph * x[m-1]; the previous sample is one word back (one chunk pad further back at a
                 // chunk start); frame sums for the DC removal are reduced over the 16 lanes of the FFT
-                float sa = 0.f, sb = 0.f;
+                float sa = 0.f, sb = 0.f, smid = 0.f;
                 const float x0 = x[0];
 #pragma unroll
                 for (int m = 0; m < NLOAD; ++m) {
@@ -1280,12 +1289,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     } else {
                         xp = px[16 * m + PAD * (m / 20) - 1];
                     }
-                    if (KALDI && m < 25) sa += x[m];
-                    if (KALDI && m >= 10) sb += x[m];
+                    // frame sums for the DC removal: rows 10..24 belong to both frames and are summed once
+                    if (KALDI && m < 10) sa += x[m];
+                    if (KALDI && m >= 10 && m < 25) smid += x[m];
+                    if (KALDI && m >= 25) sb += x[m];
                     x[m] = fmaf(-p.preemph, xp, x[m]);
                 }
                 float ka = 0.f, kb = 0.f;
                 if (KALDI) {
+                    sa += smid; sb += smid;
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) {
                         sa += __shfl_xor_sync(0xffffffffu, sa, o);
@@ -1310,16 +1322,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                     float r0 = 0.f, r1 = 0.f, i0 = 0.f, i1 = 0.f;
                     if (2 * a < NROW) {
                         const float w0 = s_win[32 * a];
-                        r0 = va ? (x[2 * a] - ka) * w0 : 0.f;
-                        i0 = vb ? (x[2 * a + 10] - kb) * w0 : 0.f;
+                        r0 = (x[2 * a] - ka) * w0;
+                        i0 = (x[2 * a + 10] - kb) * w0;
                     }
                     if (2 * a + 1 < NROW) {
                         const float w1 = s_win[32 * a + 16];
-                        r1 = va ? (x[2 * a + 1] - ka) * w1 : 0.f;
-                        i1 = vb ? (x[2 * a + 11] - kb) * w1 : 0.f;
+                        r1 = (x[2 * a + 1] - ka) * w1;
+                        i1 = (x[2 * a + 11] - kb) * w1;
                     }
                     er[a] = make_float2(r0, r1);
                     ei[a] = make_float2(i0, i1);
+                }
+            }
+            if (nvalid != FPW) {   // ragged tail (warp-uniform): frames past the clip's last one are exact zeros
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    er[a] = va ? er[a] : make_float2(0.f, 0.f);
+                    ei[a] = vb ? ei[a] : make_float2(0.f, 0.f);
                 }
             }
         }
@@ -1427,20 +1446,37 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             const float* wt = s_projw + lane;
             const float4 ps0 = s_scr[0], ps1 = s_scr[1];   // pair prescale: (floor or guard, log offset) of the four frames
             const float vq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w};
+            const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
+            int eoff = 0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int K = s_meta[s] & 0xffff;
                 const float4* pr = s_p4 + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
                 f2 acc01 = make_float2(0.f, 0.f), acc23 = acc01;
+                if (KSCHED != 0) {
+                    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int e = 0; e < ksched512(KSCHED, s); ++e) {
+                        const int ge = eoff + e;
+                        if ((ge & 3) == 0 || e == 0) w4 = wq[(ge >> 2) * 32];
+                        const float w = (ge & 3) == 0 ? w4.x : (ge & 3) == 1 ? w4.y : (ge & 3) == 2 ? w4.z : w4.w;
+                        const float4 pw = pr[e];
+                        const f2 ww = make_float2(w, w);
+                        acc01 = fma2(ww, make_float2(pw.x, pw.y), acc01);
+                        acc23 = fma2(ww, make_float2(pw.z, pw.w), acc23);
+                    }
+                    eoff += ksched512(KSCHED, s);
+                } else {
+                    const int K = s_meta[s] & 0xffff;
 #pragma unroll 4
-                for (int e = 0; e < K; ++e) {
-                    const float w = wt[e * 32];
-                    const float4 pw = pr[e];
-                    const f2 ww = make_float2(w, w);
-                    acc01 = fma2(ww, make_float2(pw.x, pw.y), acc01);
-                    acc23 = fma2(ww, make_float2(pw.z, pw.w), acc23);
+                    for (int e = 0; e < K; ++e) {
+                        const float w = wt[e * 32];
+                        const float4 pw = pr[e];
+                        const f2 ww = make_float2(w, w);
+                        acc01 = fma2(ww, make_float2(pw.x, pw.y), acc01);
+                        acc23 = fma2(ww, make_float2(pw.z, pw.w), acc23);
+                    }
+                    wt += K * 32;
                 }
-                wt += K * 32;
                 const float acc[FPW] = {acc01.x, acc01.y, acc23.x, acc23.y};
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) {
