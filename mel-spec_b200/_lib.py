@@ -15,6 +15,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("MELSPEC_B200_LIB") or os.path.join(_PKG, "lib", "libmelspec_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "melspec_api.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "melspec_kernels.cuh"), os.path.join(_PKG, "csrc", "melspec_generic.cuh"),
+           os.path.join(_PKG, "csrc", "melspec_generic2.cuh"),
            os.path.join(_ROOT, "include", "melspec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-ldl"]

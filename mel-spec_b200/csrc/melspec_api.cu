@@ -21,6 +21,7 @@
 
 #include "melspec_kernels.cuh"
 #include "melspec_generic.cuh"
+#include "melspec_generic2.cuh"
 
 namespace {
 
@@ -183,6 +184,11 @@ struct melspec_handle {
     int* d_gbands = nullptr;
     float* d_gweights = nullptr;
     std::vector<int> radices;
+    int pair_nw = 0, pair_warps = 0;   // general plan, pair form: warps per CTA (0: not chosen yet, -1: does not fit) and per SM
+    float* d_gweights_t = nullptr; // general plan, pair form: weights as [slot][entry][lane], zero padded
+    int* d_gstarts_t = nullptr;    // ... and the first power row of every mel row's window
+    int n_gweights_t = 0;
+    int g_kmax[4] = {0, 0, 0, 0};  // entries per slot of that table
     // device tables
     float* d_window = nullptr;
     float4* d_twiddle = nullptr;
@@ -276,6 +282,43 @@ int32_t build_tables_generic(melspec_handle* h) {
         for (int b = b0; b0 >= 0 && b <= b1; ++b) wts.push_back((float)h->dense[(size_t)m * nb + b]);
     }
     if (wts.empty()) wts.push_back(0.f);
+    // pair form: the same weights as [slot][entry][lane], zero padded to the slot's longest window.  A mel row's window starts at or
+    // up to 15 rows before its band (zero weights in front) so that the 16 lanes of a half-warp start at 16 different rows mod 16:
+    // their 64-bit reads of the power pairs are then conflict-free (measured before: 5 wavefronts per read instead of 2).
+    std::vector<float> wts_t;
+    std::vector<int> starts((size_t)std::max(c.n_mels, 1), 0);
+    for (int sl = 0; sl < melspec::kMaxMpl; ++sl) {
+        int lead[32] = {0};
+        for (int hw = 0; hw < 2; ++hw) {
+            bool used[16] = {false};
+            for (int l = 16 * hw; l < 16 * hw + 16; ++l) {
+                const int m = 32 * sl + l;
+                if (m >= c.n_mels) continue;
+                const int b0 = bands[3 * m];
+                int d = 0;
+                while (d < 16 && d <= b0 && used[(b0 - d) & 15]) ++d;
+                if (d == 16 || d > b0) d = 0;   // no free residue within reach: keep the band start (costs a wavefront)
+                used[(b0 - d) & 15] = true;
+                lead[l] = d;
+                starts[m] = b0 - d;
+            }
+        }
+        int km = 0;
+        for (int l = 0; l < 32; ++l)
+            if (32 * sl + l < c.n_mels) km = std::max(km, bands[3 * (32 * sl + l) + 1] + lead[l]);
+        h->g_kmax[sl] = km;
+        for (int i = 0; i < km; ++i)
+            for (int l = 0; l < 32; ++l) {
+                const int m = 32 * sl + l, j = i - lead[l];
+                wts_t.push_back(m < c.n_mels && j >= 0 && j < bands[3 * m + 1] ? wts[(size_t)bands[3 * m + 2] + j] : 0.f);
+            }
+    }
+    MS_CUDA(cudaMalloc(&h->d_gstarts_t, sizeof(int) * starts.size()));
+    MS_CUDA(cudaMemcpy(h->d_gstarts_t, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice));
+    h->n_gweights_t = (int)wts_t.size();
+    if (wts_t.empty()) wts_t.push_back(0.f);
+    MS_CUDA(cudaMalloc(&h->d_gweights_t, sizeof(float) * wts_t.size()));
+    MS_CUDA(cudaMemcpy(h->d_gweights_t, wts_t.data(), sizeof(float) * wts_t.size(), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMalloc(&h->d_gtw, sizeof(float2) * tw.size()));
     MS_CUDA(cudaMalloc(&h->d_gwin, sizeof(float) * std::max<size_t>(win.size(), 1)));
     MS_CUDA(cudaMalloc(&h->d_gbands, sizeof(int) * bands.size()));
@@ -615,7 +658,76 @@ int32_t launch_post_kernels(melspec_handle* h, const melspec::KParams& p, int64_
     return MELSPEC_OK;
 }
 
-// The general plan: one warp per pair of frames, mixed-radix shared-memory FFT (melspec_generic.cuh).
+// The general plan, pair form (melspec_generic2.cuh): one warp per two neighbouring frames.  Returns MELSPEC_OK with *launched = false
+// when two frames' buffers would leave too few warps on an SM; the caller then runs the one-frame kernel.
+template <int NFT>
+int32_t launch_generic_pair_t(melspec_handle* h, const melspec::KParams& p, const melspec::GParams& g, int64_t n_clips, cudaStream_t st,
+                              bool* launched) {
+    using namespace melspec;
+    auto kern = melspec_generic_pair_kernel<NFT>;
+    *launched = false;
+    if (g.n_weights_t == 0) return MELSPEC_OK;
+    const size_t w_bytes = ((size_t)4 * g.n_weights_t + 15) & ~(size_t)15;
+    const size_t stw_bytes = ((size_t)8 * g2_stw_elems(NFT ? NFT : 1) + 15) & ~(size_t)15;
+    const size_t budget = 226 * 1024, per_warp = (size_t)32 * generic2_buf_elems(g.Nf),
+                 tw_bytes = (((size_t)8 * (NFT ? g.N / 4 + 1 : g.N) + 15) & ~(size_t)15) + w_bytes + stw_bytes;
+    // warps per CTA: the count that keeps the most warps resident on an SM (one twiddle / weight table per CTA), asked of the
+    // occupancy calculator itself (register allocation granularity decides between one and two CTAs); 8 unless another count is
+    // clearly better.  Computed once per handle.
+    MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (h->pair_nw == 0) {
+        int warps_at[17] = {0};
+        for (int cand = 2; cand <= 16; ++cand) {
+            const size_t need = tw_bytes + per_warp * cand;
+            if (need > budget) break;
+            int blocks = 0;
+            MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, cand * 32, need));
+            warps_at[cand] = cand * blocks;
+        }
+        int nw = 8;
+        while (nw > 2 && warps_at[nw] == 0) --nw;
+        for (int cand = 2; cand <= 16; ++cand)
+            if (warps_at[cand] * 100 > warps_at[nw] * (cand < nw ? 125 : 110)) nw = cand;
+        h->pair_nw = warps_at[nw] > 0 ? nw : -1;
+        h->pair_warps = warps_at[nw];
+    }
+    static const int min_warps = [] { const char* e = std::getenv("MELSPEC_PAIR_MIN_WARPS"); return e ? std::atoi(e) : 8; }();
+    if (h->pair_nw < 0 || h->pair_warps < min_warps) return MELSPEC_OK;   // large transforms: the one-frame kernel keeps more warps in flight
+    const int nw = h->pair_nw, per_sm = h->pair_warps / nw;
+    const size_t smem = tw_bytes + per_warp * nw;
+    const long long n_pairs = (long long)((p.frames_per_clip + 1) / 2) * n_clips;
+    const long long want = (n_pairs + nw - 1) / nw;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->num_sms * per_sm));
+    kern<<<grid, nw * 32, smem, st>>>(p, g);
+    MS_CUDA(cudaGetLastError());
+    *launched = true;
+    return MELSPEC_OK;
+}
+
+int32_t launch_generic_pair(melspec_handle* h, const melspec::KParams& p, const melspec::GParams& g, int64_t n_clips, cudaStream_t st,
+                            bool* launched) {
+    // MELSPEC_GENERIC_PAIR: 0 = one-frame kernel only, 1 (default) = pair form, compiled-in sizes where they exist, 2 = pair form with
+    // sizes read at run time only, 3 = pair form for the compiled-in sizes only
+    static const int mode = [] { const char* e = std::getenv("MELSPEC_GENERIC_PAIR"); return e ? std::atoi(e) : 1; }();
+    *launched = false;
+    if (mode == 0) return MELSPEC_OK;
+    if (mode == 1 && g.N == 2 * g.Nf) {
+        switch (g.Nf) {
+            case 128: return launch_generic_pair_t<128>(h, p, g, n_clips, st, launched);
+            case 240: return launch_generic_pair_t<240>(h, p, g, n_clips, st, launched);
+            case 256: return launch_generic_pair_t<256>(h, p, g, n_clips, st, launched);
+            case 320: return launch_generic_pair_t<320>(h, p, g, n_clips, st, launched);
+            case 400: return launch_generic_pair_t<400>(h, p, g, n_clips, st, launched);
+            case 512: return launch_generic_pair_t<512>(h, p, g, n_clips, st, launched);
+            default: break;
+        }
+    }
+    // other sizes: the pair form with sizes read at run time (measured 1.1 - 1.4 x the one-frame kernel; the compiled-in sizes 1.4 - 1.9 x)
+    if (mode == 3) return MELSPEC_OK;   // (A/B: compiled-in sizes only)
+    return launch_generic_pair_t<0>(h, p, g, n_clips, st, launched);
+}
+
+// The general plan: one warp per frame (or per two frames, above), mixed-radix shared-memory FFT (melspec_generic.cuh).
 int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, const int32_t* d_lens, float* d_out,
                        int64_t row_stride, cudaStream_t st) {
     using namespace melspec;
@@ -635,8 +747,24 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     g.mode = c.frontend == MELSPEC_FRONTEND_KALDI ? 1 : c.frontend == MELSPEC_FRONTEND_NEMO ? 2 : 0;
     g.use_power = c.use_power; g.use_log = c.use_log; g.center = c.center;
     g.n_units = (long long)p.frames_per_clip * n_clips;
+    g.weights_t = h->d_gweights_t; g.starts_t = h->d_gstarts_t;
+    g.n_weights_t = h->n_gweights_t * 4 <= 32 * 1024 ? h->n_gweights_t : 0;   // (0: too large for shared memory, no pair form)
+    for (int sl = 0; sl < 4; ++sl) g.kmax[sl] = h->g_kmax[sl];
+    p.n_clips = (int)n_clips;
     // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
     g.vec2 = ((uintptr_t)p.pcm % 8 == 0) && (p.clip_stride % 2 == 0) && (c.hop % 2 == 0) && (p.frame_offset % 2 == 0) && (c.fft % 2 == 0);
+    if (c.frontend == MELSPEC_FRONTEND_NEMO && row_stride > p.frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
+        MS_CUDA(cudaMemset2DAsync(d_out + p.frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - p.frames_per_clip) * 4,
+                                  (size_t)n_clips * c.n_mels, st));   // pad_to columns are zeros (src/mel.rs:336)
+    {
+        bool launched = false;
+        const int32_t rc = launch_generic_pair(h, p, g, n_clips, st, &launched);
+        if (rc != MELSPEC_OK) return rc;
+        if (launched) {
+            h->launches += 1;
+            return launch_post_kernels(h, p, n_clips, d_lens, d_out, false, st);
+        }
+    }
     const size_t budget = 220 * 1024, per_warp = (size_t)16 * generic_buf_elems(g.Nf), tw_bytes = (size_t)8 * c.fft;
     // warps per CTA: the count that puts the most warps on an SM (the kernel is latency bound: every FFT stage is a
     // round trip through shared memory), given one twiddle table per CTA, 227 KB of shared memory and 64 K registers per SM
@@ -663,9 +791,6 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     if (per_sm < 1) return fail(MELSPEC_ERR_UNSUPPORTED, "fft_size too large for the shared-memory FFT of this build");
     const long long want = (g.n_units + nw - 1) / nw;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->num_sms * per_sm));
-    if (c.frontend == MELSPEC_FRONTEND_NEMO && row_stride > p.frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
-        MS_CUDA(cudaMemset2DAsync(d_out + p.frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - p.frames_per_clip) * 4,
-                                  (size_t)n_clips * c.n_mels, st));   // pad_to columns are zeros (src/mel.rs:336)
     melspec_generic_kernel<<<grid, nw * 32, smem, st>>>(p, g);
     MS_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -1000,6 +1125,8 @@ void melspec_destroy(melspec_handle* h) {
     cudaFree(h->d_gwin);
     cudaFree(h->d_gbands);
     cudaFree(h->d_gweights);
+    cudaFree(h->d_gweights_t);
+    cudaFree(h->d_gstarts_t);
     cudaFree(h->d_partials);
     cudaFree(h->d_fmt_img);
     cudaFree(h->d_fmt_tga);

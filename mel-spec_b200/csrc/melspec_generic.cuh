@@ -51,6 +51,13 @@ struct GParams {
     int sshift[kMaxStages]; // log2 of the stage's stride s when it is a power of two (shift instead of an integer division), else -1
     int vec2;               // Whisper prologue may use 64-bit loads (8-byte aligned rows, even hop and frame offset)
     int center;             // NeMo: frames are centred (frame count len/hop + 1), for per-clip lengths
+    // pair form (melspec_generic2.cuh): the same weights transposed and zero padded, [slot][entry][lane] with kmax[slot] entries per
+    // slot (slot = mel row / 32, lane = mel row % 32), staged in shared memory: conflict-free reads, warp-uniform trip counts
+    const float* weights_t;
+    const int* starts_t;    // [n_mels] first power row of the mel row's window: at or up to 15 rows before its band, chosen so that the
+                            // 16 lanes of a half-warp start at 16 different rows mod 16 (conflict-free 64-bit reads of the power pairs)
+    int n_weights_t;        // 32 * (kmax[0] + .. + kmax[3]); 0: table too large for shared memory, the pair form is not used
+    int kmax[4];
 };
 
 // physical position of element i in a ping-pong buffer (one pad slot per 16 elements)

@@ -1149,6 +1149,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     __syncthreads();
 
     const int need = (FPW - 1) * 160 + p.frame_len;
+#ifndef MS512_META_REGS
+#define MS512_META_REGS 0
+#endif
+#ifndef MS512_RESC
+#define MS512_RESC 0
+#endif
+    constexpr bool META_REGS = MS512_META_REGS && KSCHED != 0;   // window start | mel << 16 per slot, kept in registers
+    constexpr bool RESC = MS512_RESC && KSCHED != 0;             // prescale table written / read only in passes that scale something
+    int meta_r[MPL];
+    if (META_REGS) {
+#pragma unroll
+        for (int s = 0; s < MPL; ++s)
+            meta_r[s] = (s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane] & 0xffff) | (int)((unsigned)s_meta[kMaxMpl + s * 32 + lane] << 16);
+    }
+    auto mel_of = [&](int s) -> int { return META_REGS ? (meta_r[s] >> 16) : s_meta[kMaxMpl + s * 32 + lane]; };
+    auto win_of = [&](int s) -> int { return META_REGS ? (meta_r[s] & 0xffff) : s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane]; };
 
     // NeMo, ragged batch (per-clip lengths): every clip is its own waveform zero-padded to the common width, with its own frame
     // count (src/mel.rs:387-395); samples past its length read as zeros, columns past its frame count are written as zeros
@@ -1348,6 +1364,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         if (wt_next < p.n_wtiles) issue_load(clip_next, tin_next);
         if (nvalid != 0) {   // (tiles past a short clip's last frame do no work but still take part in the clip's CMN step)
 
+        bool resc;   // warp-uniform: some frame of this pass is scaled
         {   // pair prescale (see pair_prescale): peak levels of the two prepared frames, all-reduced over the FFT's 16 lanes
             float ma = 0.f, mb = 0.f;
 #pragma unroll
@@ -1365,8 +1382,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             int ka, kb;
             float4 tab;
             pair_prescale(pk, NEMO ? p.log_add : p.floor_val, p.log_mul, p.ps_down, p.ps_up, ka, kb, tab);
-            s_scr[g1] = tab;
-            if (__any_sync(0xffffffffu, (ka | kb) != 0)) {   // rare: exact power-of-two scaling of a frame
+            resc = __any_sync(0xffffffffu, (ka | kb) != 0);
+            if (!RESC || resc) s_scr[g1] = tab;
+            if (resc) {   // rare: exact power-of-two scaling of a frame
                 const float ra = pow2i(ka), rb = pow2i(kb);
 #pragma unroll
                 for (int a = 0; a < 16; ++a) { er[a] = mul2c(ra, er[a]); ei[a] = mul2c(rb, ei[a]); }
@@ -1444,13 +1462,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             // windowed projection (see melspec400_kernel): the lane's K_s entries are consecutive power rows from its window
             // start, so the loads do not depend on the table and pipeline freely; weights come from [entry][lane]
             const float* wt = s_projw + lane;
-            const float4 ps0 = s_scr[0], ps1 = s_scr[1];   // pair prescale: (floor or guard, log offset) of the four frames
-            const float vq[FPW] = {ps0.x, ps0.z, ps1.x, ps1.z}, cq[FPW] = {ps0.y, ps0.w, ps1.y, ps1.w};
+            // pair prescale: (floor or guard, log offset) of the four frames
+            const float v0 = NEMO ? p.log_add : p.floor_val;
+            float vq[FPW] = {v0, v0, v0, v0}, cq[FPW] = {0.f, 0.f, 0.f, 0.f};
+            if (!RESC || resc) {
+                const float4 ps0 = s_scr[0], ps1 = s_scr[1];
+                vq[0] = ps0.x; vq[1] = ps0.z; vq[2] = ps1.x; vq[3] = ps1.z;
+                cq[0] = ps0.y; cq[1] = ps0.w; cq[2] = ps1.y; cq[3] = ps1.w;
+            }
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             int eoff = 0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const float4* pr = s_p4 + s_meta[kMaxMpl + kMaxMpl * 32 + s * 32 + lane];
+                const float4* pr = s_p4 + win_of(s);
                 f2 acc01 = make_float2(0.f, 0.f), acc23 = acc01;
                 if (KSCHED != 0) {
                     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1493,7 +1517,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         if (f_layout == 0) {
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of(s);
                 float v[FPW];
 #pragma unroll
                 for (int q = 0; q < FPW; ++q) v[q] = f_norm ? fmaf(fmaxf(lg[s][q], mx[q]), 0.25f, 1.0f) : lg[s][q];
@@ -1539,7 +1563,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             float4* st4 = reinterpret_cast<float4*>(s_stage);
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of(s);
                 if (mel >= 0) {
                     float v[FPW];
 #pragma unroll
@@ -1569,7 +1593,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             float* dst = p.out + (long long)clip * p.out_clip_stride + fw0;
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of(s);
                 if (mel >= 0) {
 #pragma unroll
                     for (int q = 0; q < FPW; ++q)
@@ -1602,7 +1626,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             if (cmn_iter >= 2) mbar_wait(bar_free, ((cmn_iter >> 1) - 1) & 1);   // warp 0 has consumed this buffer's previous sums
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of(s);
                 if (mel >= 0) s_cs[warp * 128 + mel] = csum[s];
                 csum[s] = 0.f;
             }
@@ -1642,7 +1666,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             float* s_mean = s_cs + NWARPS * 128;                             // [128]
 #pragma unroll
             for (int s = 0; s < MPL; ++s) {
-                const int mel = s_meta[kMaxMpl + s * 32 + lane];
+                const int mel = mel_of(s);
                 if (mel >= 0) s_cs[warp * 128 + mel] = csum[s];
                 csum[s] = 0.f;
             }
