@@ -660,16 +660,16 @@ int32_t launch_post_kernels(melspec_handle* h, const melspec::KParams& p, int64_
 
 // The general plan, pair form (melspec_generic2.cuh): one warp per two neighbouring frames.  Returns MELSPEC_OK with *launched = false
 // when two frames' buffers would leave too few warps on an SM; the caller then runs the one-frame kernel.
-template <int NFT>
+template <int NFT, bool INPLACE = false, bool LB = false>
 int32_t launch_generic_pair_t(melspec_handle* h, const melspec::KParams& p, const melspec::GParams& g, int64_t n_clips, cudaStream_t st,
                               bool* launched) {
     using namespace melspec;
-    auto kern = melspec_generic_pair_kernel<NFT>;
+    auto kern = melspec_generic_pair_kernel<NFT, INPLACE, LB>;
     *launched = false;
     if (g.n_weights_t == 0) return MELSPEC_OK;
     const size_t w_bytes = ((size_t)4 * g.n_weights_t + 15) & ~(size_t)15;
     const size_t stw_bytes = ((size_t)8 * g2_stw_elems(NFT ? NFT : 1) + 15) & ~(size_t)15;
-    const size_t budget = 226 * 1024, per_warp = (size_t)32 * generic2_buf_elems(g.Nf),
+    const size_t budget = 226 * 1024, per_warp = (size_t)(INPLACE ? 16 : 32) * generic2_buf_elems(g.Nf),
                  tw_bytes = (((size_t)8 * (NFT ? g.N / 4 + 1 : g.N) + 15) & ~(size_t)15) + w_bytes + stw_bytes;
     // warps per CTA: the count that keeps the most warps resident on an SM (one twiddle / weight table per CTA), asked of the
     // occupancy calculator itself (register allocation granularity decides between one and two CTAs); 8 unless another count is
@@ -677,7 +677,7 @@ int32_t launch_generic_pair_t(melspec_handle* h, const melspec::KParams& p, cons
     MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (h->pair_nw == 0) {
         int warps_at[17] = {0};
-        for (int cand = 2; cand <= 16; ++cand) {
+        for (int cand = 2; cand <= (LB ? 8 : 16); ++cand) {
             const size_t need = tw_bytes + per_warp * cand;
             if (need > budget) break;
             int blocks = 0;
@@ -709,16 +709,23 @@ int32_t launch_generic_pair(melspec_handle* h, const melspec::KParams& p, const 
     // MELSPEC_GENERIC_PAIR: 0 = one-frame kernel only, 1 (default) = pair form, compiled-in sizes where they exist, 2 = pair form with
     // sizes read at run time only, 3 = pair form for the compiled-in sizes only
     static const int mode = [] { const char* e = std::getenv("MELSPEC_GENERIC_PAIR"); return e ? std::atoi(e) : 1; }();
+    // MELSPEC_PAIR_INPLACE=0: two buffers per warp everywhere (A/B); default: one buffer where two leave fewer warps than the registers allow
+    static const bool inplace = [] { const char* e = std::getenv("MELSPEC_PAIR_INPLACE"); return !(e && e[0] == '0'); }();
+    static const bool lb = [] { const char* e = std::getenv("MELSPEC_PAIR_LB"); return !(e && e[0] == '0'); }();   // (0: A/B against the 128-register build)
     *launched = false;
     if (mode == 0) return MELSPEC_OK;
     if (mode == 1 && g.N == 2 * g.Nf) {
         switch (g.Nf) {
-            case 128: return launch_generic_pair_t<128>(h, p, g, n_clips, st, launched);
+            // measured (profiles/r2_generic_pair_ab.txt): the 80-register build pays at fft 256 only (945 vs 894 M frames/s; fft 480 /
+            // 512: 5 - 7 % slower); the one-buffer form pays at fft 1024 (476 vs 407 M) and loses at fft 800 (spills: 309 vs 421 M)
+            case 128: return lb ? launch_generic_pair_t<128, false, true>(h, p, g, n_clips, st, launched)
+                                : launch_generic_pair_t<128>(h, p, g, n_clips, st, launched);
             case 240: return launch_generic_pair_t<240>(h, p, g, n_clips, st, launched);
             case 256: return launch_generic_pair_t<256>(h, p, g, n_clips, st, launched);
             case 320: return launch_generic_pair_t<320>(h, p, g, n_clips, st, launched);
             case 400: return launch_generic_pair_t<400>(h, p, g, n_clips, st, launched);
-            case 512: return launch_generic_pair_t<512>(h, p, g, n_clips, st, launched);
+            case 512: return inplace ? launch_generic_pair_t<512, true>(h, p, g, n_clips, st, launched)
+                                     : launch_generic_pair_t<512>(h, p, g, n_clips, st, launched);
             default: break;
         }
     }

@@ -174,6 +174,56 @@ __device__ __forceinline__ void pstages_ct(float4*& src, float4*& dst, const flo
         pstages_ct<NF, M, S * R, OFF + (M > 1 ? (R - 1) * M : 0)>(src, dst, s_tw, s_stw, lane);
     }
 }
+// In-place form of a compile-time stage (one buffer per warp instead of two: more warps fit on the SM).  A Stockham stage writes where
+// other lanes read, so every lane first pulls all of its butterflies into registers (NF / 8 registers) and transforms them; after a
+// warp barrier the results go back into the same buffer.
+template <int R, int NF, int M, int S>
+__device__ __forceinline__ void pstage_inplace(float4* buf, const float2* stw, const int lane) {
+    constexpr int CNT = NF / R, SM = S * M, ITERS = (CNT + 31) / 32, SH = g2_log2_or_neg(S);
+    cpair a[ITERS][R];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int bfly = lane + 32 * it;
+        if (bfly < CNT) {
+            const int pp = SH >= 0 ? bfly >> SH : bfly / S, q = bfly - pp * S, bi = q + S * pp;
+#pragma unroll
+            for (int i = 0; i < R; ++i) a[it][i] = ldp(buf, bi + SM * i);
+            if constexpr (R == 8) pdft8(a[it]);
+            else if constexpr (R == 4) { cpair y0, y1, y2, y3; pdft4(a[it][0], a[it][1], a[it][2], a[it][3], y0, y1, y2, y3); a[it][0] = y0; a[it][1] = y1; a[it][2] = y2; a[it][3] = y3; }
+            else if constexpr (R == 2) { const cpair t = padd(a[it][0], a[it][1]); a[it][1] = psub(a[it][0], a[it][1]); a[it][0] = t; }
+            else {
+                cpair y[R];
+                pdft_small<R>(a[it], y);
+#pragma unroll
+                for (int j = 0; j < R; ++j) a[it][j] = y[j];
+            }
+            if (M > 1) {
+#pragma unroll
+                for (int j = 1; j < R; ++j) a[it][j] = pmul(a[it][j], stw[(j - 1) * M + pp]);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int bfly = lane + 32 * it;
+        if (bfly < CNT) {
+            const int pp = SH >= 0 ? bfly >> SH : bfly / S, q = bfly - pp * S, bo = q + S * R * pp;
+#pragma unroll
+            for (int j = 0; j < R; ++j) stp(buf, bo + S * j, a[it][j]);
+        }
+    }
+}
+template <int NF, int NCUR, int S, int OFF>
+__device__ __forceinline__ void pstages_inplace_ct(float4* buf, const float2* s_stw, const int lane) {
+    if constexpr (NCUR > 1) {
+        constexpr int R = g2_radix(NCUR), M = NCUR / R;
+        static_assert(NCUR % R == 0, "compile-time sizes are products of 2, 3 and 5");
+        pstage_inplace<R, NF, M, S>(buf, s_stw + OFF, lane);
+        __syncwarp();
+        pstages_inplace_ct<NF, M, S * R, OFF + (M > 1 ? (R - 1) * M : 0)>(buf, s_stw, lane);
+    }
+}
 // fill the stage tables from the W_N^k table in global memory (once per CTA): W_Nf^(j p s) = W_N^(2 j p s), and j p s < Nf
 template <int NF, int NCUR, int S, int OFF>
 __device__ __forceinline__ void fill_stw_ct(const float2* tw, float2* s_stw) {
@@ -189,8 +239,11 @@ __device__ __forceinline__ void fill_stw_ct(const float2* tw, float2* s_stw) {
     }
 }
 
-template <int NFT>
-__global__ void __launch_bounds__(512) melspec_generic_pair_kernel(const KParams p, const GParams g) {
+// LB256x3: compiled for at most 256 threads per CTA and three CTAs per SM (80 registers per thread instead of up to 128): small
+// transforms are latency-bound and register-limited, so more resident warps can beat a few spills.
+template <int NFT, bool INPLACE = false, bool LB256x3 = false>
+__global__ void __launch_bounds__(LB256x3 ? 256 : 512, LB256x3 ? 3 : 1) melspec_generic_pair_kernel(const KParams p, const GParams g) {
+    static_assert(!INPLACE || NFT != 0, "the one-buffer form needs a compile-time size");
     extern __shared__ __align__(16) unsigned char gsm[];
     const int N = NFT ? 2 * NFT : g.N, Nf = NFT ? NFT : g.Nf, tmul = N / Nf;   // W_Nf^k = W_N^(tmul k)
     const bool packed = NFT ? true : Nf != N;
@@ -206,8 +259,8 @@ __global__ void __launch_bounds__(512) melspec_generic_pair_kernel(const KParams
     constexpr size_t stw_bytes = ((size_t)8 * g2_stw_elems(NFT ? NFT : 1) + 15) & ~(size_t)15;   // per-stage twiddle tables (compile-time sizes)
     float* s_wts = reinterpret_cast<float*>(gsm + tw_bytes);
     float2* s_stw = reinterpret_cast<float2*>(gsm + tw_bytes + w_bytes);
-    float4* buf0 = reinterpret_cast<float4*>(gsm + tw_bytes + w_bytes + stw_bytes) + (size_t)warp * 2 * nfp;
-    float4* buf1 = buf0 + nfp;
+    float4* buf0 = reinterpret_cast<float4*>(gsm + tw_bytes + w_bytes + stw_bytes) + (size_t)warp * (INPLACE ? 1 : 2) * nfp;
+    float4* buf1 = INPLACE ? buf0 : buf0 + nfp;
     for (int i = threadIdx.x; i < tw_elems; i += blockDim.x) s_tw[i] = g.tw[i];
     for (int i = threadIdx.x; i < g.n_weights_t; i += blockDim.x) s_wts[i] = g.weights_t[i];
     if constexpr (NFT != 0) fill_stw_ct<NFT, NFT, 1, 0>(g.tw, s_stw);
@@ -346,7 +399,9 @@ __global__ void __launch_bounds__(512) melspec_generic_pair_kernel(const KParams
         // ------------------------------------------------------------------ Stockham autosort FFT of both frames
         float4* src = buf0;
         float4* dst = buf1;
-        if constexpr (NFT != 0) {
+        if constexpr (INPLACE) {
+            pstages_inplace_ct<NFT, NFT, 1, 0>(buf0, s_stw, lane);
+        } else if constexpr (NFT != 0) {
             pstages_ct<NFT, NFT, 1, 0>(src, dst, s_tw, s_stw, lane);
         } else {
             int ncur = Nf, s = 1;
@@ -371,29 +426,45 @@ __global__ void __launch_bounds__(512) melspec_generic_pair_kernel(const KParams
             if (!g.use_power) e = make_float2(sqrtf(e.x), sqrtf(e.y));   // src/fbank.rs:197-203
             return e;
         };
-        if (packed) {
-            // X[k] = E[k] + W_N^k O[k] and X[Nf - k] = conj(E[k] - W_N^k O[k]) come from the same two values Z[k], Z[Nf - k] and
-            // the same twiddle: one lane forms both bins (k = 1 .. Nf/2; k = Nf/2 pairs with itself and is written twice)
+        // X[k] = E[k] + W_N^k O[k] and X[Nf - k] = conj(E[k] - W_N^k O[k]) come from the same two values Z[k], Z[Nf - k] and
+        // the same twiddle: one lane forms both bins (k = 1 .. Nf/2; k = Nf/2 pairs with itself and is written twice)
+        auto bins2 = [&](const int k, const cpair zk, const cpair zm) {
+            const f2 er = mul2c(0.5f, add2(zk.re, zm.re)), ei = mul2c(0.5f, sub2(zk.im, zm.im));
+            const f2 orr = mul2c(0.5f, add2(zk.im, zm.im)), oi = mul2c(-0.5f, sub2(zk.re, zm.re));
+            const float2 w = s_tw[k];
+            const f2 tr = fma2c(-w.y, oi, mul2c(w.x, orr)), ti = fma2c(w.y, orr, mul2c(w.x, oi));
+            pw[k] = mag(add2(er, tr), add2(ei, ti));
+            pw[Nf - k] = mag(sub2(er, tr), sub2(ei, ti));
+        };
+        auto bins_dc = [&](const cpair z0) {   // DC and Nyquist: X[0] = Re Z[0] + Im Z[0], X[N/2] = Re Z[0] - Im Z[0]
+            const f2 x0 = add2(z0.re, z0.im), xn = sub2(z0.re, z0.im);
+            pw[0] = g.use_power ? mul2(x0, x0) : make_float2(fabsf(x0.x), fabsf(x0.y));
+            pw[nb] = g.use_power ? mul2(xn, xn) : make_float2(fabsf(xn.x), fabsf(xn.y));
+        };
+        if constexpr (INPLACE) {   // the powers overwrite the spectrum: all of it is read into registers first
+            constexpr int CNT = NFT / 2, ITERS = (CNT + 31) / 32;
+            cpair zk[ITERS], zm[ITERS];
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int k = 1 + lane + 32 * it;
+                if (k <= CNT) { zk[it] = ldp(src, k); zm[it] = ldp(src, NFT - k); }
+            }
+            const cpair z0 = ldp(src, 0);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int k = 1 + lane + 32 * it;
+                if (k <= CNT) bins2(k, zk[it], zm[it]);
+            }
+            if (lane == 0) bins_dc(z0);
+        } else if (packed) {
             const int cnt = Nf / 2, iters = (cnt + 31) >> 5;
 #pragma unroll
             for (int it = 0; it < iters; ++it) {
                 const int k = 1 + lane + 32 * it;
-                if (k <= cnt) {
-                    const cpair zk = ldp(src, k), zm = ldp(src, Nf - k);
-                    const f2 er = mul2c(0.5f, add2(zk.re, zm.re)), ei = mul2c(0.5f, sub2(zk.im, zm.im));
-                    const f2 orr = mul2c(0.5f, add2(zk.im, zm.im)), oi = mul2c(-0.5f, sub2(zk.re, zm.re));
-                    const float2 w = s_tw[k];
-                    const f2 tr = fma2c(-w.y, oi, mul2c(w.x, orr)), ti = fma2c(w.y, orr, mul2c(w.x, oi));
-                    pw[k] = mag(add2(er, tr), add2(ei, ti));
-                    pw[Nf - k] = mag(sub2(er, tr), sub2(ei, ti));
-                }
+                if (k <= cnt) bins2(k, ldp(src, k), ldp(src, Nf - k));
             }
-            if (lane == 0) {   // DC and Nyquist: X[0] = Re Z[0] + Im Z[0], X[N/2] = Re Z[0] - Im Z[0]
-                const cpair z0 = ldp(src, 0);
-                const f2 x0 = add2(z0.re, z0.im), xn = sub2(z0.re, z0.im);
-                pw[0] = g.use_power ? mul2(x0, x0) : make_float2(fabsf(x0.x), fabsf(x0.y));
-                pw[nb] = g.use_power ? mul2(xn, xn) : make_float2(fabsf(xn.x), fabsf(xn.y));
-            }
+            if (lane == 0) bins_dc(ldp(src, 0));
         } else {
             for (int k = lane; k <= nb; k += 32) {
                 const cpair z = ldp(src, k);

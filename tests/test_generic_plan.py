@@ -239,3 +239,66 @@ def test_nemo_ragged_batch(m, torch, kw):
             assert d.max() <= LN_TOL_MAX and (d <= LN_TOL_BULK).mean() >= 0.995, (i, n, d.max())
         assert np.all(got[i][:, w:] == 0.0), (i, n)
     fe.close()
+
+
+@pytest.mark.parametrize("fft,hop,n_mels", [(480, 160, 80), (1024, 256, 128), (256, 64, 40), (450, 150, 64)])
+def test_pair_form_unaligned_and_odd_counts(m, torch, fft, hop, n_mels):
+    """The pair form of the general plan (melspec_generic2.cuh: two frames per warp) on inputs its fast paths must refuse: a PCM
+    pointer that is only 4-byte aligned (no 64-bit loads), odd and even frame counts (a last pair with one frame), both layouts."""
+    sr = 16000.0
+    h = m.CudaMelSpectrogram(fft, hop, sr, n_mels)
+    rng = np.random.default_rng(fft + 3)
+    for frames in (1, 2, 7, 32, 33):
+        n = fft + (frames - 1) * hop + 5
+        pcm = (rng.standard_normal((3, n + 1)) * 0.3).astype(np.float32)
+        base = torch.from_numpy(pcm).cuda()
+        for off in (0, 1):
+            flat = base.reshape(-1)[off:]                      # off = 1: every clip starts on an odd word
+            stride = n + 1
+            ns = n if off == 0 else n - 1                      # stay inside the allocation for the last clip
+            assert h.num_frames(ns) in (frames, frames - 1)
+            f = h.num_frames(ns)
+            if f == 0:
+                continue
+            for layout in (0, 1):
+                shape = (3, f, n_mels) if layout == 0 else (3, n_mels, f)
+                out = torch.full(shape, float("nan"), dtype=torch.float32, device="cuda")
+                h.compute_device(flat, 3, stride, ns, out, layout=layout)
+                torch.cuda.synchronize()
+                got = out.cpu().numpy()
+                if layout == 1:
+                    got = got.transpose(0, 2, 1)
+                for i in range(3):
+                    x = pcm.reshape(-1)[off + i * stride: off + i * stride + ns]
+                    want = o.whisper_mel_batch(x, fft, hop, n_mels, sr)
+                    assert want.shape == got[i].shape
+                    assert np.abs(got[i] - want).max() <= WHISPER_TOL, (frames, off, layout, i)
+    h.close()
+
+
+def test_pair_form_agrees_with_one_frame_kernel(m, jfk):
+    """Both forms of the general plan run the same Stockham schedule per frame; they differ in where the twiddles come from (table
+    entries vs products of table entries) and in the untangle step (two bins per step in the pair form), so their outputs agree to
+    within twice the distance either keeps from the f64 oracle.  The one-frame
+    kernel is selected in a child process (MELSPEC_GENERIC_PAIR is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import mel_spec_b200 as ms; x = np.load(sys.argv[1]);"
+            "h = ms.CudaMelSpectrogram(480, 160, 16000.0, 80); np.save(sys.argv[2], h.compute_mel_spectrogram(x));"
+            "k = ms.Fbank(ms.FbankConfig(sample_rate=8000.0, num_mel_bins=40)); np.save(sys.argv[3], k.compute(x))") % root
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        xin = os.path.join(td, "x.npy")
+        np.save(xin, jfk[:48000])
+        outs = {}
+        for mode in ("0", "1"):
+            a, b = os.path.join(td, f"w{mode}.npy"), os.path.join(td, f"k{mode}.npy")
+            r = subprocess.run([sys.executable, "-c", code, xin, a, b], env=dict(os.environ, MELSPEC_GENERIC_PAIR=mode), cwd=root,
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[mode] = (np.load(a), np.load(b))
+    assert outs["0"][0].shape == outs["1"][0].shape and outs["0"][1].shape == outs["1"][1].shape
+    assert np.abs(outs["0"][0] - outs["1"][0]).max() <= 6e-5   # two fp32 schedules, each within ~3e-5 of the f64 oracle
+    _ln_check(outs["0"][1], outs["1"][1])
