@@ -478,6 +478,51 @@ def measure_stream(torch, ms):
     return res
 
 
+def measure_next_rows(torch, ms, local_rank, steps=10):
+    """Device-resident timing of the frontends and sizes beside the headline configuration (SURVEY 8f rows and the general plan),
+    same clips as cfg2 (1024 x 10 s), CUDA events on the launch stream: ms per launch, frames/s, fraction of the HBM roofline."""
+    dev = torch.device("cuda", local_rank)
+    clips, n = 1024, 160000
+    x = synth_batch_torch(torch, clips, n, dev, 0)
+    st = torch.cuda.Stream(device=dev)
+    peak, kind = measured_peak_gbs()
+    rows = [
+        ("plan 512: Whisper fft 512 hop 160 80 mel (golden-file configuration)", lambda: ms.CudaMelSpectrogram(512, 160, 16000.0, 80, device=local_rank), 80),
+        ("plan 400: Whisper large-v3 style, fft 400 hop 160 128 mel", lambda: ms.CudaMelSpectrogram(400, 160, 16000.0, 128, device=local_rank), 128),
+        ("plan 512: NeMo BatchLogMel 128 mel, pre-emphasis, per-feature normalisation",
+         lambda: ms.BatchLogMelSpectrogram(ms.BatchLogMelConfig(n_mels=128, preemphasis=0.97, normalize_per_feature=True), device=local_rank), 128),
+        ("general plan: Whisper fft 1024 hop 256 128 mel", lambda: ms.CudaMelSpectrogram(1024, 256, 16000.0, 128, device=local_rank), 128),
+        ("general plan: Whisper fft 480 hop 160 80 mel", lambda: ms.CudaMelSpectrogram(480, 160, 16000.0, 80, device=local_rank), 80),
+        ("general plan: Kaldi fbank 8 kHz (fft 256, shift 80) 40 bins + CMN", lambda: ms.Fbank(ms.FbankConfig(sample_rate=8000.0, num_mel_bins=40), device=local_rank), 40),
+    ]
+    out_rows = []
+    for name, mk, nm in rows:
+        h = mk()
+        F = h.num_frames(n)
+        nemo = hasattr(h, "padded_frames")
+        cols = h.padded_frames(n) if nemo else F
+        o = torch.empty((clips, nm, cols) if nemo else (clips, F, nm), dtype=torch.float32, device=dev)
+        lay = ms.LAYOUT_MEL_MAJOR if nemo else ms.LAYOUT_FRAME_MAJOR
+        for _ in range(3):
+            h.compute_device(x, clips, n, n, o, layout=lay, stream=st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(st)
+            for _ in range(steps):
+                h.compute_device(x, clips, n, n, o, layout=lay, stream=st)
+            e1.record(st)
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / steps
+        algo = clips * (4 * n + 4 * nm * cols)
+        out_rows.append({"row": name + ", 1024 x 10 s", "ms_per_step": t, "value": clips * F / (t * 1e-3), "unit": "frames/s",
+                         "frames_per_clip": F, "roofline_frac": algo / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": algo,
+                         "peak_source": kind})
+        h.close()
+        del o
+    return out_rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -542,6 +587,7 @@ def main():
                 if "e2e_int16_pcm" in r:
                     extra[wl]["e2e_int16_pcm"] = r["e2e_int16_pcm"]
             extra["cfg5_stream"] = measure_stream(torch, ms)
+            extra["next_rows"] = measure_next_rows(torch, ms, local_rank)
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args.workload)

@@ -1149,14 +1149,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     __syncthreads();
 
     const int need = (FPW - 1) * 160 + p.frame_len;
+    // A/B switches (measured on B200, profiles/r2_ab_ksched512.txt): window starts and mel indices in registers: 1 - 2 % faster in
+    // every mode; prescale table touched only in passes that scale something: another 1 % for Whisper-512, nothing (registers) for
+    // the Kaldi and NeMo modes
 #ifndef MS512_META_REGS
-#define MS512_META_REGS 0
+#define MS512_META_REGS 1
 #endif
 #ifndef MS512_RESC
-#define MS512_RESC 0
+#define MS512_RESC 1
 #endif
     constexpr bool META_REGS = MS512_META_REGS && KSCHED != 0;   // window start | mel << 16 per slot, kept in registers
-    constexpr bool RESC = MS512_RESC && KSCHED != 0;             // prescale table written / read only in passes that scale something
+    constexpr bool RESC = MS512_RESC && KSCHED != 0 && MODE == 0;   // prescale table written / read only in passes that scale something
     int meta_r[MPL];
     if (META_REGS) {
 #pragma unroll

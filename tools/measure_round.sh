@@ -11,6 +11,9 @@ timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench.err                  
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference.json 2>> $O/bench.err
 timeout 600 python tools/bench_next_rows.py > $O/next_rows.jsonl 2>> $O/bench.err
 timeout 300 python tools/bench512.py > $O/bench512.txt 2>> $O/bench.err
+# general plan: pair form (default) against the one-frame kernel
+timeout 300 python tools/bench_generic.py > $O/bench_generic.txt 2>> $O/bench.err
+MELSPEC_GENERIC_PAIR=0 timeout 300 python tools/bench_generic.py >> $O/bench_generic.txt 2>> $O/bench.err
 # worst-case parity of the two-frames-per-transform packing: the new tests against this build and against the round-1 build
 timeout 300 python -m pytest tests/test_onset_parity.py -m gpu -q -s 2>&1 | grep -E "worst|passed|failed" > $O/onset_parity.txt
 if [ -f mel-spec_b200/lib/libmelspec_r1.so ]; then
@@ -28,8 +31,16 @@ done
 if [ "$1" = "full" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:melspec400 -c 1 -f -o $O/full400 python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/f400.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:melspec512 -c 1 -f -o $O/full512 python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/f512.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:generic_pair -s 2 -c 1 -f -o $O/fullgen1024 python tools/prof_generic.py 1024 256 128 > $O/fgen1024.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:generic_pair -s 2 -c 1 -f -o $O/fullgen480 python tools/prof_generic.py 480 160 80 > $O/fgen480.log 2>&1
+# digests of the general-plan captures are made here; their .ncu-rep files stay on the box (gpurun_out/ is capped at 64 MiB)
+for G in 1024 480; do
+  P=$(( G == 1024 ? 318464 : 510976 ))   # frame pairs per launch
+  { python tools/ncu_summary.py $O/fullgen$G.ncu-rep; python tools/ncu_smem.py $O/fullgen$G.ncu-rep $P | tail -12; python tools/ncu_ophist.py $O/fullgen$G.ncu-rep $P; } > $O/ncu_full_generic_pair_fft$G.txt 2>&1
+  rm -f $O/fullgen$G.ncu-rep
+done
 for T in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $T python -m pytest tests/test_gpu_parity.py tests/test_onset_parity.py tests/test_boundary_r2.py -m gpu -x -q -k "synthetic_batch or ragged_lengths or kaldi_fused or kaldi_batch or nemo_features or click_and_silence or int16_host or spectrogram_add_reference" > $O/san_$T.log 2>&1
+  timeout 900 compute-sanitizer --tool $T python -m pytest tests/test_gpu_parity.py tests/test_onset_parity.py tests/test_boundary_r2.py -m gpu -x -q tests/test_generic_plan.py -k "synthetic_batch or ragged_lengths or kaldi_fused or kaldi_batch or nemo_features or click_and_silence or int16_host or spectrogram_add_reference or pair_form_unaligned or generic_batch_layouts or nemo_ragged" > $O/san_$T.log 2>&1
 done
 fi
 cut -c1-300 $O/bench_n1.json
