@@ -332,6 +332,7 @@ def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps
     del scratch
     # opt-in 16-bit PCM entry: half the H2D bytes, converted in the kernel's prologue (bit-identical to f32 input of the same samples)
     e2e_i16 = None
+    e2e_tga = None
     if frontend == "whisper" and hasattr(ms.lib(), "melspec_compute_host_i16"):
         hx16 = torch.empty((clips, n_samples), dtype=torch.int16, pin_memory=True)
         hx16.copy_((x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
@@ -357,6 +358,34 @@ def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps
                    "h2d_bytes_per_step": clips * n_samples * 2, "d2h_bytes_per_step": clips * F * n_mels * 4,
                    "matches_f32_path_bit_exact": bool(torch.equal(hout16.to(dev), ref16)),
                    "entry": "melspec_compute_host_i16 (opt-in: int16 PCM, x/32768 in the kernel prologue)"}
+        # ... and the 8-bit TGA output variant (whisper.cpp's image format, src/quant.rs:38-64): int16 PCM in, one byte per mel value out
+        if hasattr(ms.lib(), "melspec_mel_tga_host_batch_i16"):
+            width = h.interleaved_width(n_samples)
+            tsz = int(ms.lib().melspec_tga_size(n_mels, width))
+            htga = torch.empty((clips, tsz), dtype=torch.uint8, pin_memory=True)
+            h.mel_tga_batch_raw(hx16.data_ptr(), clips, n_samples, n_samples, htga.data_ptr(), int16=True)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                h.mel_tga_batch_raw(hx16.data_ptr(), clips, n_samples, n_samples, htga.data_ptr(), int16=True)
+            tt = (time.perf_counter() - t0) / e2e_steps
+            ttt = torch.tensor([tt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ttt, op=dist.ReduceOp.MAX)
+            tt = float(ttt.item())
+            # the same bytes as quantising the device path's own frames of clip 0 (interleaved layout) with the device quantiser
+            img0 = torch.empty((n_mels, width), dtype=torch.float32, device=dev)
+            tga0 = torch.empty((tsz,), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            h.compute_interleaved_device(xf, 1, n_samples, n_samples, 0, img0, stream=stream)
+            h.quantize_tga_device(img0, 1, n_mels, width, tga0, stream=stream)
+            torch.cuda.synchronize()
+            e2e_tga = {"value": world * clips * F / tt, "unit": "frames/s", "ms_per_step": tt * 1e3,
+                       "h2d_bytes_per_step": clips * n_samples * 2, "d2h_bytes_per_step": clips * tsz,
+                       "clip0_equals_device_quantiser": bool(torch.equal(htga[0].to(dev), tga0)),
+                       "entry": "melspec_mel_tga_host_batch_i16 (opt-in: int16 PCM in, 8-bit TGA image per clip out)"}
+            del htga, img0, tga0
         del hx16, hout16, xf, ref16
         h.compute_device(x, clips, n_samples, n_samples, out, stream=stream)
         torch.cuda.synchronize()
@@ -386,6 +415,8 @@ def measure_workload(torch, dist, ms, name, args, rank, local_rank, world, steps
     }
     if e2e_i16 is not None:
         res["e2e_int16_pcm"] = e2e_i16
+        if e2e_tga is not None:
+            res["e2e_int16_pcm_tga_out"] = e2e_tga
     if clocks is not None:
         res["clocks"] = clocks
     if gather is not None:
@@ -571,7 +602,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": res["config"], "roofline": res["roofline"],
             "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res.get("clocks"),
         }
-        for k in ("e2e_int16_pcm", "gather"):
+        for k in ("e2e_int16_pcm", "e2e_int16_pcm_tga_out", "gather"):
             if k in res:
                 line[k] = res[k]
         if numa is not None:
@@ -584,8 +615,9 @@ def main():
                 r = measure_workload(torch, dist, ms, wl, args, 0, local_rank, 1, max(5, args.steps // 2), False)
                 extra[wl] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches", "steps")
                              if k in r}
-                if "e2e_int16_pcm" in r:
-                    extra[wl]["e2e_int16_pcm"] = r["e2e_int16_pcm"]
+                for k in ("e2e_int16_pcm", "e2e_int16_pcm_tga_out"):
+                    if k in r:
+                        extra[wl][k] = r[k]
             extra["cfg5_stream"] = measure_stream(torch, ms)
             extra["next_rows"] = measure_next_rows(torch, ms, local_rank)
             line["extra"] = extra

@@ -238,6 +238,15 @@ int32_t melspec_dequantize_tga_host(melspec_handle* h, const uint8_t* h_tga, int
  * h_img_opt (optional, n_mels*W floats) also returns the interleaved f32 image. */
 int32_t melspec_mel_tga_host(melspec_handle* h, const float* h_pcm, int64_t n_samples, int64_t min_width, uint8_t* h_tga,
                              int64_t capacity, int64_t* width_out, float* h_img_opt);
+/* The same for a batch of clips, pipelined like melspec_compute_host (H2D of chunk i+1, kernels of chunk i, D2H of chunk i-1
+ * overlap): clip i's TGA image (melspec_tga_size(n_mels, W) bytes, W = melspec_interleaved_width(frames, min_width), returned in
+ * *width_out) lands at h_tga + i * tga_stride (tga_stride 0 = images back to back).  One byte per mel value crosses PCIe on the way
+ * back instead of four; the _i16 form takes 16-bit PCM (x / 32768 on the device, like melspec_compute_host_i16).  Bytes equal
+ * tga_8bit_data (src/quant.rs:38-64) of interleave_frames (src/mel.rs:480-544) of the clip's own frames. */
+int32_t melspec_mel_tga_host_batch(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                                   int64_t min_width, uint8_t* h_tga, int64_t tga_stride, int64_t* width_out);
+int32_t melspec_mel_tga_host_batch_i16(melspec_handle* h, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                                       int64_t min_width, uint8_t* h_tga, int64_t tga_stride, int64_t* width_out);
 
 /*
  * ---- VAD over the mel image: the consumer directly downstream (reference src/vad.rs) ----

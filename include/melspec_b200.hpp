@@ -190,6 +190,25 @@ public:
         return img;
     }
 
+    // PCM batch -> one TGA image per clip (interleave_frames + tga_8bit_data of every clip's frames, pipelined on the device).
+    // `samples` holds n_clips rows of n_samples; returns n_clips * melspec_tga_size(n_mels, width) bytes, images back to back.
+    std::vector<uint8_t> mel_tga_batch(const std::vector<float>& samples, size_t n_clips, size_t n_samples, size_t min_width = 0,
+                                       size_t* width_out = nullptr) {
+        if (min_width % 2) throw std::invalid_argument("min_width must be even");          // src/mel.rs:488
+        if (samples.size() < n_clips * n_samples) throw std::invalid_argument("samples shorter than n_clips * n_samples");
+        const size_t f = num_frames(n_samples);
+        if (f == 0) throw std::invalid_argument("frames is empty");                         // src/mel.rs:487
+        const int64_t w = melspec_interleaved_width((int64_t)f, (int64_t)min_width);
+        const int64_t size = melspec_tga_size((int32_t)n_mels_, w);
+        if (size < 0) throw std::invalid_argument("width greater than TARGA max, use [`tga_8bit`]");
+        std::vector<uint8_t> bytes((size_t)size * n_clips);
+        int64_t wo = 0;
+        detail::check(melspec_mel_tga_host_batch(h_.get(), samples.data(), (int64_t)n_clips, (int64_t)n_samples, (int64_t)n_samples,
+                                                 (int64_t)min_width, bytes.data(), 0, &wo));
+        if (width_out) *width_out = (size_t)wo;
+        return bytes;
+    }
+
     // tga_8bit_data (src/quant.rs:38-64): row-major (n_mels, width) image -> TGA bytes
     std::vector<uint8_t> tga_8bit_data(const std::vector<float>& data, size_t n_mels) {
         if (n_mels == 0 || data.empty() || data.size() % n_mels) throw std::invalid_argument("data length must be a positive multiple of n_mels");

@@ -31,6 +31,7 @@ EXPORTS = [
     "melspec_dequantize_tga_device", "melspec_quantize_tga_host", "melspec_dequantize_tga_host", "melspec_mel_tga_host",
     "melspec_vad_default_settings", "melspec_vad_boundaries_device", "melspec_vad_activity_device", "melspec_vad_host",
     "melspec_stream_push_hop", "melspec_compute_host_i16", "melspec_convert_i16_device",
+    "melspec_mel_tga_host_batch", "melspec_mel_tga_host_batch_i16",
     "melspec_nccl_unique_id", "melspec_nccl_init", "melspec_gather_nccl", "melspec_nccl_destroy",
 ]
 
@@ -137,6 +138,9 @@ def lib() -> C.CDLL:
     L.melspec_dequantize_tga_host.argtypes = [vp, vp, i64, vp, i64]
     L.melspec_mel_tga_host.restype = i32
     L.melspec_mel_tga_host.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp]
+    for name in ("melspec_mel_tga_host_batch", "melspec_mel_tga_host_batch_i16"):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = [vp, vp, i64, i64, i64, i64, vp, i64, C.POINTER(i64)]
     vsp = C.POINTER(VadSettings)
     L.melspec_vad_default_settings.restype = i32
     L.melspec_vad_default_settings.argtypes = [vsp]

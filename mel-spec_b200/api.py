@@ -529,6 +529,37 @@ class CudaMelSpectrogram(_Handle):
                                             C.byref(wout), img.ctypes.data if img is not None else 0))
         return (out.tobytes(), img) if return_image else out.tobytes()
 
+    def mel_tga_batch_raw(self, h_pcm_ptr: int, n_clips: int, clip_stride: int, n_samples: int, h_tga_ptr: int, *, min_width: int = 0,
+                          tga_stride: int = 0, int16: bool = False) -> int:
+        """Pointer form of `melspec_mel_tga_host_batch[_i16]` (pinned buffers in bench.py); returns the image width."""
+        w = C.c_int64(0)
+        fn = self._L.melspec_mel_tga_host_batch_i16 if int16 else self._L.melspec_mel_tga_host_batch
+        _check(fn(self._h, int(h_pcm_ptr), int(n_clips), int(clip_stride), int(n_samples), int(min_width), int(h_tga_ptr),
+                  int(tga_stride), C.byref(w)))
+        return int(w.value)
+
+    def mel_tga_batch(self, samples, min_width: int = 0) -> list:
+        """A (n_clips, n_samples) batch of f32 or int16 PCM -> one 8-bit TGA image (bytes) per clip, pipelined on the device:
+        `tga_8bit_data(interleave_frames(frames, false, min_width))` of every clip (src/mel.rs:480-544, src/quant.rs:38-64)."""
+        x = np.asarray(samples)
+        i16 = x.dtype == np.int16
+        x = np.ascontiguousarray(x if i16 else x.astype(np.float32, copy=False))
+        if x.ndim != 2:
+            raise ValueError("samples must be (n_clips, n_samples)")
+        if min_width % 2:
+            raise ValueError("min_width must be even")                               # src/mel.rs:488
+        n_clips, n = x.shape
+        f = self.num_frames(n)
+        if f <= 0:
+            raise ValueError("frames is empty")                                      # src/mel.rs:487
+        w = int(self._L.melspec_interleaved_width(f, int(min_width)))
+        size = int(self._L.melspec_tga_size(self.n_mels, w))
+        if size < 0:
+            raise ValueError("width greater than TARGA max, use [`tga_8bit`]")
+        out = np.empty((n_clips, size), dtype=np.uint8)
+        self.mel_tga_batch_raw(x.ctypes.data, n_clips, n, n, out.ctypes.data, min_width=min_width, int16=i16)
+        return [out[i].tobytes() for i in range(n_clips)]
+
     def interleave_frames(self, samples, major_column_order: bool = False, min_width: int = 0) -> np.ndarray:
         """Mel frames of `samples` in the reference's interleave_frames layout (src/mel.rs:480-544), flat f32.
         Row-major (default, what whisper.cpp expects) comes straight from the kernel's mel-major store."""

@@ -207,6 +207,9 @@ struct melspec_handle {
     int16_t* d_slot_i16[3] = {nullptr, nullptr, nullptr};   // int16 staging of melspec_compute_host_i16
     size_t slot_pcm_cap = 0, slot_out_cap = 0, slot_i16_cap = 0;
     float2* d_partials = nullptr;   // min/max partials of the TGA quantiser
+    uint8_t* d_slot_tga[3] = {nullptr, nullptr, nullptr};   // melspec_mel_tga_host_batch: TGA bytes and min/max partials per pipeline slot
+    float2* d_slot_part[3] = {nullptr, nullptr, nullptr};
+    size_t slot_tga_cap = 0, slot_part_cap = 0;
     size_t partials_cap = 0;
     float* d_fmt_img = nullptr;     // staging of the host-buffer format entry points
     unsigned char* d_fmt_tga = nullptr;
@@ -591,6 +594,7 @@ int32_t build_tables(melspec_handle* h) {
             if (K[0] == 14 && K[1] == 4 && K[2] == 2 && !EX[0] && !EX[1] && !EX[2]) h->kspec = 1;
             if (K[0] == 8 && K[1] == 5 && K[2] == 2 && EX[0] && EX[1] && !EX[2]) h->kspec = 2;
         }
+        if (N == 400 && h->mpl == 4 && K[0] == 9 && K[1] == 4 && K[2] == 2 && K[3] == 1 && !EX[0] && !EX[1] && !EX[2] && !EX[3]) h->kspec = 4;
         h->ksched512 = 0;
         if (N == 512 && !EX[0] && !EX[1] && !EX[2] && !EX[3])
             for (int k = 1; k < 5; ++k)
@@ -927,8 +931,11 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
                     : launch_kernel(melspec400_kernel<NW, 4, false, 0>, p, grid, NW * 32, off, st)))
         // the launch shape of every large batch (frame-major, both TMA paths, no per-clip lengths) has its own instantiation with
         // those switches compiled in (KSPEC 3)
-        const bool fast = h->kspec == 1 && hop160 && nw == 12 && p.bulk_in && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR && !d_lens && p.normalize;
-        rc = fast ? launch_kernel(melspec400_kernel<12, 3, true, 3>, p, grid, 12 * 32, off, st)
+        const bool fshape = hop160 && nw == 12 && p.bulk_in && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR && !d_lens && p.normalize;
+        const bool fast = h->kspec == 1 && fshape;
+        static const bool k4 = [] { const char* e = std::getenv("MELSPEC_KSPEC4"); return !(e && e[0] == '0'); }();   // (0: A/B against the table-driven loop)
+        rc = h->kspec == 4 && fshape && k4 ? launch_kernel(melspec400_kernel<12, 4, true, 4>, p, grid, 12 * 32, off, st)
+             : fast ? launch_kernel(melspec400_kernel<12, 3, true, 3>, p, grid, 12 * 32, off, st)
              : nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
     } else {
@@ -1135,6 +1142,7 @@ void melspec_destroy(melspec_handle* h) {
     cudaFree(h->d_gweights_t);
     cudaFree(h->d_gstarts_t);
     cudaFree(h->d_partials);
+    for (int i = 0; i < 3; ++i) { cudaFree(h->d_slot_tga[i]); cudaFree(h->d_slot_part[i]); }
     cudaFree(h->d_fmt_img);
     cudaFree(h->d_fmt_tga);
     for (int i = 0; i < 3; ++i) {
@@ -1200,6 +1208,24 @@ int64_t melspec_tga_size(int32_t n_mels, int64_t width) {
     return (int64_t)melspec::kTgaHeader + (int64_t)n_mels * width;
 }
 
+namespace {
+int quantize_partials_per_image(int64_t n) { return (int)std::min<int64_t>(256, (n + 4095) / 4096); }
+// min/max partials + quantise, with the partials workspace given by the caller (one per stream that may be in flight)
+int32_t quantize_tga_launch(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels, int64_t width,
+                            uint8_t* d_tga, int64_t tga_stride, float2* d_partials, cudaStream_t st) {
+    const int64_t n = (int64_t)n_mels * width;
+    const int nblk = quantize_partials_per_image(n);
+    melspec::melspec_minmax_kernel<<<dim3(nblk, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, d_partials);
+    MS_CUDA(cudaGetLastError());
+    const int nblk2 = (int)std::min<int64_t>(1024, (n / 4 + 1023) / 1024 + 1);
+    melspec::melspec_quantize_kernel<<<dim3(nblk2, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, d_partials, nblk, d_tga, tga_stride,
+                                                                                  n_mels, (int)width);
+    MS_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return MELSPEC_OK;
+}
+}  // namespace
+
 int32_t melspec_quantize_tga_device(melspec_handle* h, const float* d_img, int64_t n_imgs, int64_t img_stride, int32_t n_mels,
                                     int64_t width, uint8_t* d_tga, int64_t tga_stride, void* stream) {
     if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
@@ -1215,21 +1241,13 @@ int32_t melspec_quantize_tga_device(melspec_handle* h, const float* d_img, int64
     if (n_imgs > 65535) return fail(MELSPEC_ERR_INVALID_ARG, "too many images for one call");
     MS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (int)std::min<int64_t>(256, (n + 4095) / 4096);
-    const size_t need = sizeof(float2) * (size_t)nblk * (size_t)n_imgs;
+    const size_t need = sizeof(float2) * (size_t)quantize_partials_per_image(n) * (size_t)n_imgs;
     if (need > h->partials_cap) {
         if (h->d_partials) { MS_CUDA(cudaStreamSynchronize(st)); cudaFree(h->d_partials); h->d_partials = nullptr; }
         MS_CUDA(cudaMalloc(&h->d_partials, need));
         h->partials_cap = need;
     }
-    melspec::melspec_minmax_kernel<<<dim3(nblk, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, h->d_partials);
-    MS_CUDA(cudaGetLastError());
-    const int nblk2 = (int)std::min<int64_t>(1024, (n / 4 + 1023) / 1024 + 1);
-    melspec::melspec_quantize_kernel<<<dim3(nblk2, (unsigned)n_imgs), 256, 0, st>>>(d_img, img_stride, n, h->d_partials, nblk, d_tga,
-                                                                                  tga_stride, n_mels, (int)width);
-    MS_CUDA(cudaGetLastError());
-    h->launches += 2;
-    return MELSPEC_OK;
+    return quantize_tga_launch(h, d_img, n_imgs, img_stride, n_mels, width, d_tga, tga_stride, h->d_partials, st);
 }
 
 int32_t melspec_dequantize_tga_device(melspec_handle* h, const uint8_t* d_tga, int64_t n_imgs, int64_t tga_stride, int32_t n_mels,
@@ -1657,6 +1675,80 @@ int32_t melspec_compute_host(melspec_handle* h, const float* h_pcm, int64_t n_cl
 int32_t melspec_compute_host_i16(melspec_handle* h, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
                                  float* h_out, int32_t layout, int64_t* frames_out) {
     return compute_host_impl(h, h_pcm, true, n_clips, clip_stride, n_samples, h_out, layout, frames_out);
+}
+
+namespace {
+// PCM -> Whisper mel -> interleave_frames image -> 8-bit TGA for a batch of clips, pipelined like compute_host_impl: the H2D copy of
+// chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.  The device -> host side carries one byte per mel value
+// instead of four.
+int32_t mel_tga_batch_impl(melspec_handle* h, const void* h_pcm, bool i16, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                           int64_t min_width, uint8_t* h_tga, int64_t tga_stride, int64_t* width_out) {
+    if (!h) return fail(MELSPEC_ERR_INVALID_ARG, "handle is null");
+    if (h->cfg.frontend != MELSPEC_FRONTEND_WHISPER) return fail(MELSPEC_ERR_UNSUPPORTED, "Whisper frontend only");
+    if (n_clips < 0 || n_samples < 0 || clip_stride < 0 || tga_stride < 0) return fail(MELSPEC_ERR_INVALID_ARG, "negative size");
+    if (min_width < 0 || (min_width & 1)) return fail(MELSPEC_ERR_INVALID_ARG, "min_width must be even");
+    const int64_t F = frames_for(h->cfg, n_samples);
+    if (F == 0) return fail(MELSPEC_ERR_INVALID_ARG, "frames is empty");
+    const int64_t W = melspec_interleaved_width(F, min_width);
+    if (width_out) *width_out = W;
+    const int64_t sz = melspec_tga_size(h->cfg.n_mels, W);
+    if (sz < 0) return fail(MELSPEC_ERR_INVALID_ARG, "width greater than TARGA max, use chunks (src/quant.rs:17-21)");
+    if (n_clips == 0) return MELSPEC_OK;
+    if (!h_pcm || !h_tga) return fail(MELSPEC_ERR_INVALID_ARG, "null host pointer");
+    if (n_clips > 1 && clip_stride < n_samples) return fail(MELSPEC_ERR_INVALID_ARG, "clip_stride < n_samples");
+    if (!tga_stride) tga_stride = sz;
+    if (tga_stride < sz) return fail(MELSPEC_ERR_INVALID_ARG, "tga_stride smaller than one image");
+    MS_CUDA(cudaSetDevice(h->device));
+    const int64_t ns4 = (n_samples + 7) / 8 * 8;
+    const int64_t img = (int64_t)h->cfg.n_mels * W;            // floats per interleaved image
+    const int64_t dsz = (sz + 15) / 16 * 16;                   // device stride between the TGA images of a chunk
+    int64_t per_chunk = std::max<int64_t>(1, ((int64_t)32 << 20) / (ns4 * 4));
+    per_chunk = std::min(per_chunk, n_clips);
+    if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
+    per_chunk = std::min<int64_t>(per_chunk, 65535);
+    const int64_t n_chunks = (n_clips + per_chunk - 1) / per_chunk;
+    int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * img * 4, i16 ? (size_t)per_chunk * ns4 * 2 : 0);
+    if (rc) return rc;
+    const size_t tga_need = (size_t)per_chunk * dsz, part_need = sizeof(float2) * (size_t)quantize_partials_per_image(img) * (size_t)per_chunk;
+    if (tga_need > h->slot_tga_cap || part_need > h->slot_part_cap) {
+        for (int i = 0; i < 3; ++i) {
+            if (h->d_slot_tga[i]) cudaFree(h->d_slot_tga[i]);
+            if (h->d_slot_part[i]) cudaFree(h->d_slot_part[i]);
+            h->d_slot_tga[i] = nullptr; h->d_slot_part[i] = nullptr;
+        }
+        h->slot_tga_cap = h->slot_part_cap = 0;
+        for (int i = 0; i < 3; ++i) {
+            MS_CUDA(cudaMalloc(&h->d_slot_tga[i], tga_need));
+            MS_CUDA(cudaMalloc(&h->d_slot_part[i], part_need));
+        }
+        h->slot_tga_cap = tga_need; h->slot_part_cap = part_need;
+    }
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += per_chunk, slot = (slot + 1) % 3) {
+        const int64_t nc = std::min(per_chunk, n_clips - c0);
+        cudaStream_t st = h->streams[slot];
+        rc = stage_rows(h, slot, h_pcm, i16, c0, nc, clip_stride, 0, n_samples, ns4, st);
+        if (rc) return rc;
+        rc = melspec_compute_interleaved_device(h, h->d_slot_pcm[slot], nc, ns4, n_samples, min_width, h->d_slot_out[slot], 0, st);
+        if (rc) return rc;
+        rc = quantize_tga_launch(h, h->d_slot_out[slot], nc, img, h->cfg.n_mels, W, h->d_slot_tga[slot], dsz, h->d_slot_part[slot], st);
+        if (rc) return rc;
+        MS_CUDA(cudaMemcpy2DAsync(h_tga + c0 * tga_stride, (size_t)tga_stride, h->d_slot_tga[slot], (size_t)dsz, (size_t)sz, (size_t)nc,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 3; ++i) MS_CUDA(cudaStreamSynchronize(h->streams[i]));
+    return MELSPEC_OK;
+}
+}  // namespace
+
+int32_t melspec_mel_tga_host_batch(melspec_handle* h, const float* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                                   int64_t min_width, uint8_t* h_tga, int64_t tga_stride, int64_t* width_out) {
+    return mel_tga_batch_impl(h, h_pcm, false, n_clips, clip_stride, n_samples, min_width, h_tga, tga_stride, width_out);
+}
+
+int32_t melspec_mel_tga_host_batch_i16(melspec_handle* h, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride, int64_t n_samples,
+                                       int64_t min_width, uint8_t* h_tga, int64_t tga_stride, int64_t* width_out) {
+    return mel_tga_batch_impl(h, h_pcm, true, n_clips, clip_stride, n_samples, min_width, h_tga, tga_stride, width_out);
 }
 
 int32_t melspec_convert_i16_device(melspec_handle* h, const int16_t* d_in, int64_t n_rows, int64_t in_stride, int64_t n_samples,

@@ -529,8 +529,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     extern __shared__ __align__(128) unsigned char smem[];
     // KSPEC 3 = KSPEC 1 for the launch shape every large batch has (frame-major output, aligned buffers so that both TMA paths
     // apply, no per-clip lengths): those run-time switches become compile-time constants
-    constexpr bool FAST = KSPEC == 3;
-    constexpr int KS_ = FAST ? 1 : KSPEC;
+    // KSPEC 4 = the same for the Slaney 128-mel bank (Whisper large-v3: 9, 4, 2 and 1 entries in its four slots)
+    constexpr bool FAST = KSPEC >= 3;
+    constexpr int KS_ = KSPEC == 3 ? 1 : KSPEC;
     const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_bulk_out = FAST ? true : (p.bulk_out != 0), f_norm = FAST ? true : (p.normalize != 0);
     const int f_layout = FAST ? 0 : p.layout;
     const int32_t* const f_lens = FAST ? nullptr : p.lens;
@@ -829,7 +830,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 #pragma unroll
         for (int q = 0; q < FPW; ++q) mx[q] = -3.0e38f;
         {
-            constexpr int KS[4] = {KS_ == 2 ? 8 : 14, KS_ == 2 ? 5 : 4, 2, 0};   // KS_ != 0: the Whisper 80-mel / fft-400 bank
+            constexpr int KS[4] = {KS_ == 4 ? 9 : KS_ == 2 ? 8 : 14, KS_ == 2 ? 5 : 4, 2, KS_ == 4 ? 1 : 0};   // KS_ != 0: the Whisper 80-mel (128-mel) / fft-400 bank
             constexpr bool EXS[4] = {KS_ == 2, KS_ == 2, false, false};         // slots whose split bands are summed by shuffle
             const float4* wq = reinterpret_cast<const float4*>(s_projw + p.proj_ktot * 32) + lane;   // [quad][lane] x 4 weights
             const float* wt = s_projw + lane;                                                          // [entry][lane]

@@ -113,6 +113,10 @@ unsafe extern "C" {
     pub fn melspec_tga_size(n_mels: i32, width: i64) -> i64;
     pub fn melspec_mel_tga_host(h: *mut MelspecHandle, h_pcm: *const f32, n_samples: i64, min_width: i64, h_tga: *mut u8, capacity: i64,
                                 width_out: *mut i64, h_img_opt: *mut f32) -> i32;
+    pub fn melspec_mel_tga_host_batch(h: *mut MelspecHandle, h_pcm: *const f32, n_clips: i64, clip_stride: i64, n_samples: i64, min_width: i64,
+                                      h_tga: *mut u8, tga_stride: i64, width_out: *mut i64) -> i32;
+    pub fn melspec_mel_tga_host_batch_i16(h: *mut MelspecHandle, h_pcm: *const i16, n_clips: i64, clip_stride: i64, n_samples: i64,
+                                          min_width: i64, h_tga: *mut u8, tga_stride: i64, width_out: *mut i64) -> i32;
     pub fn melspec_quantize_tga_host(h: *mut MelspecHandle, h_img: *const f32, n_mels: i32, width: i64, h_tga: *mut u8) -> i32;
     pub fn melspec_dequantize_tga_host(h: *mut MelspecHandle, h_tga: *const u8, tga_bytes: i64, h_img: *mut f32, capacity: i64) -> i32;
     // VAD over the mel image (src/vad.rs:251-338, 163-207)

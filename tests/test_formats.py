@@ -179,3 +179,39 @@ def test_tga_8bit_chunks_wide_images_like_the_reference(mel400, tmp_path):
     mel400.save_tga_8bit(img[:, :2000].reshape(-1), n_mels, str(tmp_path / "y.tga"))
     back = mel400.load_tga_8bit(str(tmp_path / "y.tga"))
     assert back.shape == (n_mels * 2000,) and np.abs(back - img[:, :2000].reshape(-1)).max() <= (img[:, :2000].max() - img[:, :2000].min()) / 255.0
+
+
+@pytest.mark.gpu
+def test_gpu_mel_tga_batch_equals_single_clip_calls(mel400, jfk):
+    """`melspec_mel_tga_host_batch` (pipelined PCM -> mel -> interleave -> 8-bit TGA for a batch; one byte per mel value crosses
+    PCIe on the way back) gives every clip exactly the bytes of the single-clip call, for f32 and int16 PCM, even and padded widths
+    and a strided output; the single-clip call is pinned on the reference's quantized_mel_golden.tga above."""
+    n = 16000 * 3 + 160                                               # 299 frames: odd, so min_width > 0 adds the zero frame
+    clips = np.stack([jfk[i * 7000: i * 7000 + n] * s for i, s in enumerate((1.0, 0.3, 1e-3, 0.0, 2.5))]).astype(np.float32)
+    clips[3, 100] = 1e-4                                              # a single tick in an otherwise silent clip
+    for min_width in (0, 300, 400):
+        got = mel400.mel_tga_batch(clips, min_width=min_width)
+        for i in range(clips.shape[0]):
+            assert got[i] == mel400.mel_tga(clips[i], min_width=min_width), (min_width, i)
+    # int16 PCM: identical to the f32 call on x / 32768
+    x16 = np.clip(np.round(clips * 20000.0), -32768, 32767).astype(np.int16)
+    got16 = mel400.mel_tga_batch(x16)
+    for i in range(clips.shape[0]):
+        assert got16[i] == mel400.mel_tga(x16[i].astype(np.float32) / 32768.0), i
+    # strided output rows + many clips (several pipeline chunks)
+    many = np.ascontiguousarray(np.tile(clips, (40, 1)))              # 200 clips
+    w = mel400.interleaved_width(n)
+    size = int(mel400._L.melspec_tga_size(mel400.n_mels, w))
+    stride = size + 37
+    buf = np.full((many.shape[0], stride), 0xAB, dtype=np.uint8)
+    wout = mel400.mel_tga_batch_raw(many.ctypes.data, many.shape[0], n, n, buf.ctypes.data, tga_stride=stride)
+    assert wout == w
+    single = mel400.mel_tga_batch(clips)
+    for i in range(many.shape[0]):
+        assert buf[i, :size].tobytes() == single[i % 5], i
+        assert np.all(buf[i, size:] == 0xAB), "bytes between the images stay untouched"
+    # errors: odd min_width, empty frames, width beyond the TGA header's u16
+    with pytest.raises(ValueError):
+        mel400.mel_tga_batch(clips, min_width=3)
+    with pytest.raises(ValueError):
+        mel400.mel_tga_batch(clips[:, :100])
