@@ -776,7 +776,8 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
             return launch_post_kernels(h, p, n_clips, d_lens, d_out, false, st);
         }
     }
-    const size_t budget = 220 * 1024, per_warp = (size_t)16 * generic_buf_elems(g.Nf), tw_bytes = (size_t)8 * c.fft;
+    const size_t budget = 220 * 1024, per_warp = (size_t)16 * generic_buf_elems(g.Nf),
+                 tw_bytes = (size_t)8 * c.fft + (size_t)4 * ((g.n_weights_t + 1) & ~1);   // twiddles + the transposed band weights
     // warps per CTA: the count that puts the most warps on an SM (the kernel is latency bound: every FFT stage is a
     // round trip through shared memory), given one twiddle table per CTA, 227 KB of shared memory and 64 K registers per SM
     cudaFuncAttributes fa;

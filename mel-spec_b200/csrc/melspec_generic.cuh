@@ -119,17 +119,24 @@ __device__ __forceinline__ void gdft_small(const float2 (&a)[R], float2 (&y)[R])
     }
 }
 
-__global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, const GParams g) {
+__global__ void __launch_bounds__(512, 2) melspec_generic_kernel(const KParams p, const GParams g) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int N = g.N, Nf = g.Nf, tmul = N / Nf;   // W_Nf^k = W_N^(tmul k)
     const bool packed = Nf != N;
     const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* s_tw = reinterpret_cast<float2*>(gsm);
     const int nfp = generic_buf_elems(Nf);
-    float2* buf0 = s_tw + N + (size_t)warp * 2 * nfp;
+    // [twiddles | transposed band weights (round 2, when they fit: n_weights_t > 0) | per-warp ping-pong buffers]
+    float* s_wts = reinterpret_cast<float*>(s_tw + N);
+    const int wt_floats = (g.n_weights_t + 1) & ~1;
+    float2* buf0 = s_tw + N + wt_floats / 2 + (size_t)warp * 2 * nfp;
     float2* buf1 = buf0 + nfp;
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_tw[i] = g.tw[i];
+    for (int i = threadIdx.x; i < g.n_weights_t; i += blockDim.x) s_wts[i] = g.weights_t[i];
     __syncthreads();
+    const bool wsm = g.n_weights_t > 0;   // projection from the shared-memory table (warp-uniform trip counts, conflict-free reads)
+    int kpad = 0;
+    for (int sl = 0; sl < kMaxMpl; ++sl) kpad = max(kpad, g.kmax[sl]);
 
     const int L = p.frame_len;
     const float inv_len = 1.0f / (float)L;
@@ -293,28 +300,36 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
 
         // ------------------------------------------------------------------ power (or magnitude) of bins 0..N/2 -> pw[k]
         float* pw = reinterpret_cast<float*>(dst);
-        // bins 0 .. N/2 - 1 (k = lane + 32 i); the Nyquist bin of an even N, X[N/2] = Re Z[0] - Im Z[0], is written by lane 0
-        for (int k = lane; k < (packed ? nb : nb + 1); k += 32) {
-            float xr, xi;
-            if (packed) {   // X[k] = E[k] + W_N^k O[k]
-                const float2 zk = src[gph(k)], zm = src[gph(k == 0 ? 0 : Nf - k)];
+        if (packed) {
+            // X[k] = E[k] + W_N^k O[k] and X[Nf - k] = conj(E[k] - W_N^k O[k]) share Z[k], Z[Nf - k] and the twiddle: one lane forms
+            // both bins (k = 1 .. Nf/2; k = Nf/2 pairs with itself and is written twice); DC and Nyquist come from Z[0]
+            for (int k = 1 + lane; k <= Nf / 2; k += 32) {
+                const float2 zk = src[gph(k)], zm = src[gph(Nf - k)];
                 const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
                 const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
                 const float2 w = s_tw[k];
-                xr = er + (orr * w.x - oi * w.y);
-                xi = ei + fmaf(orr, w.y, oi * w.x);
-            } else {
-                xr = src[gph(k)].x; xi = src[gph(k)].y;
+                const float tr = orr * w.x - oi * w.y, ti = fmaf(orr, w.y, oi * w.x);
+                const float ar = er + tr, ai = ei + ti, br = er - tr, bi = ei - ti;
+                float ea = fmaf(ar, ar, ai * ai), eb = fmaf(br, br, bi * bi);
+                if (!g.use_power) { ea = sqrtf(ea); eb = sqrtf(eb); }   // src/fbank.rs:197-203
+                pw[k] = ea;
+                pw[Nf - k] = eb;
             }
-            float e = fmaf(xr, xr, xi * xi);
-            if (!g.use_power) e = sqrtf(e);   // src/fbank.rs:197-203
-            pw[k] = e;
+            if (lane == 0) {
+                const float2 z0 = src[0];
+                const float x0 = z0.x + z0.y, xn = z0.x - z0.y;
+                pw[0] = g.use_power ? x0 * x0 : fabsf(x0);
+                pw[nb] = g.use_power ? xn * xn : fabsf(xn);
+            }
+        } else {
+            for (int k = lane; k <= nb; k += 32) {
+                const float2 z = src[gph(k)];
+                float e = fmaf(z.x, z.x, z.y * z.y);
+                if (!g.use_power) e = sqrtf(e);
+                pw[k] = e;
+            }
         }
-        if (packed && lane == 0) {
-            const float2 z0 = src[0];
-            const float xn = z0.x - z0.y;
-            pw[nb] = g.use_power ? xn * xn : fabsf(xn);
-        }
+        if (wsm) for (int i = lane; i < kpad; i += 32) pw[nb + 1 + i] = 0.f;   // rows a padded (zero-weight) entry may touch
         __syncwarp();
 
         // ------------------------------------------------------------------ banded projection + log + stores
@@ -325,9 +340,19 @@ __global__ void __launch_bounds__(512) melspec_generic_kernel(const KParams p, c
             const int mrow = lane + 32 * sl;
             v[sl] = -INFINITY;
             if (mrow < p.n_mels) {
-                const int b0 = __ldg(g.bands + 3 * mrow), cnt = __ldg(g.bands + 3 * mrow + 1), wo = __ldg(g.bands + 3 * mrow + 2);
                 float e = 0.f;
-                for (int i = 0; i < cnt; ++i) e = fmaf(__ldg(g.weights + wo + i), pw[b0 + i], e);
+                if (wsm) {   // (the branch is warp-uniform; lanes past n_mels skip the slot)
+                    int kb = 0;
+                    for (int q = 0; q < sl; ++q) kb += g.kmax[q];
+                    const float* wp = s_wts + 32 * kb + lane;
+                    const float* pp = pw + __ldg(g.starts_t + mrow);
+                    const int K = g.kmax[sl];
+#pragma unroll 4
+                    for (int i = 0; i < K; ++i) e = fmaf(wp[32 * i], pp[i], e);
+                } else {
+                    const int b0 = __ldg(g.bands + 3 * mrow), cnt = __ldg(g.bands + 3 * mrow + 1), wo = __ldg(g.bands + 3 * mrow + 2);
+                    for (int i = 0; i < cnt; ++i) e = fmaf(__ldg(g.weights + wo + i), pw[b0 + i], e);
+                }
                 if (g.mode == 2) e = logf(e + p.log_add);                    // ln(E + guard), src/mel.rs:365-368
                 else if (g.mode == 1) {                                      // max(E, floor), optional ln, src/fbank.rs:207-221
                     e = fmaxf(e, p.floor_val);
