@@ -764,9 +764,12 @@ int32_t launch_generic(melspec_handle* h, melspec::KParams& p, int64_t n_clips, 
     p.n_clips = (int)n_clips;
     // warps per CTA: as many as fit beside the twiddle table (8 N bytes) at 16 Nf bytes each, at most 8
     g.vec2 = ((uintptr_t)p.pcm % 8 == 0) && (p.clip_stride % 2 == 0) && (c.hop % 2 == 0) && (p.frame_offset % 2 == 0) && (c.fft % 2 == 0);
-    if (c.frontend == MELSPEC_FRONTEND_NEMO && row_stride > p.frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
-        MS_CUDA(cudaMemset2DAsync(d_out + p.frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - p.frames_per_clip) * 4,
-                                  (size_t)n_clips * c.n_mels, st));   // pad_to columns are zeros (src/mel.rs:336)
+    if (c.frontend == MELSPEC_FRONTEND_NEMO && row_stride > p.frames_per_clip && p.out_clip_stride == row_stride * c.n_mels) {
+        const long long total = (long long)n_clips * c.n_mels * (row_stride - p.frames_per_clip);   // pad_to columns are zeros (src/mel.rs:336)
+        melspec_zero_cols_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8), 256, 0, st>>>(
+            d_out, p.out_clip_stride, c.n_mels, row_stride, p.frames_per_clip, (int)row_stride, n_clips);
+        MS_CUDA(cudaGetLastError());
+    }
     {
         bool launched = false;
         const int32_t rc = launch_generic_pair(h, p, g, n_clips, st, &launched);
@@ -918,6 +921,10 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     if (fused_cmn && cmn_fuse_mode == 2 && !p.bulk_out) p.cmn_fused = 1;   // (bulk reductions need the bulk-store alignment)
     off += (size_t)p.smem_warp_stride * nw;
     if (off > 227 * 1024) return fail(MELSPEC_ERR_UNSUPPORTED, "hop_size too large for the shared-memory tile of this build");
+    {   // MELSPEC_TILE_ORDER=0|1 overrides (A/B); default: interleaved warps for the mel-major layouts of plan 400
+        static const int forced = [] { const char* e = std::getenv("MELSPEC_TILE_ORDER"); return e ? std::atoi(e) : -1; }();
+        p.tile_order = forced >= 0 ? forced : (h->plan == 400 && layout == MELSPEC_LAYOUT_MEL_MAJOR ? 1 : 0);
+    }
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;
     const int grid = fused_cmn ? h->num_sms : (int)std::min<int64_t>(n_tiles, h->num_sms);
     int32_t rc;
@@ -935,7 +942,12 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         const bool fshape = hop160 && nw == 12 && p.bulk_in && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR && !d_lens && p.normalize;
         const bool fast = h->kspec == 1 && fshape;
         static const bool k4 = [] { const char* e = std::getenv("MELSPEC_KSPEC4"); return !(e && e[0] == '0'); }();   // (0: A/B against the table-driven loop)
-        rc = h->kspec == 4 && fshape && k4 ? launch_kernel(melspec400_kernel<12, 4, true, 4>, p, grid, 12 * 32, off, st)
+        // ... and the mel-major layout of the 80-mel bank (interleave_frames / whisper.cpp images; MELSPEC_KSPEC5=0: A/B)
+        static const bool k5 = [] { const char* e = std::getenv("MELSPEC_KSPEC5"); return !(e && e[0] == '0'); }();
+        const bool fmm = k5 && h->kspec == 1 && c.n_mels == 80 && hop160 && nw == 12 && p.bulk_in && layout == MELSPEC_LAYOUT_MEL_MAJOR && p.mm_aligned8 &&
+                         !d_lens && p.normalize && row_stride * 80 < ((int64_t)1 << 31);
+        rc = fmm ? launch_kernel(melspec400_kernel<12, 3, true, 5>, p, grid, 12 * 32, off, st)
+             : h->kspec == 4 && fshape && k4 ? launch_kernel(melspec400_kernel<12, 4, true, 4>, p, grid, 12 * 32, off, st)
              : fast ? launch_kernel(melspec400_kernel<12, 3, true, 3>, p, grid, 12 * 32, off, st)
              : nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);
 #undef MS_DISPATCH
@@ -955,9 +967,12 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         const int ks = ksched_on ? h->ksched512 : 0;
         if (nemo) {
             // padding columns (pad_to) are zeros in the reference's feature matrix (src/mel.rs:336)
-            if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels)
-                MS_CUDA(cudaMemset2DAsync(d_out + frames_per_clip, (size_t)row_stride * 4, 0, (size_t)(row_stride - frames_per_clip) * 4,
-                                          (size_t)n_clips * c.n_mels, st));
+            if (row_stride > frames_per_clip && p.out_clip_stride == row_stride * c.n_mels) {
+                const long long total = (long long)n_clips * c.n_mels * (row_stride - frames_per_clip);
+                melspec_zero_cols_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8), 256, 0, st>>>(
+                    d_out, p.out_clip_stride, c.n_mels, row_stride, (int)frames_per_clip, (int)row_stride, n_clips);
+                MS_CUDA(cudaGetLastError());
+            }
             if (d_lens) rc = nw == 8 ? MS_DISPATCH(8, 3) : MS_DISPATCH(12, 3);   // ragged batch (per-clip lengths)
             else if (fast && ks == 3) rc = launch_kernel(melspec512_kernel<12, 3, 2, true, 3>, p, grid, 12 * 32, off, st);
             else if (fast && ks == 4) rc = launch_kernel(melspec512_kernel<12, 4, 2, true, 4>, p, grid, 12 * 32, off, st);
@@ -1195,11 +1210,11 @@ int32_t melspec_compute_interleaved_device(melspec_handle* h, const float* d_pcm
     MS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (W > F) {   // the zero frame / zero padding block of src/mel.rs:497-516
-        if (ocs == W * h->cfg.n_mels)
-            MS_CUDA(cudaMemset2DAsync(d_out + F, (size_t)W * 4, 0, (size_t)(W - F) * 4, (size_t)n_clips * h->cfg.n_mels, st));
-        else
-            for (int64_t c = 0; c < n_clips; ++c)
-                MS_CUDA(cudaMemset2DAsync(d_out + c * ocs + F, (size_t)W * 4, 0, (size_t)(W - F) * 4, (size_t)h->cfg.n_mels, st));
+        const long long total = (long long)n_clips * h->cfg.n_mels * (W - F);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
+        melspec::melspec_zero_cols_kernel<<<blocks, 256, 0, st>>>(d_out, ocs, h->cfg.n_mels, W, (int)F, (int)W, n_clips);
+        MS_CUDA(cudaGetLastError());
+        h->launches += 1;
     }
     return launch_device(h, d_pcm, n_clips, clip_stride, n_samples, F, nullptr, d_out, ocs, MELSPEC_LAYOUT_MEL_MAJOR, st, W);
 }

@@ -72,6 +72,7 @@ struct KParams {
     int vec_out;             // frame-major output rows are 16-byte aligned (float4 stores when TMA stores are not used)
     int n_clips;
     int smem_cmn;            // [NWARPS][128] column sums + [128] means (floats)
+    int tile_order;          // plan 400: 0 = every warp owns a contiguous range of tiles, 1 = the CTA does and its warps interleave
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off, smem_scr_off;
 };
@@ -530,10 +531,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     // KSPEC 3 = KSPEC 1 for the launch shape every large batch has (frame-major output, aligned buffers so that both TMA paths
     // apply, no per-clip lengths): those run-time switches become compile-time constants
     // KSPEC 4 = the same for the Slaney 128-mel bank (Whisper large-v3: 9, 4, 2 and 1 entries in its four slots)
-    constexpr bool FAST = KSPEC >= 3;
-    constexpr int KS_ = KSPEC == 3 ? 1 : KSPEC;
-    const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_bulk_out = FAST ? true : (p.bulk_out != 0), f_norm = FAST ? true : (p.normalize != 0);
-    const int f_layout = FAST ? 0 : p.layout;
+    // KSPEC 5 = KSPEC 3 with the mel-major (`interleave_frames`, whisper.cpp) output layout instead: 8-byte aligned rows, full tiles
+    // stored from a per-lane offset table (ragged tiles take the generic path below)
+    constexpr bool FAST = KSPEC >= 3, FASTMM = KSPEC == 5;
+    constexpr int KS_ = (KSPEC == 3 || KSPEC == 5) ? 1 : KSPEC;
+    const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_bulk_out = FAST ? !FASTMM : (p.bulk_out != 0), f_norm = FAST ? true : (p.normalize != 0);
+    const int f_layout = FAST ? (FASTMM ? 1 : 0) : p.layout;
     const int32_t* const f_lens = FAST ? nullptr : p.lens;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the tile-loop state lives in uniform registers
@@ -599,6 +602,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     }
     for (int i = threadIdx.x; i < 30; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i % 10];
     const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + l30;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
+    // KSPEC 5: where float2 i of a staged [80 mels][3 x float2] tile goes, relative to the tile's first output column:
+    // (i / 3) * row stride + 2 (i % 3) floats; i = lane + 32 k, one table row per k (behind the window factors: 480 bytes are in use there)
+    int* const s_mmoff = reinterpret_cast<int*>(smem + p.smem_win + 512);
+    if (FASTMM)
+        for (int i = threadIdx.x; i < 240; i += NWARPS * 32) s_mmoff[i] = (i / 3) * p.out_row_stride + 2 * (i % 3);
     __syncthreads();
 
     const int hop = HOP160 ? 160 : p.hop;
@@ -639,12 +647,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
     // every warp owns a contiguous range of warp tiles (no division in the loop, neighbouring tiles share their
     // 240-sample halo through L2)
+    // Mel-major output (tile_order 1): the CTA owns a contiguous range and its warps take neighbouring tiles (warp, warp + NWARPS, ...).
+    // A mel row then receives the 24-byte pieces of up to twelve neighbouring tiles at about the same time, so its L2 lines fill
+    // up and leave quickly; with per-warp ranges the partially written lines of all 1 776 warps sit in L2 for five passes each,
+    // which pushed the PCM halo out of L2 (measured: DRAM 657 -> 802 MB read, 300 -> 406 MB written per cfg2 launch).
+    const bool interleaved_tiles = (FAST && !FASTMM) ? false : (p.tile_order != 0);
+    const int tstep = interleaved_tiles ? NWARPS : 1;
     int clip, tin, cnt;
-    {
+    if (!interleaved_tiles) {
         const int nwt = gridDim.x * NWARPS, gw = blockIdx.x * NWARPS + warp;
         const int base = p.n_wtiles / nwt, rem = p.n_wtiles - base * nwt;
         const int lo = gw * base + min(gw, rem);
         cnt = base + (gw < rem ? 1 : 0);
+        clip = lo / p.wtiles_per_clip;
+        tin = lo - clip * p.wtiles_per_clip;
+    } else {
+        const int nct = gridDim.x, b = blockIdx.x;
+        const int base = p.n_wtiles / nct, rem = p.n_wtiles - base * nct;
+        const int lo = b * base + min(b, rem) + warp, cntb = base + (b < rem ? 1 : 0);
+        cnt = cntb > warp ? (cntb - warp + NWARPS - 1) / NWARPS : 0;
         clip = lo / p.wtiles_per_clip;
         tin = lo - clip * p.wtiles_per_clip;
     }
@@ -694,7 +715,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         __syncwarp();   // every lane has read its samples (HOP160: the loads are ordered before the refill below; their values are
                         // consumed after it, which keeps only the 56 sample registers live across the TMA issue)
         const int cur_clip = clip;
-        if (++tin == p.wtiles_per_clip) { tin = 0; ++clip; }
+        tin += tstep;
+        while (tin >= p.wtiles_per_clip) { tin -= p.wtiles_per_clip; ++clip; }   // (warp-uniform)
         // 12-warp build: the refill goes out now.  16-warp build (LATE_LOAD): the PCM stage shares its first 3.7 KB with the tail
         // of the exchange slab, which is live until the row loads of step 3 are done, so the refill goes out after those.
         if ((!LATE_LOAD || nvalid == 0) && it + 1 < cnt) issue_load(clip, tin);
@@ -949,6 +971,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             }
             __syncwarp();
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
+            if (FASTMM) {   // 80 mels, aligned rows: 240 float2, offsets from the table (7 full rounds + 16 lanes)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < 7 || lane < 16) *reinterpret_cast<float2*>(dst + s_mmoff[lane + 32 * k]) = st2[lane + 32 * k];
+            } else
             if (p.mm_aligned8) {   // all rows 8-byte aligned: walk the staged tile linearly, three lanes per row, one STG.64 each
                 int row = lane / 3, u = lane - 3 * row;
                 for (int i = lane; i < 3 * p.n_mels; i += 32) {
@@ -1841,6 +1868,22 @@ __global__ void __launch_bounds__(256) melspec_featnorm_kernel(float* out, long 
     for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float inv = 1.0f / (sqrtf(var / fmaxf((float)frames - 1.0f, 1.0f)) + 1e-5f);
     for (int f = lane; f < frames; f += 32) r[f] = (r[f] - mean) * inv;
+}
+
+// Zero padding columns [c0, c1) of every row of a batch of row-major images (interleave_frames' zero frame / min_width padding,
+// src/mel.rs:497-516; NeMo's pad_to columns, src/mel.rs:336).  One thread per (row, column): a 2-D memset of 8-byte rows costs more
+// than the fused kernel itself.
+__global__ void __launch_bounds__(256) melspec_zero_cols_kernel(float* img, long long img_stride, int rows, long long row_stride, int c0, int c1,
+                                                                long long n_imgs) {
+    const int ncol = c1 - c0;
+    const long long total = n_imgs * rows * ncol;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long r = i / ncol;
+        const int cidx = (int)(i - r * ncol);
+        const long long im = r / rows;
+        const int row = (int)(r - im * rows);
+        img[im * img_stride + (long long)row * row_stride + c0 + cidx] = 0.f;
+    }
 }
 
 // ================================================================================================ 16-bit PCM input
