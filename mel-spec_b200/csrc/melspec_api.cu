@@ -872,6 +872,7 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     p.smem_rot = (int)off; off = up(off + 512, 128);
     p.smem_proj = (int)off; off = up(off + sizeof(float2) * 32 * (size_t)(h->proj_ktot + 1), 128);
     p.smem_meta = (int)off; off = up(off + sizeof(int) * kMetaInts, 128);
+    p.smem_mmoff = (int)off; if (h->plan == 400) off = up(off + sizeof(int) * 3 * 128, 128);
     p.smem_cmn = (int)off;
     // fused CMN: mode 1 column sums per warp + means; mode 2 two sets of column sums + kCmnRows replicated rows of -mean
     if (h->plan == 512) off = up(off + sizeof(float) * 128 * (size_t)(kaldi && c.cmn ? 2 * 12 + p512::kCmnRows : 12 + 1), 128);
@@ -924,6 +925,10 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
     {   // MELSPEC_TILE_ORDER=0|1 overrides (A/B); default: interleaved warps for the mel-major layouts of plan 400
         static const int forced = [] { const char* e = std::getenv("MELSPEC_TILE_ORDER"); return e ? std::atoi(e) : -1; }();
         p.tile_order = forced >= 0 ? forced : (h->plan == 400 && layout == MELSPEC_LAYOUT_MEL_MAJOR ? 1 : 0);
+        // measured (profiles/r2_ab_melmajor.txt): 80 rows per tile stay inside L2 without a barrier (and lose 4 - 19 % to one); 128 rows
+        // do not: DRAM 1.54 GB -> 1.20 GB per launch and 0.61 -> 0.45 ms with a barrier every 8 passes
+        static const int sync_forced = [] { const char* e = std::getenv("MELSPEC_MM_SYNC"); return e ? std::atoi(e) : -1; }();
+        p.mm_sync = sync_forced >= 0 ? sync_forced : (c.n_mels > 80 ? 8 : 0);
     }
     const int64_t n_tiles = (n_wtiles + nw - 1) / nw;
     const int grid = fused_cmn ? h->num_sms : (int)std::min<int64_t>(n_tiles, h->num_sms);
@@ -946,7 +951,10 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         static const bool k5 = [] { const char* e = std::getenv("MELSPEC_KSPEC5"); return !(e && e[0] == '0'); }();
         const bool fmm = k5 && h->kspec == 1 && c.n_mels == 80 && hop160 && nw == 12 && p.bulk_in && layout == MELSPEC_LAYOUT_MEL_MAJOR && p.mm_aligned8 &&
                          !d_lens && p.normalize && row_stride * 80 < ((int64_t)1 << 31);
+        const bool fmm128 = k5 && h->kspec == 4 && c.n_mels == 128 && hop160 && nw == 12 && p.bulk_in && layout == MELSPEC_LAYOUT_MEL_MAJOR &&
+                            p.mm_aligned8 && !d_lens && p.normalize && row_stride * 128 < ((int64_t)1 << 31);
         rc = fmm ? launch_kernel(melspec400_kernel<12, 3, true, 5>, p, grid, 12 * 32, off, st)
+             : fmm128 ? launch_kernel(melspec400_kernel<12, 4, true, 6>, p, grid, 12 * 32, off, st)
              : h->kspec == 4 && fshape && k4 ? launch_kernel(melspec400_kernel<12, 4, true, 4>, p, grid, 12 * 32, off, st)
              : fast ? launch_kernel(melspec400_kernel<12, 3, true, 3>, p, grid, 12 * 32, off, st)
              : nw == 16 ? launch_kernel(melspec400_kernel<16, 3, true, 1>, p, grid, 16 * 32, off, st) : nw == 8 ? MS_DISPATCH(8) : MS_DISPATCH(12);

@@ -73,6 +73,8 @@ struct KParams {
     int n_clips;
     int smem_cmn;            // [NWARPS][128] column sums + [128] means (floats)
     int tile_order;          // plan 400: 0 = every warp owns a contiguous range of tiles, 1 = the CTA does and its warps interleave
+    int smem_mmoff;          // plan 400, KSPEC 5 / 6: [3 * n_mels] ints, the mel-major store offsets of a staged tile
+    int mm_sync;             // plan 400, tile_order 1: CTA barrier every mm_sync passes (0: never)
     // shared-memory carve-up (bytes from the start of dynamic smem), computed on the host
     int smem_win, smem_tw, smem_rot, smem_proj, smem_meta, smem_warp0, smem_warp_stride, smem_stage_off, smem_pcm_off, smem_scr_off;
 };
@@ -533,8 +535,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     // KSPEC 4 = the same for the Slaney 128-mel bank (Whisper large-v3: 9, 4, 2 and 1 entries in its four slots)
     // KSPEC 5 = KSPEC 3 with the mel-major (`interleave_frames`, whisper.cpp) output layout instead: 8-byte aligned rows, full tiles
     // stored from a per-lane offset table (ragged tiles take the generic path below)
-    constexpr bool FAST = KSPEC >= 3, FASTMM = KSPEC == 5;
-    constexpr int KS_ = (KSPEC == 3 || KSPEC == 5) ? 1 : KSPEC;
+    // KSPEC 6 = the same for the 128-mel bank (KSPEC 4's schedule)
+    constexpr bool FAST = KSPEC >= 3, FASTMM = KSPEC == 5 || KSPEC == 6;
+    constexpr int KS_ = (KSPEC == 3 || KSPEC == 5) ? 1 : KSPEC == 6 ? 4 : KSPEC;
+    constexpr int MM_MELS = KSPEC == 6 ? 128 : 80;
     const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_bulk_out = FAST ? !FASTMM : (p.bulk_out != 0), f_norm = FAST ? true : (p.normalize != 0);
     const int f_layout = FAST ? (FASTMM ? 1 : 0) : p.layout;
     const int32_t* const f_lens = FAST ? nullptr : p.lens;
@@ -602,11 +606,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     }
     for (int i = threadIdx.x; i < 30; i += NWARPS * 32) reinterpret_cast<float4*>(smem + p.smem_rot)[i] = reinterpret_cast<const float4*>(p.rot10)[i % 10];
     const float4* s_rot = reinterpret_cast<const float4*>(smem + p.smem_rot) + l30;   // (rx.x, rx.y, ry.x, ry.y): W_40^(-c), c = 2t, 2t+1
-    // KSPEC 5: where float2 i of a staged [80 mels][3 x float2] tile goes, relative to the tile's first output column:
-    // (i / 3) * row stride + 2 (i % 3) floats; i = lane + 32 k, one table row per k (behind the window factors: 480 bytes are in use there)
-    int* const s_mmoff = reinterpret_cast<int*>(smem + p.smem_win + 512);
+    // KSPEC 5 / 6: where float2 i of a staged [mels][3 x float2] tile goes, relative to the tile's first output column:
+    // (i / 3) * row stride + 2 (i % 3) floats; i = lane + 32 k, one table row per k
+    int* const s_mmoff = reinterpret_cast<int*>(smem + p.smem_mmoff);
     if (FASTMM)
-        for (int i = threadIdx.x; i < 240; i += NWARPS * 32) s_mmoff[i] = (i / 3) * p.out_row_stride + 2 * (i % 3);
+        for (int i = threadIdx.x; i < 3 * MM_MELS; i += NWARPS * 32) s_mmoff[i] = (i / 3) * p.out_row_stride + 2 * (i % 3);
     __syncthreads();
 
     const int hop = HOP160 ? 160 : p.hop;
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     // which pushed the PCM halo out of L2 (measured: DRAM 657 -> 802 MB read, 300 -> 406 MB written per cfg2 launch).
     const bool interleaved_tiles = (FAST && !FASTMM) ? false : (p.tile_order != 0);
     const int tstep = interleaved_tiles ? NWARPS : 1;
-    int clip, tin, cnt;
+    int clip, tin, cnt, cnt_cta = 0;
     if (!interleaved_tiles) {
         const int nwt = gridDim.x * NWARPS, gw = blockIdx.x * NWARPS + warp;
         const int base = p.n_wtiles / nwt, rem = p.n_wtiles - base * nwt;
@@ -666,12 +670,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         const int base = p.n_wtiles / nct, rem = p.n_wtiles - base * nct;
         const int lo = b * base + min(b, rem) + warp, cntb = base + (b < rem ? 1 : 0);
         cnt = cntb > warp ? (cntb - warp + NWARPS - 1) / NWARPS : 0;
+        cnt_cta = (cntb + NWARPS - 1) / NWARPS;
         clip = lo / p.wtiles_per_clip;
         tin = lo - clip * p.wtiles_per_clip;
     }
     if (cnt > 0) issue_load(clip, tin);
 
-    for (int it = 0; it < cnt; ++it) {
+    for (int it = 0, since_sync = 0; it < (interleaved_tiles ? cnt_cta : cnt); ++it) {
+        // interleaved tile order: the warps of a CTA must stay near each other in the tile sequence, or the rows' partially written L2
+        // lines pile up again (left alone they drift apart by many passes); a CTA barrier every few passes bounds the drift
+        if (interleaved_tiles) {
+            if (p.mm_sync > 0 && ++since_sync == p.mm_sync) { since_sync = 0; __syncthreads(); }
+            if (it >= cnt) continue;   // (this warp's share is one tile shorter)
+        }
         const int fw0 = tin * FPW;   // first frame of this pass
         int nfr = p.frames_per_clip;
         if (f_lens) {
@@ -971,10 +982,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
             }
             __syncwarp();
             float* dst = p.out + (long long)cur_clip * p.out_clip_stride + fw0;
-            if (FASTMM) {   // 80 mels, aligned rows: 240 float2, offsets from the table (7 full rounds + 16 lanes)
+            if (FASTMM) {   // aligned rows: 3 float2 per mel, offsets from the table (80 mels: 7 full rounds + 16 lanes; 128 mels: 12 rounds)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < 7 || lane < 16) *reinterpret_cast<float2*>(dst + s_mmoff[lane + 32 * k]) = st2[lane + 32 * k];
+                for (int k = 0; k < (3 * MM_MELS + 31) / 32; ++k)
+                    if (32 * k + 32 <= 3 * MM_MELS || lane < 3 * MM_MELS - 32 * k) *reinterpret_cast<float2*>(dst + s_mmoff[lane + 32 * k]) = st2[lane + 32 * k];
             } else
             if (p.mm_aligned8) {   // all rows 8-byte aligned: walk the staged tile linearly, three lanes per row, one STG.64 each
                 int row = lane / 3, u = lane - 3 * row;

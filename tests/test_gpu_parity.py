@@ -136,6 +136,35 @@ def test_mel_major_layout(m, mel400, torch):
     assert np.array_equal(a.transpose(0, 2, 1), b)
 
 
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_mel_major_large_batch_equals_frame_major(m, torch, n_mels):
+    """The mel-major launch shapes of round 2 (CTA-contiguous tile ranges with interleaved warps, offset-table stores, compiled-in
+    80 / 128-mel schedules; a ragged last tile and a batch large enough that every warp owns several tiles): bit-identical to the
+    frame-major output transposed, which is checked against the oracle; untouched padding behind a wider row stride stays untouched."""
+    h = m.CudaMelSpectrogram(400, 160, 16000.0, n_mels)
+    clips, n = 300, 16000 * 2 + 400 + 160 * 3                     # 204 frames = 34 tiles of 6; 300 clips > 148 CTAs x 12 warps / 34
+    pcm = np.stack([o.synth_clip(i % 7, n) * (0.1 + 0.05 * (i % 5)) for i in range(clips)]).astype(np.float32)
+    f = h.num_frames(n)
+    assert f == 204
+    a = _device_run(torch, h, pcm, layout=0, n_mels=n_mels)
+    b = _device_run(torch, h, pcm, layout=1, n_mels=n_mels)
+    assert np.array_equal(a.transpose(0, 2, 1), b)
+    for i in (0, 1, 299):
+        assert np.abs(a[i] - o.whisper_mel_batch(pcm[i], 400, 160, n_mels, 16000.0)).max() <= WHISPER_TOL
+    pcm2 = np.ascontiguousarray(pcm[:, : n - 160 * 2])              # 202 frames: ragged last tile (4 of 6 frames)
+    a2 = _device_run(torch, h, pcm2, layout=0, n_mels=n_mels)
+    b2 = _device_run(torch, h, pcm2, layout=1, n_mels=n_mels)
+    assert a2.shape[1] == 202 and np.array_equal(a2.transpose(0, 2, 1), b2)
+    # interleave_frames image with padding columns (even width > frames): columns [frames, width) are zeros
+    x = torch.from_numpy(pcm2).cuda()
+    img = torch.full((clips, n_mels, 210), float("nan"), dtype=torch.float32, device="cuda")
+    h.compute_interleaved_device(x, clips, pcm2.shape[1], pcm2.shape[1], 210, img)
+    torch.cuda.synchronize()
+    got = img.cpu().numpy()
+    assert np.array_equal(got[:, :, :202], b2) and np.all(got[:, :, 202:] == 0.0)
+    h.close()
+
+
 def test_unaligned_device_pointers(m, mel400, torch):
     # odd strides / offsets force the cooperative-copy input path and the plain-store output path
     rng = np.random.default_rng(9)
