@@ -1,0 +1,14 @@
+#!/bin/bash
+cd ${GRAFT_REPO_ROOT:-.}
+O=gpurun_out/r2; mkdir -p $O
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+timeout 600 ncu --metrics $M --clock-control none -k regex:melspec512 --csv --log-file $O/nemo.csv python tools/prof_nemo.py > $O/nemo.log 2>&1
+python - <<'P'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2/nemo.csv')) if len(r)>10 and r[0].isdigit()]
+by={}
+for r in rows: by.setdefault((int(r[0]), r[4]), {})[r[12]]=r[14]
+for k in sorted(by):
+    v=by[k]; print(k[0], k[1][:44], ' '.join(f"{m.split('.')[0][-20:]}={v[m]}" for m in sorted(v)))
+P
+tail -3 $O/nemo.log
