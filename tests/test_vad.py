@@ -115,3 +115,46 @@ def test_gpu_vad_on_kernel_output_batch(mel400, jfk):
         assert [(k, bool(a[i, k, 0]), int(a[i, k, 1]), int(a[i, k, 2])) for k in range(st.min_x - 1, w)] == [t[:4] for t in want]
         assert (a[i, :st.min_x - 1] == -1).all()
     assert s[0].sum() > 100 and s[2].sum() == 0
+
+
+@pytest.mark.gpu
+def test_gpu_vad_decisions_at_the_threshold(mel400):
+    """The VAD kernel evaluates the reference's f64 expression in the reference's operation order (src/vad.rs:284-316).  Images whose
+    Sobel energies sit within a few ulp of min_energy^2 — exact ties included — must give the oracle's masks, for single-pixel
+    decisions (min_y = 1).  (Round 2 tried an fp32 evaluation with a rigorous error band and f64 only inside the band: identical masks
+    on these cases, but 0.297 instead of 0.209 ms per 1024 images — the kernel is not bound by the FP64 pipe on B200 — so it was dropped.)"""
+    import mel_spec_b200 as ms
+    rng = np.random.default_rng(17)
+    h, w = 24, 300
+    for s0 in (0.125, 0.3, 1.0 / 3.0, 7.77):
+        # a horizontal ramp whose step varies by a few ulp from column to column: gx = 4 (s_x + s_x+1) ~ 8 s0, gy ~ 0
+        steps = np.float32(s0) * (1.0 + rng.integers(-3, 4, w).astype(np.float64) * 2.0 ** -23)
+        row = np.cumsum(steps).astype(np.float32)
+        img = np.tile(row, (h, 1))
+        img[rng.integers(0, h, 40), rng.integers(0, w, 40)] += np.float32(s0 * 2.0 ** -22)      # a little vertical structure
+        for min_energy in (8.0 * s0, float(np.float32(8.0 * s0)), 8.0 * s0 * (1 + 2.0 ** -24), 8.0 * s0 * (1 - 2.0 ** -24)):
+            for min_y in (1, 3):
+                st = ms.DetectionSettings(min_energy, min_y, 4, 0)
+                ei = mel400.vad_boundaries(img, st)
+                non, inter = o.vad_boundaries(img, min_energy, min_y, 4, 0)
+                assert ei.intersected() == inter and ei.non_intersected() == non, (s0, min_energy, min_y)
+    # random images, thresholds equal to the f64 energy of actual pixels (ties) and to their neighbours in f64
+    img = rng.standard_normal((40, 200)).astype(np.float32)
+    d = img.astype(np.float64)
+    gx = (d[:-2, 2:] + 2 * d[1:-1, 2:] + d[2:, 2:]) - (d[:-2, :-2] + 2 * d[1:-1, :-2] + d[2:, :-2])
+    gy = (d[2:, :-2] + 2 * d[2:, 1:-1] + d[2:, 2:]) - (d[:-2, :-2] + 2 * d[:-2, 1:-1] + d[:-2, 2:])
+    e = gx * gx + gy * gy
+    for k in rng.integers(0, e.size, 6):
+        thr = float(np.sqrt(e.reshape(-1)[k]))
+        for me in (thr, np.nextafter(thr, 0.0), np.nextafter(thr, 1e9)):
+            st = ms.DetectionSettings(float(me), 1, 3, 0)
+            ei = mel400.vad_boundaries(img, st)
+            non, inter = o.vad_boundaries(img, float(me), 1, 3, 0)
+            assert ei.intersected() == inter and ei.non_intersected() == non
+    # non-finite pixels fall back to the f64 path (NaN energies compare false, like the reference's)
+    img[5, 7] = np.inf
+    img[9, 100] = np.nan
+    st = ms.DetectionSettings(1.0, 2, 3, 0)
+    ei = mel400.vad_boundaries(img, st)
+    non, inter = o.vad_boundaries(img, 1.0, 2, 3, 0)
+    assert ei.intersected() == inter and ei.non_intersected() == non
