@@ -859,6 +859,8 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
         const int ef = (int)((bits >> 23) & 255u);
         p.ps_down = v > 0.f ? std::min(melspec::kMaxShift, std::max(0, (ef - 1) / 2)) : 0;
         p.ps_up = v > 0.f ? std::min(melspec::kMaxShift, std::max(0, (254 - ef) / 2)) : 0;
+        static const bool no_prescale = [] { const char* e = std::getenv("MELSPEC_NO_PRESCALE"); return e && e[0] == '1'; }();   // (debugging / A-B only)
+        if (no_prescale) p.ps_down = p.ps_up = 0;
     }
     if (kaldi) { p.log_mul = c.use_log ? (float)std::log(2.0) : 0.f; p.normalize = 0; }   // ln(max(e, floor)), src/fbank.rs:207-221
     else if (nemo) { p.log_mul = (float)std::log(2.0); p.normalize = 0; }                 // ln(e + guard), src/mel.rs:365-368
@@ -990,7 +992,10 @@ int32_t launch_device(melspec_handle* h, const float* d_pcm, int64_t n_clips, in
             else rc = fast && p.bulk_out ? MS_DISPATCH_FAST(1) : nw == 8 ? MS_DISPATCH(8, 1) : MS_DISPATCH(12, 1);
         } else {
             const bool f0 = fast && p.bulk_out && layout == MELSPEC_LAYOUT_FRAME_MAJOR;
-            if (f0 && ks == 1) rc = launch_kernel(melspec512_kernel<12, 3, 0, true, 1>, p, grid, 12 * 32, off, st);
+            // Whisper-512 into the interleave_frames / whisper.cpp layout: the same compiled-in shape with the mel-major store
+            const bool fmm = nw == 12 && p.bulk_in && !d_lens && ks == 1 && layout == MELSPEC_LAYOUT_MEL_MAJOR && p.normalize;
+            if (fmm) rc = launch_kernel(melspec512_kernel<12, 3, 0, true, 1, true>, p, grid, 12 * 32, off, st);
+            else if (f0 && ks == 1) rc = launch_kernel(melspec512_kernel<12, 3, 0, true, 1>, p, grid, 12 * 32, off, st);
             else if (f0 && ks == 4) rc = launch_kernel(melspec512_kernel<12, 4, 0, true, 4>, p, grid, 12 * 32, off, st);
             else rc = f0 ? MS_DISPATCH_FAST(0) : nw == 8 ? MS_DISPATCH(8, 0) : MS_DISPATCH(12, 0);
         }

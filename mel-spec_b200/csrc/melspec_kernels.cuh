@@ -233,6 +233,21 @@ __device__ __forceinline__ void bulk_s2g_commit_if(bool pred, void* dst, uint32_
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// The PCM stage of a warp is single-buffered: a pass issues the shared-memory loads of all of its samples and then the TMA refill
+// for the warp's next tile.  The refill does not depend on the loaded registers, so nothing in the instruction stream makes it
+// wait for loads that are still queued in the LSU - and when that queue is backed up (mel-major output: hundreds of scattered
+// global stores per tile and warp) the bulk copy, one L2 round trip later, overwrote samples the last loads had not read yet
+// (seen as one frame of a pair computed from the next tile's samples in about 1 launch in 100 of a ragged 128-mel mel-major
+// batch; racecheck does not see the async proxy).  The loads (generic proxy) and the bulk copy (async proxy) are ordered the
+// way PTX prescribes: every lane's loads -> __syncwarp() -> fence.proxy.async -> cp.async.bulk.  Measured (profiles/
+// r2_refill_guard.md): 0 differing launches in 600 with the fence (5 in 600 without), +0.7 % on the plan-400 kernel.
+#ifndef MS_REFILL_GUARD
+#define MS_REFILL_GUARD 1   // A/B switch: 0 = no ordering (the round-1 behaviour, racy)
+#endif
+__device__ __forceinline__ void order_loads_before_refill() {
+    if (MS_REFILL_GUARD) fence_proxy_async();
+}
+
 // log2 of a normal, positive number: the energies are floored (>= 1e-10 / FLT_EPSILON / log_zero_guard) before the
 // logarithm, so the denormal fix-up that __log2f() carries (FSETP + 2 predicated FMUL/FADD per call) is dead weight
 __device__ __forceinline__ float lg2_normal(float x) {
@@ -621,6 +636,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
 
     // Stage the PCM of warp tile `wt` into this warp's buffer (TMA bulk copies issued by one lane).
     auto issue_load = [&](int clip, int tin) {
+        order_loads_before_refill();   // (callers: __syncwarp() after the pass's last sample loads)
         const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * hop;
         const long long left = (long long)p.n_samples - s0;
@@ -723,8 +739,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 win_first_layer(ld(pb, n0, vb), ld(pb, n1, vb), ld(pb, n2, vb), ld(pb, n3, vb), w0, w1, w2, w3, QI[b]);
             }
         }
-        __syncwarp();   // every lane has read its samples (HOP160: the loads are ordered before the refill below; their values are
-                        // consumed after it, which keeps only the 56 sample registers live across the TMA issue)
+        __syncwarp();   // every lane has issued its sample loads (HOP160: their values are consumed after the refill below, which keeps
+                        // only the 56 sample registers live across the TMA issue); issue_load() orders them before the bulk copy
         const int cur_clip = clip;
         tin += tstep;
         while (tin >= p.wtiles_per_clip) { tin -= p.wtiles_per_clip; ++clip; }   // (warp-uniform)
@@ -1128,13 +1144,14 @@ __host__ __device__ constexpr int ksched512(int k, int s) {
     constexpr int T[5][4] = {{0, 0, 0, 0}, {18, 5, 2, 0}, {16, 6, 2, 0}, {19, 5, 2, 0}, {12, 6, 3, 2}};
     return T[k][s];
 }
-template <int NWARPS, int MPL, int MODE, bool FAST = false, int KSCHED = 0>
+// MM (with FAST, MODE 0): the mel-major / interleave_frames layout compiled in instead of the frame-major one.
+template <int NWARPS, int MPL, int MODE, bool FAST = false, int KSCHED = 0, bool MM = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParams p) {
     using namespace p512;
     extern __shared__ __align__(128) unsigned char smem[];
     const bool f_bulk_in = FAST ? true : (p.bulk_in != 0), f_norm = FAST ? (MODE == 0) : (p.normalize != 0);
-    const int f_layout = FAST ? (MODE >= 2 ? 1 : 0) : p.layout;
-    const bool f_bulk_out = FAST ? (MODE < 2) : (p.bulk_out != 0);
+    const int f_layout = FAST ? ((MODE >= 2 || MM) ? 1 : 0) : p.layout;
+    const bool f_bulk_out = FAST ? (MODE < 2 && !MM) : (p.bulk_out != 0);
     const int32_t* const f_lens = FAST ? nullptr : p.lens;
     constexpr bool KALDI = MODE == 1, NEMO = MODE == 2 || MODE == 3, RAGGED = MODE == 3, FRAME400 = MODE != 0;
     constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
@@ -1212,6 +1229,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     // count (src/mel.rs:387-395); samples past its length read as zeros, columns past its frame count are written as zeros
     auto clip_len = [&](int clip) -> int { return RAGGED ? max(0, min(p.lens[clip], p.n_samples)) : p.n_samples; };   // (RAGGED is never FAST)
     auto issue_load = [&](int clip, int tin) {
+        order_loads_before_refill();   // (callers: __syncwarp() after the pass's last sample loads)
         const int fw0 = tin * FPW;
         const long long s0 = (long long)fw0 * 160;
         const long long left = (long long)p.n_samples - s0;
