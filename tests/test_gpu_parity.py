@@ -165,6 +165,28 @@ def test_mel_major_large_batch_equals_frame_major(m, torch, n_mels):
     h.close()
 
 
+@pytest.mark.parametrize("n_mels,layout", [(128, 1), (80, 1), (80, 0)])
+def test_repeated_launches_are_identical(m, torch, n_mels, layout):
+    """Regression test of the single-buffered PCM stage (profiles/r2_refill_guard.md): before the proxy fence between a pass's sample
+    loads and the TMA refill of the same buffer, about 1 launch in 100 of this ragged mel-major batch computed one frame from the
+    next tile's samples.  300 launches of the same input, each compared with the first on the device, bit for bit."""
+    h = m.CudaMelSpectrogram(400, 160, 16000.0, n_mels)
+    clips, n = 300, 400 + 160 * 201                                   # 202 frames: 33 full tiles + a ragged one
+    pcm = np.stack([o.synth_clip(i % 7, n) * (0.1 + 0.05 * (i % 5)) for i in range(clips)]).astype(np.float32)
+    x = torch.from_numpy(pcm).cuda()
+    shape = (clips, 202, n_mels) if layout == 0 else (clips, n_mels, 202)
+    ref = torch.empty(shape, dtype=torch.float32, device="cuda")
+    h.compute_device(x, clips, n, n, ref, layout=layout)
+    torch.cuda.synchronize()
+    differing = 0
+    for _ in range(300):
+        out = torch.full(shape, float("nan"), dtype=torch.float32, device="cuda")
+        h.compute_device(x, clips, n, n, out, layout=layout)
+        differing += int(bool((out != ref).any()))
+    assert differing == 0
+    h.close()
+
+
 def test_unaligned_device_pointers(m, mel400, torch):
     # odd strides / offsets force the cooperative-copy input path and the plain-store output path
     rng = np.random.default_rng(9)
