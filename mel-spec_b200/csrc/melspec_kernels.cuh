@@ -106,6 +106,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Non-blocking phase test (1 = the phase with this parity has completed).  The tile loops issue it late in a pass for the NEXT
+// pass's PCM, so the shared-memory round trip of the mbarrier instruction (queued behind the pass's loads and stores on a pipe
+// that is 80 % busy) is not on the critical path at the top of the next pass; mbar_wait() remains the fallback.
+#ifndef MS_EARLY_TEST
+#define MS_EARLY_TEST 1
+#endif
+#ifndef MS_TMA_LEAD
+#define MS_TMA_LEAD 1
+#endif
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 // TMA 1-D bulk copy global -> shared, completion reported as bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -186,7 +206,8 @@ __device__ __forceinline__ void tma_load_chunks4(uint32_t bar, uint32_t total, u
 }
 // the same with an L2 eviction policy on the copies (plan 512)
 __device__ __forceinline__ void tma_load_chunks4_hint(uint32_t bar, uint32_t total, uint32_t dst0, uint32_t dst_stride, const void* src,
-                                                      uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t src_stride, uint64_t pol) {
+                                                      uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t src_stride, uint64_t pol,
+                                                      uint32_t lead16 = 0) {   // lead16 != 0: also the 16 bytes in front of src / dst0 (counted in total)
     asm volatile(
         "{\n\t"
         ".reg .pred p, q;\n\t"
@@ -194,6 +215,10 @@ __device__ __forceinline__ void tma_load_chunks4_hint(uint32_t bar, uint32_t tot
         ".reg .b64 s, st;\n\t"
         "elect.sync _|p, 0xffffffff;\n\t"
         "@p mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t"
+        "setp.ne.and.u32 q, %11, 0, p;\n\t"
+        "sub.u32 d, %2, 16;\n\t"
+        "sub.u64 s, %4, 16;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [d], [s], 16, [%0], %10;\n\t"
         "setp.ne.and.u32 q, %5, 0, p;\n\t"
         "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%2], [%4], %5, [%0], %10;\n\t"
         "add.u32 d, %2, %3;\n\t"
@@ -209,7 +234,8 @@ __device__ __forceinline__ void tma_load_chunks4_hint(uint32_t bar, uint32_t tot
         "setp.ne.and.u32 q, %8, 0, p;\n\t"
         "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [d], [s], %8, [%0], %10;\n\t"
         "}" ::"r"(bar),
-        "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride), "l"(pol)
+        "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride), "l"(pol),
+        "r"(lead16)
         : "memory");
 }
 __device__ __forceinline__ void bulk_s2g_hint_commit_if(bool pred, void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
@@ -692,6 +718,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
     }
     if (cnt > 0) issue_load(clip, tin);
 
+    uint32_t pcm_ready = 0;   // (warp-uniform) result of the early phase test of the previous pass
     for (int it = 0, since_sync = 0; it < (interleaved_tiles ? cnt_cta : cnt); ++it) {
         // interleaved tile order: the warps of a CTA must stay near each other in the tile sequence, or the rows' partially written L2
         // lines pile up again (left alone they drift apart by many passes); a CTA barrier every few passes bounds the drift
@@ -707,7 +734,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         }
         const int nvalid = max(0, min(FPW, nfr - fw0));          // warp-uniform
 
-        mbar_wait(bar, it & 1);
+        if (!pcm_ready) mbar_wait(bar, it & 1);
+        pcm_ready = 0;
 
         // ------------------------------------------------------------------ step 1: window + column DFTs
         // The two column transforms of a worker (columns 2t, 2t+1) advance together in packed FADD2/FMUL2/FFMA2 instructions;
@@ -938,6 +966,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
                 }
             }
         }
+        if (MS_EARLY_TEST && it + 1 < cnt) pcm_ready = mbar_test(bar, (it + 1) & 1);   // (the refill went out at the top of this pass)
         if (f_norm) {
 #pragma unroll
             for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
@@ -1154,6 +1183,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
     const bool f_bulk_out = FAST ? (MODE < 2 && !MM) : (p.bulk_out != 0);
     const int32_t* const f_lens = FAST ? nullptr : p.lens;
     constexpr bool KALDI = MODE == 1, NEMO = MODE == 2 || MODE == 3, RAGGED = MODE == 3, FRAME400 = MODE != 0;
+    // Where the pre-emphasis look-back sample comes from (see the tile loop).  Kaldi only: the NeMo modes measured 0.3 % (80 mel) to 12 %
+    // (128 mel) slower with it (profiles/r2_early_test_tma_lead.md)
+    constexpr bool TMA_LEAD = MS_TMA_LEAD && FAST && KALDI;
     constexpr int NLOAD = FRAME400 ? 35 : 42;  // rows of 16 samples covering frames A and B (B = A shifted by 10 rows)
     constexpr int NROW = FRAME400 ? 25 : 32;   // non-zero rows of a frame (400 samples zero-padded to 512)
 
@@ -1269,7 +1301,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
         } else if (FAST) {   // the whole warp is converged here: one elected lane, one predicated sequence
             const int a0 = min(CHUNK, avail), a1 = max(0, min(CHUNK, avail - CHUNK)), a2 = max(0, min(CHUNK, avail - 2 * CHUNK)),
                       a3 = max(0, min(CHUNK, avail - 3 * CHUNK));
-            tma_load_chunks4_hint(bar, (uint32_t)avail * 4u, smem_u32(s_pcm), CS * 4u, src, a0 * 4u, a1 * 4u, a2 * 4u, a3 * 4u, CHUNK * 4u, pol_in);
+            const uint32_t lead16 = TMA_LEAD && s0 > 0 ? 16u : 0u;   // the pre-emphasis look-back sample rides in front of the tile
+            tma_load_chunks4_hint(bar, (uint32_t)avail * 4u + lead16, smem_u32(s_pcm), CS * 4u, src, a0 * 4u, a1 * 4u, a2 * 4u, a3 * 4u, CHUNK * 4u, pol_in, lead16);
         } else if (f_bulk_in) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)avail * 4u);
@@ -1313,6 +1346,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
 #pragma unroll
     for (int s = 0; s < MPL; ++s) csum[s] = 0.f;
     if (wt < p.n_wtiles) issue_load(clip_f, tile_in_clip);
+    uint32_t pcm_ready = 0;   // (warp-uniform) result of the early phase test of the previous pass
 
     for (int it = 0; wt < p.n_wtiles; ++it) {
         const int clip = clip_f;
@@ -1327,13 +1361,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
             nfr = min(nfr, len_c <= 0 ? 0 : p.frame_offset < 0 ? len_c / 160 + 1 : (len_c < N ? 0 : (len_c - N) / 160 + 1));
         const int nvalid = max(0, min(FPW, nfr - fw0));
 
-        // pre-emphasis look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it)
+        // pre-emphasis look-back: the sample just before the tile (only the lane that owns tile sample 0 needs it).  TMA_LEAD: it
+        // arrives with the tile (issue_load puts it into the word in front of the stage); otherwise a global load, whose latency the
+        // whole warp waits out at the first use of its register (2 % of the Kaldi kernel's stall samples)
         float lead = 0.f;
-        const bool owns_first = FRAME400 && g1 == 0 && c == 0;
+        const bool owns_first = FRAME400 && g1 == 0 && c == 0;   // (lane 0)
         const long long tile0 = (long long)fw0 * 160 + (NEMO ? p.frame_offset : 0);   // clip index of tile sample 0
-        if (owns_first && tile0 > 0 && tile0 - 1 < len_c) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + tile0 - 1);
+        if (!TMA_LEAD && owns_first && tile0 > 0 && tile0 - 1 < len_c) lead = __ldg(p.pcm + (long long)clip * p.clip_stride + tile0 - 1);
 
-        mbar_wait(bar, it & 1);
+        if (!pcm_ready) mbar_wait(bar, it & 1);
+        pcm_ready = 0;
+        if (TMA_LEAD && owns_first && tile0 > 0) lead = s_pcm[-1];
 
         // ------------------------------------------------------------------ step 1
         // column c: re = frame A (fw0 + 2g), im = frame B (fw0 + 2g + 1); er[a] = (re[2a], re[2a+1]) feeds the packed codelet
@@ -1570,6 +1608,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec512_kernel(const KParam
                 }
             }
         }
+        if (MS_EARLY_TEST && wt_next < p.n_wtiles) pcm_ready = mbar_test(bar, (it + 1) & 1);   // (the refill went out at the top of this pass)
         if (f_norm) {
 #pragma unroll
             for (int q = 0; q < FPW; ++q) mx[q] = warp_max_f32(mx[q]) - 8.0f;
