@@ -1735,7 +1735,6 @@ int32_t mel_tga_batch_impl(melspec_handle* h, const void* h_pcm, bool i16, int64
     per_chunk = std::min(per_chunk, n_clips);
     if (n_clips >= 3) per_chunk = std::min(per_chunk, (n_clips + 2) / 3);
     per_chunk = std::min<int64_t>(per_chunk, 65535);
-    const int64_t n_chunks = (n_clips + per_chunk - 1) / per_chunk;
     int32_t rc = ensure_host_resources(h, (size_t)per_chunk * ns4 * 4, (size_t)per_chunk * img * 4, i16 ? (size_t)per_chunk * ns4 * 2 : 0);
     if (rc) return rc;
     const size_t tga_need = (size_t)per_chunk * dsz, part_need = sizeof(float2) * (size_t)quantize_partials_per_image(img) * (size_t)per_chunk;
