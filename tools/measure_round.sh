@@ -16,6 +16,8 @@ timeout 300 python tools/bench_generic.py > $O/bench_generic.txt 2>> $O/bench.er
 MELSPEC_GENERIC_PAIR=0 timeout 300 python tools/bench_generic.py >> $O/bench_generic.txt 2>> $O/bench.err
 # worst-case parity of the two-frames-per-transform packing: the new tests against this build and against the round-1 build
 timeout 300 python -m pytest tests/test_onset_parity.py -m gpu -q -s 2>&1 | grep -E "worst|passed|failed" > $O/onset_parity.txt
+# (the round-1 library lacks the ABI-2 entry points the Python loader now binds, so this block only runs against an old checkout's
+# build placed there by hand; profiles/r2_ab_r1_vs_r2_cfg2.txt and the lower half of r2_onset_parity.txt are from when it still loaded)
 if [ -f mel-spec_b200/lib/libmelspec_r1.so ]; then
   echo "--- the same tests against the round-1 library (before the pair prescale)" >> $O/onset_parity.txt
   MELSPEC_B200_LIB=$PWD/mel-spec_b200/lib/libmelspec_r1.so timeout 300 python -m pytest tests/test_onset_parity.py -m gpu -q 2>&1 | grep -E "^E   +Assertion|^FAILED|passed|failed" >> $O/onset_parity.txt
