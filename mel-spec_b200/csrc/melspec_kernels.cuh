@@ -109,6 +109,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Non-blocking phase test (1 = the phase with this parity has completed).  The tile loops issue it late in a pass for the NEXT
 // pass's PCM, so the shared-memory round trip of the mbarrier instruction (queued behind the pass's loads and stores on a pipe
 // that is 80 % busy) is not on the critical path at the top of the next pass; mbar_wait() remains the fallback.
+#ifndef MS_REFILL_FULL
+#define MS_REFILL_FULL 1
+#endif
 #ifndef MS_EARLY_TEST
 #define MS_EARLY_TEST 1
 #endif
@@ -202,6 +205,25 @@ __device__ __forceinline__ void tma_load_chunks4(uint32_t bar, uint32_t total, u
         "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [s], %8, [%0];\n\t"
         "}" ::"r"(bar),
         "r"(total), "r"(dst0), "r"(dst_stride), "l"(src), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"((unsigned long long)src_stride)
+        : "memory");
+}
+// Interior tile of plan 400 (every tile but a clip's last): the four chunk sizes are compile-time constants, so the byte counts are
+// immediates and nothing is tested (the general form spends ~40 uniform-pipe instructions per pass on min / max / select chains).
+template <uint32_t B012, uint32_t B3, uint32_t DST_STRIDE>
+__device__ __forceinline__ void tma_load_chunks4_full(uint32_t bar, uint32_t dst0, const void* src) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 st;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %3;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %4, [%0];\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1+%6], [%2+%4], %4, [%0];\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1+%7], [%2+%8], %4, [%0];\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1+%9], [%2+%10], %5, [%0];\n\t"
+        "}" ::"r"(bar),
+        "r"(dst0), "l"(src), "n"(3 * B012 + B3), "n"(B012), "n"(B3), "n"(DST_STRIDE), "n"(2 * DST_STRIDE), "n"(2 * B012), "n"(3 * DST_STRIDE),
+        "n"(3 * B012)
         : "memory");
 }
 // the same with an L2 eviction policy on the copies (plan 512)
@@ -668,7 +690,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) melspec400_kernel(const KParam
         const long long left = (long long)p.n_samples - s0;
         const int avail = left < need ? (int)left : need;
         const float* src = p.pcm + (long long)clip * p.clip_stride + s0;
-        if (FAST) {   // (HOP160, aligned: the whole warp is converged here)
+        if (FAST && MS_REFILL_FULL && left >= need) {   // (warp-uniform) interior tile: constant chunk sizes
+            constexpr uint32_t NEED = (FPW - 1) * 160 + 400;   // (FAST implies HOP160, fft 400)
+            tma_load_chunks4_full<CHUNK * 4u, (NEED - 3 * CHUNK) * 4u, CS320 * 4u>(bar, smem_u32(s_pcm), src);
+        } else if (FAST) {   // (HOP160, aligned: the whole warp is converged here)
             const int a0 = min(CHUNK, avail), a1 = max(0, min(CHUNK, avail - CHUNK)), a2 = max(0, min(CHUNK, avail - 2 * CHUNK)),
                       a3 = max(0, min(CHUNK, avail - 3 * CHUNK));
             tma_load_chunks4(bar, (uint32_t)avail * 4u, smem_u32(s_pcm), CS320 * 4u, src, a0 * 4u, a1 * 4u, a2 * 4u, a3 * 4u, CHUNK * 4u);
