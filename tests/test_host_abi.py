@@ -108,3 +108,20 @@ def test_general_sizes_host_logic(m):
         for n in (0, 1, 767, 768, 50000):
             want = 0 if n == 0 else o.batch_num_frames(n, 768, 123, center)
             assert L.melspec_num_frames_cfg(C.byref(c2), n) == want
+
+
+def test_environment_switches_are_documented():
+    """Every MELSPEC_* variable the library reads (std::getenv in csrc/) has a row in INTEGRATION.md's table, and the table
+    names no variable the sources do not read (MELSPEC_B200_LIB belongs to the Python loader)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    csrc = os.path.join(root, "mel-spec_b200", "csrc")
+    for name in os.listdir(csrc):
+        read |= set(re.findall(r'getenv\("(MELSPEC_[A-Z0-9_]+)"\)', open(os.path.join(csrc, name)).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    table = doc[doc.index("## Environment switches of the library"):]
+    named = set()
+    for cell in re.findall(r"^\| (.+?) \|", table, flags=re.M):
+        named |= set(re.findall(r"`(MELSPEC_[A-Z0-9_]+)(?:=\d)?`", cell))
+    named.discard("MELSPEC_B200_LIB")
+    assert read and read == named, (sorted(read - named), sorted(named - read))
