@@ -1179,6 +1179,9 @@ constexpr int PAD = 16;
 constexpr int CS = CHUNK + PAD;
 constexpr int NCHUNK = 4;                    // 3*160 + 512 = 992 samples
 __host__ __device__ constexpr int slot_of_row(int r) { return r <= 16 ? r : 48 - r; }
+// TMA_LEAD (Kaldi look-back sample): the 16 bytes in front of a warp's PCM stage must be free.  The stage starts at the next multiple
+// of 128 after the slab and the prescale scratch (launch_device: smem_pcm_off), which leaves this much unused in front of it:
+static_assert((ZBYTES + SCRBYTES + 127) / 128 * 128 - (ZBYTES + SCRBYTES) >= 16, "no room for the look-back sample in front of the PCM stage");
 }  // namespace p512
 
 // MODE 0: Whisper fft 512.  MODE 1: Kaldi fbank.  MODE 2: NeMo BatchLogMel (whole-waveform pre-emphasis, frames may
